@@ -1,0 +1,156 @@
+/* mafb200.h — C ABI of libmafb200.so: the B200 (sm_100a) forward/detect hot path of MAF-YOLO.
+ *
+ * Every entry point replaces one group of PyTorch library calls on the reference's
+ * inference path (citations are into the reference tree, yang-0201/MAF-YOLO):
+ *
+ *   mafb200_stem_conv3x3s2   RepVGGBlock layer 0 in deploy form           yolov6/layers/common.py:206,214-217
+ *   mafb200_conv3x3s2        RepVGGBlock / ConvWrapper 3x3 stride 2        common.py:76-83,166-283,776-792
+ *   mafb200_conv1x1          Conv(k=1) incl. the Concat that feeds it      common.py:29-50,148-154,938-946
+ *   mafb200_dwconv           UniRepLKNetBlock / DilatedReparamBlock deploy common.py:2948-3100
+ *   mafb200_maxpool2x2       MP inside MPRep                               common.py:667-673,787-792
+ *   mafb200_sppf_pool        SPPF's three chained 5x5 max-pools            common.py:114-129
+ *   mafb200_upsample2x       nn.Upsample(None, 2, 'nearest')               configs/yaml/MAF-YOLO-n.yaml:21,26
+ *   mafb200_head_decode      Head_DepthUni sigmoid + Detect_yaml eval      common.py:1332, yolov6/models/yolo.py:355-396,
+ *                            branch + generate_anchors + dist2bbox         yolov6/assigners/anchor_generator.py:11-25,
+ *                                                                          yolov6/utils/general.py:29-40
+ *   mafb200_nms              non_max_suppression + torchvision.ops.nms     yolov6/utils/nms.py:31-105
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *   - all buffers are caller-owned DEVICE memory (except where "host" is stated);
+ *     the library allocates nothing and never synchronises: work is enqueued on
+ *     `stream` (a cudaStream_t passed as void*), so every call is CUDA-graph capturable.
+ *   - return value: 0 on success, negative MAF_E_* code on error; the text of the last
+ *     error of the calling thread is available from mafb200_last_error().  Nothing throws.
+ *   - there is NO CPU fallback: on a machine without an sm_100 GPU every compute entry
+ *     point returns MAF_E_ARCH.
+ *   - activations are NHWC ("channels last") fp16: pixel (n,y,x) of a `maf_tensor` starts at
+ *     ptr + ((n*h + y)*w + x) * c_stride elements and holds `c` valid channels.  c_stride >= c
+ *     lets a tensor be a channel slice of a wider buffer — this is how Concat / split of the
+ *     reference (common.py:148-154,940,944) cost no memory traffic.  For fp16, ptr must be
+ *     16-byte aligned and c_stride a multiple of 8.
+ */
+#ifndef MAFB200_H_
+#define MAFB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAFB200_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define MAFB200_API __attribute__((visibility("default")))
+#else
+#define MAFB200_API
+#endif
+
+/* error codes */
+#define MAF_OK 0
+#define MAF_E_ARG (-1)     /* bad shape / null pointer / unsupported parameter */
+#define MAF_E_ALIGN (-2)   /* pointer or stride alignment violated */
+#define MAF_E_ARCH (-3)    /* no sm_100 device / driver entry point missing */
+#define MAF_E_CUDA (-4)    /* a CUDA runtime/driver call failed (see mafb200_last_error) */
+#define MAF_E_WORKSPACE (-5) /* workspace too small */
+
+/* dtypes */
+#define MAF_F16 0
+#define MAF_F32 1
+#define MAF_U8 2
+
+/* activations fused into the conv epilogues */
+#define MAF_ACT_NONE 0
+#define MAF_ACT_SILU 1    /* x * sigmoid(x)  — Conv, common.py:29-50 */
+#define MAF_ACT_RELU 2    /* RepVGGBlock, common.py:198 */
+#define MAF_ACT_SIGMOID 3 /* Head_DepthUni cls branch, common.py:1332 */
+
+#define MAF_MAX_SRC 4 /* a MAFPN fusion stage concatenates at most 4 maps (MAF-YOLO-n.yaml:36) */
+
+typedef struct maf_tensor {
+  void* ptr;        /* device pointer to channel 0 of pixel (0,0,0) of this view */
+  int32_t n, h, w;  /* batch, height, width */
+  int32_t c;        /* valid channels of this view */
+  int32_t c_stride; /* elements between consecutive pixels */
+  int32_t dtype;    /* MAF_F16 for activations */
+} maf_tensor;
+
+MAFB200_API int32_t mafb200_version(void);
+MAFB200_API const char* mafb200_last_error(void);
+/* 0 if device `device` (or the current one if < 0) can run the kernels (compute capability 10.x). */
+MAFB200_API int32_t mafb200_device_ok(int32_t device);
+
+/* ---- packed-weight geometry (pure host arithmetic; usable without a GPU) -------------------
+ * A conv with `cout` output channels is computed as ceil-split N tiles of `tile_n` columns
+ * (tile_n % 16 == 0, tile_n <= 256).  Packed weights are fp16 [n_tiles*tile_n][k_packed],
+ * row = output channel (zero rows beyond cout), columns = for each source s (1x1) or each tap
+ * (ky,kx) row-major (3x3) a zero-padded block of round_up(C, 64) input channels.
+ * Bias is fp32 [n_tiles*tile_n], zero padded. */
+MAFB200_API int32_t mafb200_gemm_tiling(int32_t cout, int32_t* n_tiles, int32_t* tile_n);
+MAFB200_API int32_t mafb200_packed_k_1x1(const int32_t* src_channels, int32_t n_src);
+MAFB200_API int32_t mafb200_packed_k_3x3(int32_t cin);
+
+/* ---- convolutions on tcgen05 tensor cores --------------------------------------------------
+ * dst[m, :] = act( sum_s srcs[s][m, :] @ W_s^T + bias ),  m over all n*h*w pixels.
+ * All sources and dst share n,h,w.  If dst_up2x != NULL the result is additionally written
+ * nearest-upsampled x2 (nn.Upsample fused into the producer) to that [n,2h,2w,c] tensor. */
+MAFB200_API int32_t mafb200_conv1x1(const maf_tensor* srcs, int32_t n_src, const void* w_packed, const float* bias,
+                        int32_t act, const maf_tensor* dst, const maf_tensor* dst_up2x, void* stream);
+
+/* 3x3, stride 2, padding 1 implicit GEMM (im2col folded into the TMA descriptor).
+ * src [n,h,w,cin] -> dst [n,h/2,w/2,cout]; h and w even. */
+MAFB200_API int32_t mafb200_conv3x3s2(const maf_tensor* src, const void* w_packed, const float* bias, int32_t act,
+                          const maf_tensor* dst, void* stream);
+
+/* First layer: reads the reference's input tensor directly — NCHW, `x_dtype` in {MAF_F32, MAF_F16
+ * (values in [0,1], evaler.py:161-163), MAF_U8 (raw pixels; the /255 is folded in)} — 3 input
+ * channels, 3x3 stride 2 pad 1.  w: fp32 [cout][3][3][3] (co, ky, kx, ci); bias fp32 [cout]. */
+MAFB200_API int32_t mafb200_stem_conv3x3s2(const void* x_nchw, int32_t x_dtype, int32_t n, int32_t h, int32_t w,
+                               const float* weight, const float* bias, int32_t act, const maf_tensor* dst,
+                               void* stream);
+
+/* ---- depth-wise k x k (k in 3,5,7,9), stride 1, padding k/2 -----------------------------------
+ * weight fp32 [k][k][c] (tap-major, channel fastest); bias fp32 [c]. */
+MAFB200_API int32_t mafb200_dwconv(const maf_tensor* src, const float* weight, const float* bias, int32_t k, int32_t act,
+                       const maf_tensor* dst, void* stream);
+
+/* ---- pooling / resampling ------------------------------------------------------------------- */
+MAFB200_API int32_t mafb200_maxpool2x2(const maf_tensor* src, const maf_tensor* dst, void* stream);
+/* y1 = maxpool5(x), y2 = maxpool5(y1), y3 = maxpool5(y2) (stride 1, pad 2, -inf padding). */
+MAFB200_API int32_t mafb200_sppf_pool(const maf_tensor* src, const maf_tensor* y1, const maf_tensor* y2,
+                          const maf_tensor* y3, void* stream);
+MAFB200_API int32_t mafb200_upsample2x(const maf_tensor* src, const maf_tensor* dst, void* stream);
+
+/* layout converters used by the block-level nn.Module drop-ins (reference tensors are NCHW fp32) */
+MAFB200_API int32_t mafb200_nchw_to_nhwc_f16(const void* src, int32_t src_dtype, const maf_tensor* dst, void* stream);
+MAFB200_API int32_t mafb200_nhwc_f16_to_nchw(const maf_tensor* src, void* dst, int32_t dst_dtype, void* stream);
+
+/* ---- detect head decode ----------------------------------------------------------------------
+ * For each of `n_levels` pyramid levels: cls_logits[l] [n,h_l,w_l,nc] (raw cls_pred output, the
+ * sigmoid of common.py:1332 is applied here) and reg[l] [n,h_l,w_l,4*(reg_max+1)] (raw reg_pred
+ * output, side-major: ch = side*(reg_max+1)+bin, yolo.py:377).  Writes pred fp32
+ * [n, sum(h_l*w_l), 5+nc] = (cx, cy, w, h in input pixels, 1.0, class probabilities). */
+MAFB200_API int32_t mafb200_head_decode(const maf_tensor* cls_logits, const maf_tensor* reg, const float* strides,
+                            int32_t n_levels, int32_t reg_max, float* pred, void* stream);
+
+/* ---- batched NMS ------------------------------------------------------------------------------
+ * Same result as yolov6/utils/nms.py:31-105 on the same `pred` ([B, A, 5+nc] fp32), without its
+ * 10 s wall-clock bail-out.  `class_filter`: optional device array of nc bytes (non-zero = keep
+ * class; NULL = all classes; = the `classes` argument).  Outputs: det fp32 [B, max_det, 6]
+ * (x1,y1,x2,y2,score,class; rows >= count are zero) and count int32 [B].  `conf_thres` is compared
+ * in fp32 and `iou_thres` in fp64 exactly as torch / torchvision do on CPU. */
+MAFB200_API size_t mafb200_nms_workspace_bytes(int32_t batch, int32_t anchors, int32_t nc);
+MAFB200_API int32_t mafb200_nms(const float* pred, int32_t batch, int32_t anchors, int32_t nc, double conf_thres,
+                    double iou_thres, int32_t multi_label, int32_t agnostic, const uint8_t* class_filter,
+                    int32_t max_det, int32_t max_nms, float* det, int32_t* count, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
+/* number of kernel launches issued by this library in the calling process (bench.py gpu_launches) */
+MAFB200_API int64_t mafb200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAFB200_H_ */

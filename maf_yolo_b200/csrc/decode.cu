@@ -1,0 +1,144 @@
+// K7 — detect-head decode: class sigmoid + DFL integral + anchor/grid-offset decode in ONE kernel.
+//
+// Restates, per pyramid level, the eval branch of Detect_yaml.forward
+// (yolov6/models/yolo.py:355-396): softmax over the reg_max+1 bins of each box side, expectation
+// with proj = 0..reg_max (yolo.py:328-330,377-378), anchor points (x+0.5, y+0.5) in grid units
+// (yolov6/assigners/anchor_generator.py:11-25), dist2bbox 'xywh' (yolov6/utils/general.py:29-40),
+// times the level stride (yolo.py:389), objectness column = 1 (yolo.py:393), plus the class
+// sigmoid of Head_DepthUni.forward (yolov6/layers/common.py:1332).
+//
+// A CTA handles 64 consecutive anchors of one (image, level): 4 lanes per anchor integrate the
+// four sides (17 fp16 logits each, fp32 math) and exchange l/t/r/b with warp shuffles; then the
+// whole CTA streams the 64 x (5+nc) fp32 output rows — contiguous in `pred` — with coalesced
+// stores, applying the sigmoid to the class logits on the way.
+#include <math.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "host.h"
+
+namespace mafb200 {
+
+constexpr int kMaxLevels = 8;
+constexpr int kAnchorsPerCta = 64;
+
+struct DecodeParams {
+  const __half* cls[kMaxLevels];
+  const __half* reg[kMaxLevels];
+  int32_t cls_ld[kMaxLevels], reg_ld[kMaxLevels];
+  int32_t h[kMaxLevels], w[kMaxLevels];
+  int32_t anchor_off[kMaxLevels];  // first anchor index of the level in the concatenated list
+  int32_t cta_off[kMaxLevels + 1]; // first CTA (per image) of the level
+  float stride[kMaxLevels];
+  int32_t n_levels, nc, bins, total_anchors;
+  float* pred;
+};
+
+__global__ void __launch_bounds__(256) head_decode_kernel(const __grid_constant__ DecodeParams p) {
+  __shared__ float s_box[kAnchorsPerCta][4];
+  const int b = blockIdx.y;
+  int lvl = 0;
+  while (lvl + 1 < p.n_levels && static_cast<int>(blockIdx.x) >= p.cta_off[lvl + 1]) ++lvl;
+  const int L = p.h[lvl] * p.w[lvl];
+  const int a0 = (blockIdx.x - p.cta_off[lvl]) * kAnchorsPerCta;
+  const int na = min(kAnchorsPerCta, L - a0);
+  const int no = 5 + p.nc;
+
+  // ---- phase 1: DFL expectation per (anchor, side); 4 consecutive lanes = one anchor ------------
+  {
+    const int al = threadIdx.x >> 2, side = threadIdx.x & 3;
+    const int a = a0 + al;
+    float dist = 0.f;
+    if (al < na) {
+      const __half* r = p.reg[lvl] + (static_cast<size_t>(b) * L + a) * p.reg_ld[lvl] + side * p.bins;
+      float mx = -INFINITY;
+      for (int i = 0; i < p.bins; ++i) mx = fmaxf(mx, __half2float(__ldg(r + i)));
+      float s = 0.f, e = 0.f;
+      for (int i = 0; i < p.bins; ++i) {
+        const float ex = expf(__half2float(__ldg(r + i)) - mx);
+        s += ex;
+        e = fmaf(static_cast<float>(i), ex, e);
+      }
+      dist = e / s;
+    }
+    // gather l,t,r,b of this anchor from the 4-lane group
+    const unsigned base = (threadIdx.x & 31) & ~3u;
+    const float dl = __shfl_sync(0xffffffffu, dist, base + 0);
+    const float dt = __shfl_sync(0xffffffffu, dist, base + 1);
+    const float dr = __shfl_sync(0xffffffffu, dist, base + 2);
+    const float db = __shfl_sync(0xffffffffu, dist, base + 3);
+    if (al < na && side == 0) {
+      const int gy = a / p.w[lvl], gx = a - gy * p.w[lvl];
+      const float ax = static_cast<float>(gx) + 0.5f, ay = static_cast<float>(gy) + 0.5f;
+      const float x1 = ax - dl, y1 = ay - dt, x2 = ax + dr, y2 = ay + db;
+      const float st = p.stride[lvl];
+      s_box[al][0] = ((x1 + x2) / 2.0f) * st;
+      s_box[al][1] = ((y1 + y2) / 2.0f) * st;
+      s_box[al][2] = (x2 - x1) * st;
+      s_box[al][3] = (y2 - y1) * st;
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: stream the [na, 5+nc] rows -----------------------------------------------------
+  float* dst = p.pred + (static_cast<size_t>(b) * p.total_anchors + p.anchor_off[lvl] + a0) * no;
+  const __half* cls = p.cls[lvl] + (static_cast<size_t>(b) * L + a0) * p.cls_ld[lvl];
+  const int count = na * no;
+  for (int i = threadIdx.x; i < count; i += blockDim.x) {
+    const int al = i / no, j = i - al * no;
+    float v;
+    if (j < 4) {
+      v = s_box[al][j];
+    } else if (j == 4) {
+      v = 1.0f;
+    } else {
+      const float z = __half2float(__ldg(cls + static_cast<size_t>(al) * p.cls_ld[lvl] + (j - 5)));
+      v = 1.0f / (1.0f + expf(-z));
+    }
+    dst[i] = v;
+  }
+}
+
+}  // namespace mafb200
+
+using namespace mafb200;
+
+extern "C" int32_t mafb200_head_decode(const maf_tensor* cls_logits, const maf_tensor* reg, const float* strides,
+                                       int32_t n_levels, int32_t reg_max, float* pred, void* stream) {
+  if (!cls_logits || !reg || !strides || !pred) return fail(MAF_E_ARG, "head_decode: null pointer");
+  if (n_levels < 1 || n_levels > kMaxLevels) return fail(MAF_E_ARG, "head_decode: n_levels=%d (1..%d)", n_levels, kMaxLevels);
+  if (reg_max < 1 || reg_max > 63) return fail(MAF_E_ARG, "head_decode: reg_max=%d", reg_max);
+  DecodeParams p;
+  memset(&p, 0, sizeof(p));
+  const int nc = cls_logits[0].c, n = cls_logits[0].n;
+  int anchors = 0, ctas = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    const maf_tensor* c = &cls_logits[l];
+    const maf_tensor* r = &reg[l];
+    if (!valid_f16_view(c) || !valid_f16_view(r)) return fail(MAF_E_ARG, "head_decode: bad tensor at level %d", l);
+    if (c->c != nc || c->n != n || !same_nhw(c, r) || r->c != 4 * (reg_max + 1))
+      return fail(MAF_E_ARG, "head_decode: level %d shape mismatch (cls c=%d reg c=%d)", l, c->c, r->c);
+    p.cls[l] = static_cast<const __half*>(c->ptr);
+    p.reg[l] = static_cast<const __half*>(r->ptr);
+    p.cls_ld[l] = c->c_stride;
+    p.reg_ld[l] = r->c_stride;
+    p.h[l] = c->h;
+    p.w[l] = c->w;
+    p.stride[l] = strides[l];
+    p.anchor_off[l] = anchors;
+    p.cta_off[l] = ctas;
+    anchors += c->h * c->w;
+    ctas += ceil_div(c->h * c->w, kAnchorsPerCta);
+  }
+  p.cta_off[n_levels] = ctas;
+  p.n_levels = n_levels;
+  p.nc = nc;
+  p.bins = reg_max + 1;
+  p.total_anchors = anchors;
+  p.pred = pred;
+  if (n > 65535) return fail(MAF_E_ARG, "head_decode: batch %d > 65535", n);
+  int32_t rc = require_sm100();
+  if (rc) return rc;
+  head_decode_kernel<<<dim3(ctas, n), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  return check_launch("head_decode kernel launch");
+}

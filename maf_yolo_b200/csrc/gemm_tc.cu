@@ -1,0 +1,394 @@
+// K1 / K2 — convolution as (implicit) GEMM on tcgen05 tensor cores.
+//
+//   D[M, N] = act( A[M, K] * W[N, K]^T + bias )       fp16 operands, fp32 accumulate in TMEM
+//
+// K1 (1x1 conv, yolov6/layers/common.py:29-50): A = NHWC activations, M = n*h*w pixels, K = Cin.
+//     Up to four sources are walked back-to-back along K, which is the reference's
+//     Concat -> Conv(1x1) (the MAFPN fusion stages, configs/yaml/MAF-YOLO-n.yaml:17-42, and the
+//     concat inside RepHDW / MPRep / SPPF, common.py:944,791,129) without materialising the concat.
+// K2 (3x3 stride-2 pad-1 conv, common.py:76-83,206): same core, the A tile of tap (ky,kx) is
+//     fetched by an im2col-mode TMA descriptor (traversal stride 2, bounding-box corners -1/-1,
+//     zero fill = the padding), K = 9 * Cin.
+//
+// One CTA computes one 128 x tile_n output tile:
+//   warp 0 / lane 0 : TMA producer (A tile 128x64 + W tile tile_n x 64 per stage, SWIZZLE_128B)
+//   warp 1 / lane 0 : tcgen05.mma issuer (UMMA 128 x tile_n x 16, 4 per stage), commits free the stage
+//   all 4 warps     : epilogue — tcgen05.ld 32x32b (one output row per thread) -> +bias -> act ->
+//                     fp16 -> 16-byte global stores (optionally also the x2 nearest-upsampled copy)
+// Several CTAs are resident per SM (smem <= ~100 KB, TMEM <= 256 columns each), so one CTA's
+// epilogue overlaps its neighbours' loads; K is tiny here (1-12 blocks), the kernel is HBM-bound.
+#include <string.h>
+
+#include "common.cuh"
+#include "host.h"
+
+namespace mafb200 {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB
+
+struct GemmParams {
+  CUtensorMap tmA[MAF_MAX_SRC];
+  CUtensorMap tmW;
+  const float* bias;
+  __half* out;
+  __half* out2;  // x2-upsampled copy or nullptr
+  int32_t M, N, tile_n;
+  int32_t out_ld, out2_ld;
+  int32_t out_h, out_w;  // spatial size of the output map (for out2 and im2col tile origin)
+  int32_t nsrc;
+  int32_t kblocks[MAF_MAX_SRC];  // 1x1: 64-wide K blocks of each source; 3x3: kblocks[0] = blocks per tap
+  int32_t act;
+  int32_t stages;
+  int32_t tmem_cols;
+  uint32_t idesc;
+};
+
+template <bool kIm2col>
+__global__ void __launch_bounds__(128) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int b_bytes = p.tile_n * kBlockK * 2;
+  const int stage_bytes = kABytes + b_bytes;
+  const int stages = p.stages;
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + stages;
+  uint64_t* tmem_full_bar = empty_bar + stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);
+
+  const int n0 = blockIdx.x * p.tile_n;
+  const int m0 = blockIdx.y * kBlockM;
+
+  int total_kb;
+  if (kIm2col) {
+    total_kb = 9 * p.kblocks[0];
+  } else {
+    total_kb = 0;
+    for (int s = 0; s < p.nsrc; ++s) total_kb += p.kblocks[s];
+  }
+
+  // ---- one-time setup -------------------------------------------------------------------------
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < (kIm2col ? 1 : p.nsrc); ++s) tma_prefetch_desc(&p.tmA[s]);
+    tma_prefetch_desc(&p.tmW);
+    for (int i = 0; i < stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, p.tmem_cols);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < p.tile_n; i += blockDim.x) s_bias[i] = p.bias[n0 + i];
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // ---- producer ---------------------------------------------------------------------------------
+  if (warp == 0 && lane == 0) {
+    int q0 = 0, p0 = 0, img = 0;
+    if (kIm2col) {
+      const int hw = p.out_h * p.out_w;
+      img = m0 / hw;
+      const int rem = m0 - img * hw;
+      p0 = rem / p.out_w;
+      q0 = rem - p0 * p.out_w;
+    }
+    int kb = 0;
+    int wk = 0;  // column in the packed weights
+    const int n_outer = kIm2col ? 9 : p.nsrc;
+    for (int o = 0; o < n_outer; ++o) {
+      const int nblk = kIm2col ? p.kblocks[0] : p.kblocks[o];
+      for (int j = 0; j < nblk; ++j, ++kb, wk += kBlockK) {
+        const int stage = kb % stages;
+        const uint32_t phase = (kb / stages) & 1;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * stage_bytes;
+        uint8_t* sb = sa + kABytes;
+        mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+        if (kIm2col) {
+          const int ky = o / 3, kx = o - ky * 3;
+          tma_load_im2col_4d(sa, &p.tmA[0], &full_bar[stage], j * kBlockK, 2 * q0 - 1, 2 * p0 - 1, img,
+                             static_cast<uint16_t>(kx), static_cast<uint16_t>(ky));
+        } else {
+          tma_load_2d(sa, &p.tmA[o], &full_bar[stage], j * kBlockK, m0);
+        }
+        tma_load_2d(sb, &p.tmW, &full_bar[stage], wk, n0);
+      }
+    }
+  }
+  // ---- MMA issuer -------------------------------------------------------------------------------
+  else if (warp == 1 && lane == 0) {
+    for (int kb = 0; kb < total_kb; ++kb) {
+      const int stage = kb % stages;
+      const uint32_t phase = (kb / stages) & 1;
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after_sync();
+      const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+      const uint64_t da = umma_smem_desc_sw128(sa);
+      const uint64_t db = umma_smem_desc_sw128(sa + kABytes);
+#pragma unroll
+      for (int k = 0; k < kBlockK / 16; ++k) {
+        // advance 16 fp16 = 32 B inside the 128-B swizzle row: +2 in the (addr >> 4) field
+        tc_mma_f16(tmem_base, da + 2 * k, db + 2 * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
+      }
+      tc_commit(&empty_bar[stage]);
+    }
+    tc_commit(tmem_full_bar);
+  }
+
+  // ---- epilogue (all 128 threads; thread t owns output row m0 + t == TMEM lane t) ----------------
+  __syncwarp();
+  mbar_wait(tmem_full_bar, 0);
+  tc_fence_after_sync();
+
+  const int row = warp * 32 + lane;
+  const int m = m0 + row;
+  const bool row_ok = m < p.M;
+  const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+  __half* orow = p.out + static_cast<size_t>(row_ok ? m : 0) * p.out_ld;
+  __half* urow = nullptr;
+  if (p.out2 != nullptr && row_ok) {
+    const int hw = p.out_h * p.out_w;
+    const int img = m / hw;
+    const int rem = m - img * hw;
+    const int y = rem / p.out_w;
+    const int x = rem - y * p.out_w;
+    urow = p.out2 + ((static_cast<size_t>(img) * 2 * p.out_h + 2 * y) * (2 * p.out_w) + 2 * x) * p.out2_ld;
+  }
+  const size_t up_dx = p.out2_ld;
+  const size_t up_dy = static_cast<size_t>(2) * p.out_w * p.out2_ld;
+
+#pragma unroll 1
+  for (int c = 0; c < p.tile_n; c += 16) {
+    uint32_t r[16];
+    __syncwarp();  // tcgen05.ld is .sync.aligned: the warp must be converged here
+    tmem_ld_32x32b_x16(taddr + c, r);
+    tmem_ld_wait();
+    const int n = n0 + c;
+    if (row_ok && n < p.N) {
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = apply_act(__uint_as_float(r[j]) + s_bias[c + j], p.act);
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const int ng = n + 8 * g;
+      if (ng + 8 <= p.N) {
+        uint4 pk;
+        pk.x = pack_half2(v[8 * g + 0], v[8 * g + 1]);
+        pk.y = pack_half2(v[8 * g + 2], v[8 * g + 3]);
+        pk.z = pack_half2(v[8 * g + 4], v[8 * g + 5]);
+        pk.w = pack_half2(v[8 * g + 6], v[8 * g + 7]);
+        *reinterpret_cast<uint4*>(orow + ng) = pk;
+        if (urow != nullptr) {
+          *reinterpret_cast<uint4*>(urow + ng) = pk;
+          *reinterpret_cast<uint4*>(urow + up_dx + ng) = pk;
+          *reinterpret_cast<uint4*>(urow + up_dy + ng) = pk;
+          *reinterpret_cast<uint4*>(urow + up_dy + up_dx + ng) = pk;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (ng + j < p.N) {
+            const __half hv = __float2half_rn(v[8 * g + j]);
+            orow[ng + j] = hv;
+            if (urow != nullptr) {
+              urow[ng + j] = hv;
+              urow[up_dx + ng + j] = hv;
+              urow[up_dy + ng + j] = hv;
+              urow[up_dy + up_dx + ng + j] = hv;
+            }
+          }
+        }
+      }
+    }
+    }
+  }
+
+  // ---- teardown -----------------------------------------------------------------------------------
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static int32_t encode_w_map(CUtensorMap* tm, const void* w, int k_packed, int rows, int tile_n) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return fail(MAF_E_ARCH, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(k_packed), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(k_packed) * 2};
+  cuuint32_t box[2] = {kBlockK, static_cast<cuuint32_t>(tile_n)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(MAF_E_CUDA, "cuTensorMapEncodeTiled(W %dx%d) failed: %d", rows, k_packed, (int)r);
+  return MAF_OK;
+}
+
+static int32_t encode_a_map_2d(CUtensorMap* tm, const maf_tensor* t) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return fail(MAF_E_ARCH, "cuTensorMapEncodeTiled entry point not available");
+  const cuuint64_t M = static_cast<cuuint64_t>(t->n) * t->h * t->w;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(t->c), M};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(t->c_stride) * 2};
+  cuuint32_t box[2] = {kBlockK, kBlockM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, t->ptr, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(MAF_E_CUDA, "cuTensorMapEncodeTiled(A c=%d ld=%d M=%llu) failed: %d", t->c, t->c_stride,
+                (unsigned long long)M, (int)r);
+  return MAF_OK;
+}
+
+static int32_t encode_a_map_im2col(CUtensorMap* tm, const maf_tensor* t) {
+  EncodeIm2colFn enc = encode_im2col_fn();
+  if (!enc) return fail(MAF_E_ARCH, "cuTensorMapEncodeIm2col entry point not available");
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(t->c), static_cast<cuuint64_t>(t->w), static_cast<cuuint64_t>(t->h),
+                        static_cast<cuuint64_t>(t->n)};
+  const cuuint64_t px = static_cast<cuuint64_t>(t->c_stride) * 2;
+  cuuint64_t strides[3] = {px, px * t->w, px * t->w * t->h};
+  // 3x3, pad 1, dilation 1: lower corner = -pad, upper corner = pad - (k-1) = -1 (W, H order).
+  int lower[2] = {-1, -1};
+  int upper[2] = {-1, -1};
+  cuuint32_t estr[4] = {1, 2, 2, 1};  // traversal stride 2 in W and H
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, t->ptr, dims, strides, lower, upper, kBlockK, kBlockM, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(MAF_E_CUDA, "cuTensorMapEncodeIm2col(c=%d w=%d h=%d n=%d) failed: %d", t->c, t->w, t->h, t->n, (int)r);
+  return MAF_OK;
+}
+
+static int pow2_cols(int n) {
+  int c = 32;
+  while (c < n) c <<= 1;
+  return c;
+}
+
+template <bool kIm2col>
+static int32_t launch_gemm(GemmParams& p, int n_tiles, int total_kb, cudaStream_t stream) {
+  const int stage_bytes = kABytes + p.tile_n * kBlockK * 2;
+  int stages = total_kb < 4 ? total_kb : 4;
+  while (stages > 1 && stages * stage_bytes > 112 * 1024) --stages;
+  p.stages = stages;
+  p.tmem_cols = pow2_cols(p.tile_n);
+  p.idesc = umma_idesc_f16(kBlockM, p.tile_n);
+  const size_t smem = static_cast<size_t>(stages) * stage_bytes + (2 * stages + 1) * 8 + 16 + p.tile_n * 4 + 1024;
+  static size_t configured[2] = {0, 0};
+  if (smem > configured[kIm2col]) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<kIm2col>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         200 * 1024);
+    if (e != cudaSuccess) return fail(MAF_E_CUDA, "cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e));
+    configured[kIm2col] = 200 * 1024;
+  }
+  dim3 grid(n_tiles, ceil_div(p.M, kBlockM));
+  gemm_tc_kernel<kIm2col><<<grid, 128, smem, stream>>>(p);
+  return check_launch(kIm2col ? "conv3x3s2 kernel launch" : "conv1x1 kernel launch");
+}
+
+}  // namespace mafb200
+
+using namespace mafb200;
+
+extern "C" int32_t mafb200_conv1x1(const maf_tensor* srcs, int32_t n_src, const void* w_packed, const float* bias,
+                                   int32_t act, const maf_tensor* dst, const maf_tensor* dst_up2x, void* stream) {
+  if (!srcs || n_src < 1 || n_src > MAF_MAX_SRC) return fail(MAF_E_ARG, "conv1x1: n_src=%d (1..%d)", n_src, MAF_MAX_SRC);
+  if (!w_packed || !bias) return fail(MAF_E_ARG, "conv1x1: null weights/bias");
+  if (!valid_f16_view(dst)) return fail(MAF_E_ARG, "conv1x1: bad dst tensor");
+  if (!aligned_f16_view(dst)) return fail(MAF_E_ALIGN, "conv1x1: dst must be 16-B aligned with c_stride %% 8 == 0");
+  if (act < MAF_ACT_NONE || act > MAF_ACT_SIGMOID) return fail(MAF_E_ARG, "conv1x1: bad act %d", act);
+  if ((reinterpret_cast<uintptr_t>(w_packed) & 15) != 0) return fail(MAF_E_ALIGN, "conv1x1: w_packed not 16-B aligned");
+  int32_t rc = require_sm100();
+  if (rc) return rc;
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  int chans[MAF_MAX_SRC];
+  int total_kb = 0;
+  for (int s = 0; s < n_src; ++s) {
+    const maf_tensor* t = &srcs[s];
+    if (!valid_f16_view(t)) return fail(MAF_E_ARG, "conv1x1: bad src[%d]", s);
+    if (!aligned_f16_view(t)) return fail(MAF_E_ALIGN, "conv1x1: src[%d] alignment", s);
+    if (!same_nhw(t, dst)) return fail(MAF_E_ARG, "conv1x1: src[%d] n/h/w differ from dst", s);
+    rc = encode_a_map_2d(&p.tmA[s], t);
+    if (rc) return rc;
+    chans[s] = t->c;
+    p.kblocks[s] = ceil_div(t->c, kBlockK);
+    total_kb += p.kblocks[s];
+  }
+  int n_tiles = 0, tile_n = 0;
+  mafb200_gemm_tiling(dst->c, &n_tiles, &tile_n);
+  const int k_packed = mafb200_packed_k_1x1(chans, n_src);
+  rc = encode_w_map(&p.tmW, w_packed, k_packed, n_tiles * tile_n, tile_n);
+  if (rc) return rc;
+
+  p.bias = bias;
+  p.out = static_cast<__half*>(dst->ptr);
+  p.out_ld = dst->c_stride;
+  p.M = dst->n * dst->h * dst->w;
+  p.N = dst->c;
+  p.tile_n = tile_n;
+  p.out_h = dst->h;
+  p.out_w = dst->w;
+  p.nsrc = n_src;
+  p.act = act;
+  if (dst_up2x) {
+    if (!valid_f16_view(dst_up2x) || !aligned_f16_view(dst_up2x) || dst_up2x->n != dst->n ||
+        dst_up2x->h != 2 * dst->h || dst_up2x->w != 2 * dst->w || dst_up2x->c != dst->c)
+      return fail(MAF_E_ARG, "conv1x1: dst_up2x must be [n,2h,2w,c] fp16");
+    p.out2 = static_cast<__half*>(dst_up2x->ptr);
+    p.out2_ld = dst_up2x->c_stride;
+  }
+  return launch_gemm<false>(p, n_tiles, total_kb, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int32_t mafb200_conv3x3s2(const maf_tensor* src, const void* w_packed, const float* bias, int32_t act,
+                                     const maf_tensor* dst, void* stream) {
+  if (!valid_f16_view(src) || !valid_f16_view(dst)) return fail(MAF_E_ARG, "conv3x3s2: bad src/dst tensor");
+  if (!aligned_f16_view(src) || !aligned_f16_view(dst)) return fail(MAF_E_ALIGN, "conv3x3s2: alignment");
+  if (!w_packed || !bias) return fail(MAF_E_ARG, "conv3x3s2: null weights/bias");
+  if ((reinterpret_cast<uintptr_t>(w_packed) & 15) != 0) return fail(MAF_E_ALIGN, "conv3x3s2: w_packed alignment");
+  if ((src->h & 1) || (src->w & 1) || dst->h != src->h / 2 || dst->w != src->w / 2 || dst->n != src->n)
+    return fail(MAF_E_ARG, "conv3x3s2: need even h,w and dst = [n,h/2,w/2,cout] (src %dx%d dst %dx%d)", src->h, src->w,
+                dst->h, dst->w);
+  if (act < MAF_ACT_NONE || act > MAF_ACT_SIGMOID) return fail(MAF_E_ARG, "conv3x3s2: bad act %d", act);
+  int32_t rc = require_sm100();
+  if (rc) return rc;
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  rc = encode_a_map_im2col(&p.tmA[0], src);
+  if (rc) return rc;
+  int n_tiles = 0, tile_n = 0;
+  mafb200_gemm_tiling(dst->c, &n_tiles, &tile_n);
+  const int k_packed = mafb200_packed_k_3x3(src->c);
+  rc = encode_w_map(&p.tmW, w_packed, k_packed, n_tiles * tile_n, tile_n);
+  if (rc) return rc;
+  p.kblocks[0] = ceil_div(src->c, kBlockK);
+  p.nsrc = 1;
+  p.bias = bias;
+  p.out = static_cast<__half*>(dst->ptr);
+  p.out_ld = dst->c_stride;
+  p.M = dst->n * dst->h * dst->w;
+  p.N = dst->c;
+  p.tile_n = tile_n;
+  p.out_h = dst->h;
+  p.out_w = dst->w;
+  p.act = act;
+  return launch_gemm<true>(p, n_tiles, 9 * p.kblocks[0], static_cast<cudaStream_t>(stream));
+}

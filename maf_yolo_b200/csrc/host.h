@@ -1,0 +1,48 @@
+// Host-side plumbing shared by the C-ABI translation units: error text, argument checks,
+// launch counting and the driver entry points for tensor-map encoding.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/mafb200.h"
+
+namespace mafb200 {
+
+// Sets the calling thread's last-error text and returns `code` (so call sites read
+// `return fail(MAF_E_ARG, "...")`).
+int32_t fail(int32_t code, const char* fmt, ...);
+void count_launch();
+
+// Checks the sticky launch error right after a kernel launch (no synchronisation).
+int32_t check_launch(const char* what);
+
+// Returns MAF_OK if the current device is sm_100-class (cached per device).
+int32_t require_sm100();
+
+// cuTensorMapEncodeTiled / cuTensorMapEncodeIm2col resolved through
+// cudaGetDriverEntryPoint, so the library does not link libcuda directly.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn();
+EncodeIm2colFn encode_im2col_fn();
+
+inline bool valid_f16_view(const maf_tensor* t) {
+  return t && t->ptr && t->dtype == MAF_F16 && t->n > 0 && t->h > 0 && t->w > 0 && t->c > 0 && t->c_stride >= t->c;
+}
+inline bool aligned_f16_view(const maf_tensor* t) {
+  return (reinterpret_cast<uintptr_t>(t->ptr) & 15) == 0 && (t->c_stride % 8) == 0;
+}
+inline bool same_nhw(const maf_tensor* a, const maf_tensor* b) {
+  return a->n == b->n && a->h == b->h && a->w == b->w;
+}
+
+}  // namespace mafb200

@@ -1,0 +1,372 @@
+// K8 — batched NMS with the exact semantics of the reference's non_max_suppression
+// (yolov6/utils/nms.py:31-105) + torchvision.ops.nms, without host round trips:
+//
+//   nms.py:48   candidates: obj > conf  AND  max_c cls > conf          (fp32 compares)
+//   nms.py:69   score = cls * obj
+//   nms.py:72   box = xywh2xyxy (x1 = cx - w/2 ...)                    (fp32)
+//   nms.py:75-80 multi_label: every (anchor, class) with score > conf, in (anchor asc, class asc)
+//               order; else the best class per anchor (first maximum), kept if score > conf
+//   nms.py:83-84 optional class filter
+//   nms.py:90-91 more than max_nms candidates -> keep the max_nms best scores
+//   nms.py:94-95 boxes + class * 4096 (0 if agnostic)                  (fp32 add, rounding kept)
+//   nms.py:96   torchvision nms: stable sort by score descending, greedy suppression where
+//               inter / (area_i + area_j - inter) > iou_thres (strict, IEEE division,
+//               threshold compared in double as torchvision's CPU kernel does)
+//   nms.py:97-100 first max_det survivors, in score order
+//   (nms.py:101-103, the 10 s wall-clock bail-out, is deliberately NOT reproduced.)
+//
+// Kernel 1 (compaction): one warp per anchor row; candidates are emitted UNORDERED (warp-
+//   aggregated atomics) as 64-bit keys  (~score_bits << 32) | (anchor*nc + class): ascending key
+//   order == (score desc, anchor asc, class asc) == the reference's stable sort of its ordered list.
+// Kernel 2 (one CTA per image): bitonic sort of the keys (shared memory when they fit, global
+//   workspace otherwise), then greedy NMS in score order over 256-candidate chunks: every
+//   candidate is tested against the boxes kept so far (<= max_det of them, in smem), the chunk's
+//   own 256x256 IoU bit matrix resolves intra-chunk dependencies, and the loop stops as soon as
+//   max_det boxes are kept (later boxes cannot change the first max_det results).
+// All float ops that decide a comparison use explicit round-to-nearest intrinsics so the
+// compiler cannot contract them into FMAs.
+#include <string.h>
+
+#include "common.cuh"
+#include "host.h"
+
+namespace mafb200 {
+
+constexpr int kSortSmemKeys = 8192;  // 64 KB of keys
+constexpr int kChunk = 256;
+constexpr int kMaxDetCap = 2048;
+constexpr float kMaxWh = 4096.0f;    // nms.py:54
+
+struct NmsParams {
+  const float* pred;
+  int32_t B, A, nc;
+  float conf;
+  double iou;
+  int32_t multi_label, agnostic;
+  const uint8_t* class_filter;
+  int32_t max_det, max_nms;
+  float* det;
+  int32_t* count;
+  int32_t* ncand;       // [B]
+  unsigned long long* keys;  // [B][cap_pow2]
+  long long cap_pow2;
+};
+
+// ---- kernel 1: threshold + compaction ----------------------------------------------------------
+__global__ void __launch_bounds__(256) nms_compact_kernel(const NmsParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int a = blockIdx.x * 8 + warp;
+  const int b = blockIdx.y;
+  if (a >= p.A) return;
+  const int no = 5 + p.nc;
+  const float* row = p.pred + (static_cast<size_t>(b) * p.A + a) * no;
+  const float obj = __ldg(row + 4);
+
+  // pass 1: raw class maximum (nms.py:48)
+  float mx = -INFINITY;
+  for (int c = lane; c < p.nc; c += 32) mx = fmaxf(mx, __ldg(row + 5 + c));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (!(obj > p.conf) || !(mx > p.conf)) return;
+
+  unsigned long long* keys = p.keys + static_cast<size_t>(b) * p.cap_pow2;
+  if (p.multi_label) {
+    for (int c0 = 0; c0 < p.nc; c0 += 32) {
+      const int c = c0 + lane;
+      float s = 0.f;
+      bool pass = false;
+      if (c < p.nc) {
+        s = __fmul_rn(__ldg(row + 5 + c), obj);
+        pass = s > p.conf && (p.class_filter == nullptr || p.class_filter[c] != 0);
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, pass);
+      if (m == 0) continue;
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&p.ncand[b], __popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (pass) {
+        const long long slot = base + __popc(m & ((1u << lane) - 1));
+        if (slot < p.cap_pow2) {
+          const unsigned sb = __float_as_uint(s);
+          keys[slot] = (static_cast<unsigned long long>(~sb) << 32) |
+                       static_cast<unsigned long long>(static_cast<unsigned>(a) * p.nc + c);
+        }
+      }
+    }
+  } else {
+    // best class by score, first maximum on ties (torch.max semantics on CPU)
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int c = lane; c < p.nc; c += 32) {
+      const float s = __fmul_rn(__ldg(row + 5 + c), obj);
+      if (s > best) {
+        best = s;
+        bi = c;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) {
+        best = ob;
+        bi = oi;
+      }
+    }
+    if (lane == 0 && best > p.conf && bi < p.nc && (p.class_filter == nullptr || p.class_filter[bi] != 0)) {
+      const long long slot = atomicAdd(&p.ncand[b], 1);
+      if (slot < p.cap_pow2) {
+        const unsigned sb = __float_as_uint(best);
+        keys[slot] = (static_cast<unsigned long long>(~sb) << 32) |
+                     static_cast<unsigned long long>(static_cast<unsigned>(a) * p.nc + bi);
+      }
+    }
+  }
+}
+
+// ---- bitonic sort helpers ------------------------------------------------------------------------
+__device__ __forceinline__ void bitonic_sort(unsigned long long* k, int P) {
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+        const int i = 2 * t - (t & (stride - 1));
+        const int j = i + stride;
+        const bool up = (i & size) == 0;
+        const unsigned long long a = k[i], c = k[j];
+        if ((a > c) == up) {
+          k[i] = c;
+          k[j] = a;
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ bool iou_gt(float ax1, float ay1, float ax2, float ay2, float aarea, float bx1, float by1,
+                                       float bx2, float by2, float barea, double thr) {
+  const float xx1 = fmaxf(ax1, bx1), yy1 = fmaxf(ay1, by1);
+  const float xx2 = fminf(ax2, bx2), yy2 = fminf(ay2, by2);
+  const float w = fmaxf(0.0f, __fsub_rn(xx2, xx1));
+  const float h = fmaxf(0.0f, __fsub_rn(yy2, yy1));
+  const float inter = __fmul_rn(w, h);
+  const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aarea, barea), inter));
+  return static_cast<double>(ovr) > thr;
+}
+
+// ---- kernel 2: per-image sort + greedy NMS ---------------------------------------------------------
+__global__ void __launch_bounds__(1024) nms_select_kernel(const NmsParams p) {
+  extern __shared__ unsigned long long s_dyn[];
+  unsigned long long* s_keys = s_dyn;                                          // [kSortSmemKeys]
+  float* k_box = reinterpret_cast<float*>(s_keys + kSortSmemKeys);             // kept: [max_det][5]
+  float* c_box = k_box + static_cast<size_t>(round_up(p.max_det, 2)) * 5;      // chunk: [kChunk][5] (8-B aligned)
+  unsigned long long* c_mask = reinterpret_cast<unsigned long long*>(c_box + kChunk * 5);  // [kChunk][4]
+  int* c_alive = reinterpret_cast<int*>(c_mask + kChunk * 4);                  // [kChunk]
+  __shared__ int s_nk;
+  __shared__ int s_done;
+
+  const int b = blockIdx.x;
+  const int no = 5 + p.nc;
+  long long n = p.ncand[b];
+  if (n > p.cap_pow2) n = p.cap_pow2;
+  float* det = p.det + static_cast<size_t>(b) * p.max_det * 6;
+  for (int i = threadIdx.x; i < p.max_det * 6; i += blockDim.x) det[i] = 0.0f;
+  if (n == 0) {
+    if (threadIdx.x == 0) p.count[b] = 0;
+    return;
+  }
+
+  // ---- sort -----------------------------------------------------------------------------------
+  unsigned long long* gkeys = p.keys + static_cast<size_t>(b) * p.cap_pow2;
+  unsigned long long* keys;
+  int P = 1;
+  while (P < n) P <<= 1;
+  if (P <= kSortSmemKeys) {
+    for (int i = threadIdx.x; i < P; i += blockDim.x) s_keys[i] = i < n ? gkeys[i] : ~0ull;
+    keys = s_keys;
+  } else {
+    for (long long i = n + threadIdx.x; i < P; i += blockDim.x) gkeys[i] = ~0ull;
+    keys = gkeys;
+  }
+  bitonic_sort(keys, P);
+  const int n_eff = static_cast<int>(n < p.max_nms ? n : p.max_nms);
+
+  if (threadIdx.x == 0) {
+    s_nk = 0;
+    s_done = 0;
+  }
+  __syncthreads();
+
+  const float* pred_b = p.pred + static_cast<size_t>(b) * p.A * no;
+  for (int base = 0; base < n_eff; base += kChunk) {
+    const int cn = min(kChunk, n_eff - base);
+    const int nk0 = s_nk;
+    // (1) materialise the chunk's class-offset boxes
+    if (threadIdx.x < cn) {
+      const unsigned idx = static_cast<unsigned>(keys[base + threadIdx.x] & 0xffffffffull);
+      const int a = idx / p.nc, c = idx - a * p.nc;
+      const float* row = pred_b + static_cast<size_t>(a) * no;
+      const float cx = row[0], cy = row[1], w = row[2], h = row[3];
+      const float off = p.agnostic ? 0.0f : __fmul_rn(static_cast<float>(c), kMaxWh);
+      const float x1 = __fadd_rn(__fsub_rn(cx, __fdiv_rn(w, 2.0f)), off);
+      const float y1 = __fadd_rn(__fsub_rn(cy, __fdiv_rn(h, 2.0f)), off);
+      const float x2 = __fadd_rn(__fadd_rn(cx, __fdiv_rn(w, 2.0f)), off);
+      const float y2 = __fadd_rn(__fadd_rn(cy, __fdiv_rn(h, 2.0f)), off);
+      float* cb = c_box + threadIdx.x * 5;
+      cb[0] = x1;
+      cb[1] = y1;
+      cb[2] = x2;
+      cb[3] = y2;
+      cb[4] = __fmul_rn(__fsub_rn(x2, x1), __fsub_rn(y2, y1));
+      c_alive[threadIdx.x] = 1;
+    }
+    for (int i = threadIdx.x; i < kChunk * 4; i += blockDim.x) c_mask[i] = 0ull;
+    __syncthreads();
+    // (2) suppression by boxes kept in earlier chunks: 4 threads per candidate stride the kept list
+    {
+      const int ci = threadIdx.x >> 2, part = threadIdx.x & 3;
+      if (ci < cn) {
+        const float* cb = c_box + ci * 5;
+        bool dead = false;
+        for (int k = part; k < nk0 && !dead; k += 4) {
+          const float* kb = k_box + k * 5;
+          dead = iou_gt(kb[0], kb[1], kb[2], kb[3], kb[4], cb[0], cb[1], cb[2], cb[3], cb[4], p.iou);
+        }
+        if (dead) c_alive[ci] = 0;
+      }
+    }
+    // (3) intra-chunk IoU bit matrix: bit j of row i set if i suppresses j (j > i)
+    for (int t = threadIdx.x; t < kChunk * 4; t += blockDim.x) {
+      const int i = t >> 2, wq = t & 3;
+      if (i >= cn) continue;
+      const float* ib = c_box + i * 5;
+      unsigned long long bits = 0ull;
+      const int j0 = wq * 64;
+      for (int jj = 0; jj < 64; ++jj) {
+        const int j = j0 + jj;
+        if (j > i && j < cn) {
+          const float* jb = c_box + j * 5;
+          if (iou_gt(ib[0], ib[1], ib[2], ib[3], ib[4], jb[0], jb[1], jb[2], jb[3], jb[4], p.iou)) bits |= 1ull << jj;
+        }
+      }
+      c_mask[t] = bits;
+    }
+    __syncthreads();
+    // (4) sequential resolve (one thread), appends to the kept list and writes the output rows
+    if (threadIdx.x == 0) {
+      unsigned long long rem[4] = {0ull, 0ull, 0ull, 0ull};
+      int nk = nk0;
+      for (int i = 0; i < cn && nk < p.max_det; ++i) {
+        if (!c_alive[i] || ((rem[i >> 6] >> (i & 63)) & 1ull)) continue;
+        rem[0] |= c_mask[i * 4 + 0];
+        rem[1] |= c_mask[i * 4 + 1];
+        rem[2] |= c_mask[i * 4 + 2];
+        rem[3] |= c_mask[i * 4 + 3];
+        const float* cb = c_box + i * 5;
+        float* kb = k_box + nk * 5;
+        kb[0] = cb[0];
+        kb[1] = cb[1];
+        kb[2] = cb[2];
+        kb[3] = cb[3];
+        kb[4] = cb[4];
+        // output row: un-offset box, score, class (nms.py:76-80,100)
+        const unsigned long long key = keys[base + i];
+        const unsigned idx = static_cast<unsigned>(key & 0xffffffffull);
+        const int a = idx / p.nc, c = idx - a * p.nc;
+        const float* row = pred_b + static_cast<size_t>(a) * no;
+        const float cx = row[0], cy = row[1], w = row[2], h = row[3];
+        float* o = det + static_cast<size_t>(nk) * 6;
+        o[0] = __fsub_rn(cx, __fdiv_rn(w, 2.0f));
+        o[1] = __fsub_rn(cy, __fdiv_rn(h, 2.0f));
+        o[2] = __fadd_rn(cx, __fdiv_rn(w, 2.0f));
+        o[3] = __fadd_rn(cy, __fdiv_rn(h, 2.0f));
+        o[4] = __uint_as_float(~static_cast<unsigned>(key >> 32));
+        o[5] = static_cast<float>(c);
+        ++nk;
+      }
+      s_nk = nk;
+      s_done = nk >= p.max_det ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_done) break;
+  }
+  if (threadIdx.x == 0) p.count[b] = s_nk;
+}
+
+static long long pow2_ceil(long long v) {
+  long long p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+}  // namespace mafb200
+
+using namespace mafb200;
+
+extern "C" size_t mafb200_nms_workspace_bytes(int32_t batch, int32_t anchors, int32_t nc) {
+  if (batch <= 0 || anchors <= 0 || nc <= 0) return 0;
+  const long long cap = pow2_ceil(static_cast<long long>(anchors) * nc);
+  return 256 + static_cast<size_t>(batch) * cap * sizeof(unsigned long long) +
+         ((static_cast<size_t>(batch) * 4 + 255) / 256) * 256;
+}
+
+extern "C" int32_t mafb200_nms(const float* pred, int32_t batch, int32_t anchors, int32_t nc, double conf_thres,
+                               double iou_thres, int32_t multi_label, int32_t agnostic, const uint8_t* class_filter,
+                               int32_t max_det, int32_t max_nms, float* det, int32_t* count, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  if (!pred || !det || !count || !workspace) return fail(MAF_E_ARG, "nms: null pointer");
+  if (batch <= 0 || anchors <= 0 || nc <= 0) return fail(MAF_E_ARG, "nms: bad shape B=%d A=%d nc=%d", batch, anchors, nc);
+  // same parameter checks as the reference's asserts (nms.py:50-51)
+  if (!(conf_thres >= 0.0 && conf_thres <= 1.0)) return fail(MAF_E_ARG, "nms: conf_thres must be in [0,1], got %g", conf_thres);
+  if (!(iou_thres >= 0.0 && iou_thres <= 1.0)) return fail(MAF_E_ARG, "nms: iou_thres must be in [0,1], got %g", iou_thres);
+  if (max_det <= 0 || max_det > kMaxDetCap) return fail(MAF_E_ARG, "nms: max_det=%d (1..%d)", max_det, kMaxDetCap);
+  if (max_nms <= 0) return fail(MAF_E_ARG, "nms: max_nms=%d", max_nms);
+  if (static_cast<long long>(anchors) * nc > 0x7fffffffll) return fail(MAF_E_ARG, "nms: anchors*nc overflows int32");
+  if (batch > 65535) return fail(MAF_E_ARG, "nms: batch %d > 65535", batch);
+  if (workspace_bytes < mafb200_nms_workspace_bytes(batch, anchors, nc))
+    return fail(MAF_E_WORKSPACE, "nms: workspace %zu < required %zu", workspace_bytes,
+                mafb200_nms_workspace_bytes(batch, anchors, nc));
+  if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(MAF_E_ALIGN, "nms: workspace must be 256-B aligned");
+  int32_t rc = require_sm100();
+  if (rc) return rc;
+
+  NmsParams p;
+  memset(&p, 0, sizeof(p));
+  p.pred = pred;
+  p.B = batch;
+  p.A = anchors;
+  p.nc = nc;
+  p.conf = static_cast<float>(conf_thres);  // torch compares an fp32 tensor with the scalar cast to fp32
+  p.iou = iou_thres;
+  p.multi_label = (multi_label != 0 && nc > 1) ? 1 : 0;  // nms.py:57
+  p.agnostic = agnostic != 0;
+  p.class_filter = class_filter;
+  p.max_det = max_det;
+  p.max_nms = max_nms;
+  p.det = det;
+  p.count = count;
+  const size_t hdr = ((static_cast<size_t>(batch) * 4 + 255) / 256) * 256;
+  p.ncand = static_cast<int32_t*>(workspace);
+  p.keys = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(workspace) + hdr);
+  p.cap_pow2 = pow2_ceil(static_cast<long long>(anchors) * nc);
+
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(p.ncand, 0, static_cast<size_t>(batch) * 4, st);
+  if (e != cudaSuccess) return fail(MAF_E_CUDA, "nms: cudaMemsetAsync: %s", cudaGetErrorString(e));
+  nms_compact_kernel<<<dim3(ceil_div(anchors, 8), batch), 256, 0, st>>>(p);
+  rc = check_launch("nms_compact kernel launch");
+  if (rc) return rc;
+
+  const size_t smem = static_cast<size_t>(kSortSmemKeys) * 8 + static_cast<size_t>(round_up(max_det, 2)) * 5 * 4 +
+                      kChunk * 5 * 4 +
+                      kChunk * 4 * 8 + kChunk * 4;
+  static bool configured = false;
+  if (!configured) {
+    e = cudaFuncSetAttribute(nms_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (e != cudaSuccess) return fail(MAF_E_CUDA, "nms: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  nms_select_kernel<<<batch, 1024, smem, st>>>(p);
+  return check_launch("nms_select kernel launch");
+}

@@ -1,0 +1,331 @@
+"""GPU parity tests of every kernel behind the C ABI, one op at a time.
+
+Floating-point kernels are compared with a plain PyTorch fp32 CPU computation of the same op on
+the same fp16-rounded inputs/weights (tolerance: fp16 output rounding, stated per test); the NMS
+kernel is compared bit-exactly with the oracle (oracle/nms.py), which is itself pinned
+bit-exactly against the reference's non_max_suppression.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 2e-3  # fp16 output rounding is 2^-11 = 4.9e-4 relative; accumulation order adds a little
+ATOL = 2e-3
+
+
+def _act_ref(y, act):
+    return {"none": lambda t: t, "silu": F.silu, "relu": F.relu, "sigmoid": torch.sigmoid}[act](y)
+
+
+def _close(got, ref, what, rtol=RTOL, atol=ATOL):
+    got, ref = got.float().cpu(), ref.float().cpu()
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    err = (got - ref).abs()
+    tol = atol + rtol * ref.abs()
+    bad = err > tol
+    assert not bad.any(), (f"{what}: {int(bad.sum())}/{bad.numel()} outside tolerance, max abs err "
+                           f"{err.max().item():.4e} at {np.unravel_index(int(err.argmax()), err.shape)}, "
+                           f"ref there {ref.flatten()[err.argmax()].item():.4e}")
+
+
+# every distinct (sources -> cout @ H) family of the N/S/M graphs, small batch
+CONV1X1_CASES = [
+    # (src_channels, cout, h, w, n, act)
+    ([48], 48, 20, 20, 2, "silu"),
+    ([24], 72, 40, 40, 1, "silu"),       # K < 64 (zero-filled K tail), N not multiple of 16
+    ([72], 24, 40, 40, 1, "silu"),       # K = 64 + 8 tail
+    ([144], 96, 20, 12, 3, "silu"),      # M not a multiple of 128
+    ([288], 192, 20, 20, 2, "silu"),
+    ([192], 576, 20, 20, 1, "silu"),     # 3 N tiles
+    ([576], 384, 20, 20, 1, "silu"),     # 9 K blocks > 4 stages, 2 N tiles
+    ([768], 384, 20, 20, 2, "silu"),     # 12 K blocks
+    ([96, 384], 192, 20, 20, 2, "silu"),             # L11 concat
+    ([64, 192, 192], 128, 40, 40, 1, "silu"),        # L15 concat
+    ([128, 128, 128, 192], 128, 40, 40, 2, "silu"),  # L25 concat (4 sources)
+    ([24, 24, 24], 48, 40, 40, 1, "silu"),           # RepHDW conv2 at c_=24 (three 24-ch slices)
+    ([128], 80, 40, 40, 2, "none"),      # cls_pred
+    ([128], 68, 40, 40, 2, "none"),      # reg_pred (cout % 8 == 4)
+    ([192], 80, 20, 20, 2, "sigmoid"),
+    ([1536], 768, 20, 20, 1, "silu"),    # M variant, 24 K blocks, 3 N tiles of 256
+    ([64], 64, 7, 9, 1, "relu"),         # tiny M < 128
+]
+
+
+@pytest.mark.parametrize("src_channels,cout,h,w,n,act", CONV1X1_CASES)
+def test_conv1x1(cuda_device, src_channels, cout, h, w, n, act):
+    from maf_yolo_b200 import ops
+
+    g = torch.Generator().manual_seed(1234 + cout + sum(src_channels))
+    ktot = sum(src_channels)
+    xs = [torch.randn(n, c, h, w, generator=g).half().float() for c in src_channels]
+    wgt = (torch.randn(cout, ktot, generator=g) / ktot ** 0.5).half().float()
+    bias = torch.randn(cout, generator=g)
+    ref = _act_ref(F.conv2d(torch.cat(xs, 1), wgt[:, :, None, None], bias), act)
+
+    # sources are channel slices of ONE wider buffer when they all have equal spatial size:
+    # exercises c_stride > c and non-zero channel offsets (zero-copy concat views)
+    wide = ops.NHWC.from_nchw(torch.cat(xs + [torch.randn(n, 8, h, w, generator=g)], 1).to(cuda_device))
+    srcs, off = [], 0
+    for c in src_channels:
+        srcs.append(wide.slice(off, c))
+        off += c
+    wp, bp = ops.pack_conv1x1(wgt, bias, src_channels, cuda_device)
+    dst_buf = ops.NHWC.empty(n, h, w, cout + 16, cuda_device)
+    dst_buf.buf.fill_(-77.0)
+    dst = dst_buf.slice(8, cout)
+    ops.conv1x1(srcs, wp, bp, act, dst)
+    torch.cuda.synchronize()
+    _close(dst.to_nchw(), ref, f"conv1x1 {src_channels}->{cout}")
+    # neighbours of the destination slice must be untouched
+    assert (dst_buf.buf[..., :8] == -77.0).all() and (dst_buf.buf[..., 8 + cout:] == -77.0).all()
+
+
+def test_conv1x1_fused_upsample(cuda_device):
+    from maf_yolo_b200 import ops
+
+    g = torch.Generator().manual_seed(7)
+    n, cin, cout, h, w = 2, 96, 192, 20, 20
+    x = torch.randn(n, cin, h, w, generator=g).half().float()
+    wgt = (torch.randn(cout, cin, generator=g) / cin ** 0.5).half().float()
+    bias = torch.randn(cout, generator=g)
+    ref = F.silu(F.conv2d(x, wgt[:, :, None, None], bias))
+    src = ops.NHWC.from_nchw(x.to(cuda_device))
+    wp, bp = ops.pack_conv1x1(wgt, bias, [cin], cuda_device)
+    dst = ops.NHWC.empty(n, h, w, cout, cuda_device)
+    up = ops.NHWC.empty(n, 2 * h, 2 * w, cout, cuda_device)
+    ops.conv1x1([src], wp, bp, "silu", dst, up)
+    torch.cuda.synchronize()
+    _close(dst.to_nchw(), ref, "conv1x1+up: main output")
+    assert torch.equal(up.to_nchw(), F.interpolate(dst.to_nchw(), scale_factor=2, mode="nearest")), "upsampled copy"
+
+
+CONV3X3_CASES = [
+    # (cin, cout, h, w, n, act)
+    (24, 48, 64, 64, 1, "relu"),      # L1-like: cin < 64
+    (48, 48, 40, 40, 2, "relu"),
+    (96, 64, 40, 40, 1, "silu"),      # cin = 64 + 32 tail
+    (128, 128, 40, 40, 2, "silu"),
+    (192, 96, 40, 40, 1, "silu"),
+    (192, 192, 20, 20, 3, "relu"),    # tiles straddle images (100 px / image)
+    (384, 256, 20, 20, 1, "silu"),    # M variant, 54 K blocks
+    (32, 64, 12, 20, 1, "relu"),      # non-square, M = 60 < 128
+]
+
+
+@pytest.mark.parametrize("cin,cout,h,w,n,act", CONV3X3_CASES)
+def test_conv3x3s2(cuda_device, cin, cout, h, w, n, act):
+    from maf_yolo_b200 import ops
+
+    g = torch.Generator().manual_seed(99 + cin + cout)
+    x = torch.randn(n, cin, h, w, generator=g).half().float()
+    wgt = (torch.randn(cout, cin, 3, 3, generator=g) / (9 * cin) ** 0.5).half().float()
+    bias = torch.randn(cout, generator=g)
+    ref = _act_ref(F.conv2d(x, wgt, bias, stride=2, padding=1), act)
+    src = ops.NHWC.from_nchw(x.to(cuda_device))
+    wp, bp = ops.pack_conv3x3(wgt, bias, cuda_device)
+    dst = ops.NHWC.empty(n, h // 2, w // 2, cout, cuda_device)
+    ops.conv3x3s2(src, wp, bp, act, dst)
+    torch.cuda.synchronize()
+    _close(dst.to_nchw(), ref, f"conv3x3s2 {cin}->{cout} @{h}x{w}")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.uint8])
+@pytest.mark.parametrize("cout", [24, 32, 48])
+def test_stem_conv(cuda_device, dtype, cout):
+    from maf_yolo_b200 import ops
+
+    g = torch.Generator().manual_seed(5 + cout)
+    n, h, w = 2, 64, 96
+    if dtype == torch.uint8:
+        x = torch.randint(0, 256, (n, 3, h, w), generator=g, dtype=torch.uint8)
+        xf = x.float() / 255
+    else:
+        x = torch.rand(n, 3, h, w, generator=g).to(dtype)
+        xf = x.float()
+    wgt = torch.randn(cout, 3, 3, 3, generator=g) / 27 ** 0.5
+    bias = torch.randn(cout, generator=g)
+    ref = F.relu(F.conv2d(xf, wgt, bias, stride=2, padding=1))
+    wp, bp = ops.pack_stem(wgt, bias, cuda_device)
+    dst = ops.NHWC.empty(n, h // 2, w // 2, cout, cuda_device)
+    ops.stem_conv3x3s2(x.to(cuda_device), wp, bp, "relu", dst)
+    torch.cuda.synchronize()
+    _close(dst.to_nchw(), ref, f"stem conv {dtype} cout={cout}")
+
+
+DW_CASES = [(72, 3, 40, 40, 2, "silu"), (144, 5, 40, 40, 1, "silu"), (288, 7, 40, 40, 1, "silu"),
+            (576, 9, 20, 20, 2, "silu"), (128, 5, 24, 20, 1, "none"), (192, 9, 20, 20, 1, "none"),
+            (64, 7, 10, 15, 1, "silu"), (96, 3, 7, 13, 1, "relu")]
+
+
+@pytest.mark.parametrize("c,k,h,w,n,act", DW_CASES)
+def test_dwconv(cuda_device, c, k, h, w, n, act):
+    from maf_yolo_b200 import ops
+
+    g = torch.Generator().manual_seed(31 + c + k)
+    x = torch.randn(n, c, h, w, generator=g).half().float()
+    wgt = torch.randn(c, 1, k, k, generator=g) / k
+    bias = torch.randn(c, generator=g)
+    ref = _act_ref(F.conv2d(x, wgt, bias, padding=k // 2, groups=c), act)
+    wide = ops.NHWC.from_nchw(torch.cat([torch.zeros(n, 8, h, w), x], 1).to(cuda_device))
+    src = wide.slice(8, c)
+    wp, bp = ops.pack_dw(wgt, bias, cuda_device)
+    dst = ops.NHWC.empty(n, h, w, c, cuda_device)
+    ops.dwconv(src, wp, bp, k, act, dst)
+    torch.cuda.synchronize()
+    _close(dst.to_nchw(), ref, f"dwconv c={c} k={k}")
+
+
+def test_pool_upsample_layout(cuda_device):
+    from maf_yolo_b200 import ops
+
+    g = torch.Generator().manual_seed(3)
+    n, c, h, w = 2, 48, 20, 24
+    x = torch.randn(n, c, h, w, generator=g).half().float()
+    src = ops.NHWC.from_nchw(x.to(cuda_device))
+    # 2x2 max pool: exact
+    dst = ops.NHWC.empty(n, h // 2, w // 2, c, cuda_device)
+    ops.maxpool2x2(src, dst)
+    assert torch.equal(dst.to_nchw().cpu(), F.max_pool2d(x, 2, 2))
+    # SPPF chain: exact, written into channel slices of one concat buffer
+    cat = ops.NHWC.empty(n, h, w, 4 * c, cuda_device)
+    ops.sppf_pool(src, cat.slice(c, c), cat.slice(2 * c, c), cat.slice(3 * c, c))
+    y1 = F.max_pool2d(x, 5, 1, 2)
+    y2 = F.max_pool2d(y1, 5, 1, 2)
+    y3 = F.max_pool2d(y2, 5, 1, 2)
+    assert torch.equal(cat.slice(c, c).to_nchw().cpu(), y1)
+    assert torch.equal(cat.slice(2 * c, c).to_nchw().cpu(), y2)
+    assert torch.equal(cat.slice(3 * c, c).to_nchw().cpu(), y3)
+    # nearest upsample: exact
+    up = ops.NHWC.empty(n, 2 * h, 2 * w, c, cuda_device)
+    ops.upsample2x(src, up)
+    assert torch.equal(up.to_nchw().cpu(), F.interpolate(x, scale_factor=2, mode="nearest"))
+    # layout converters round-trip
+    xin = torch.randn(n, 37, h, w, generator=g)
+    d2 = ops.NHWC.empty(n, h, w, 37, cuda_device)
+    ops.nchw_to_nhwc(xin.to(cuda_device), d2)
+    assert torch.equal(d2.to_nchw().cpu(), xin.half().float())
+    back = torch.empty(n, 37, h, w, device=cuda_device)
+    ops.nhwc_to_nchw(d2, back)
+    torch.cuda.synchronize()
+    assert torch.equal(back.cpu(), xin.half().float())
+
+
+def _decode_ref(cls_logits, regs, strides, reg_max=16):
+    """Plain torch fp32 restatement of Detect_yaml eval branch (yolo.py:355-396) + the head sigmoid."""
+    outs_c, outs_r, pts, sts = [], [], [], []
+    for cl, rg, s in zip(cls_logits, regs, strides):
+        b, _, h, w = cl.shape
+        l = h * w
+        r = rg.reshape(b, 4, reg_max + 1, l).permute(0, 2, 1, 3)
+        r = (F.softmax(r, dim=1) * torch.arange(reg_max + 1.0).view(1, -1, 1, 1)).sum(1)
+        outs_c.append(torch.sigmoid(cl).reshape(b, -1, l))
+        outs_r.append(r.reshape(b, 4, l))
+        sy, sx = torch.meshgrid(torch.arange(h) + 0.5, torch.arange(w) + 0.5, indexing="ij")
+        pts.append(torch.stack([sx, sy], -1).reshape(-1, 2))
+        sts.append(torch.full((l, 1), float(s)))
+    c = torch.cat(outs_c, -1).permute(0, 2, 1)
+    r = torch.cat(outs_r, -1).permute(0, 2, 1)
+    pts, sts = torch.cat(pts), torch.cat(sts)
+    x1y1, x2y2 = pts - r[..., :2], pts + r[..., 2:]
+    box = torch.cat([(x1y1 + x2y2) / 2, x2y2 - x1y1], -1) * sts
+    return torch.cat([box, torch.ones(c.shape[0], c.shape[1], 1), c], -1)
+
+
+def test_head_decode(cuda_device):
+    from maf_yolo_b200 import ops
+
+    g = torch.Generator().manual_seed(17)
+    n, nc = 2, 80
+    sizes, strides = [(16, 24), (8, 12), (5, 6)], [8.0, 16.0, 32.0]
+    cls = [(torch.randn(n, nc, h, w, generator=g) * 2 - 3).half().float() for h, w in sizes]
+    reg = [(torch.randn(n, 68, h, w, generator=g) * 2).half().float() for h, w in sizes]
+    ref = _decode_ref(cls, reg, strides)
+    pred = torch.empty(ref.shape, device=cuda_device)
+    ops.head_decode([ops.NHWC.from_nchw(t.to(cuda_device)) for t in cls],
+                    [ops.NHWC.from_nchw(t.to(cuda_device)) for t in reg], strides, 16, pred)
+    torch.cuda.synchronize()
+    # fp32 in / fp32 out: boxes within 1e-3 relative to max(1,|ref|), scores within 1e-5
+    _close(pred[..., :4], ref[..., :4], "decode boxes", rtol=1e-5, atol=1e-3)
+    assert (pred[..., 4] == 1).all()
+    _close(pred[..., 5:], ref[..., 5:], "decode scores", rtol=0, atol=1e-6)
+
+
+def _synthetic_pred(b, a, nc, seed, dup=True):
+    g = torch.Generator().manual_seed(seed)
+    pred = torch.zeros(b, a, 5 + nc)
+    pred[..., 0:2] = torch.rand(b, a, 2, generator=g) * 640
+    pred[..., 2:4] = torch.rand(b, a, 2, generator=g) * 200 + 4
+    pred[..., 4] = 1.0
+    pred[..., 5:] = torch.sigmoid(torch.randn(b, a, nc, generator=g) * 1.5 - 8)
+    if dup and a > 120:  # exact score ties and identical boxes
+        pred[0, 100:110] = pred[0, 90:100]
+        pred[0, 110:120, 5:] = pred[0, 90:100, 5:]
+    return pred
+
+
+NMS_CASES = [
+    dict(conf_thres=0.03, iou_thres=0.65, multi_label=True, max_det=300),                      # eval settings
+    dict(conf_thres=0.4, iou_thres=0.45, multi_label=False, max_det=1000),                     # tools/infer.py defaults
+    dict(conf_thres=0.01, iou_thres=0.45, multi_label=False, max_det=1000),
+    dict(conf_thres=0.03, iou_thres=0.65, multi_label=True, agnostic=True, classes=[1, 5, 7]),
+    dict(conf_thres=0.001, iou_thres=0.65, multi_label=True, max_det=300),                     # > 8192 candidates: global sort path
+    dict(conf_thres=0.001, iou_thres=0.65, multi_label=True, max_det=300, max_nms=3000),       # max_nms cut
+    dict(conf_thres=0.9999, iou_thres=0.5, multi_label=True),                                  # no candidates at all
+]
+
+
+@pytest.mark.parametrize("kw", NMS_CASES)
+def test_nms_bitexact(cuda_device, kw):
+    from maf_yolo_b200 import nn as mnn
+    from oracle import nms as onms
+
+    pred = _synthetic_pred(3, 8400, 80, seed=1)
+    ref = onms.non_max_suppression(pred.numpy(), **kw)
+    kw2 = dict(kw)
+    max_nms = kw2.pop("max_nms", None)
+    got = mnn.non_max_suppression(pred.to(cuda_device), **kw2, **({"max_nms": max_nms} if max_nms else {}))
+    assert len(got) == len(ref)
+    for i, (gt, rf) in enumerate(zip(got, ref)):
+        assert gt.shape == rf.shape, (i, gt.shape, rf.shape)
+        assert np.array_equal(gt.cpu().numpy(), rf), f"image {i}: NMS output differs from the oracle"
+
+
+def test_nms_obj_and_small(cuda_device):
+    """objectness != 1, a batch where one image is empty, nc == 1 (multi_label is forced off)."""
+    from maf_yolo_b200 import nn as mnn
+    from oracle import nms as onms
+
+    pred = _synthetic_pred(2, 500, 6, seed=9, dup=False)
+    pred[..., 4] = torch.rand(2, 500, generator=torch.Generator().manual_seed(2))
+    pred[..., 5:] = pred[..., 5:] * 50
+    pred[1, :, 4] = 0.0  # second image: nothing passes
+    for kw in (dict(conf_thres=0.05, iou_thres=0.5, multi_label=True), dict(conf_thres=0.05, iou_thres=0.5)):
+        ref = onms.non_max_suppression(pred.numpy(), **kw)
+        got = mnn.non_max_suppression(pred.to(cuda_device), **kw)
+        for gt, rf in zip(got, ref):
+            assert np.array_equal(gt.cpu().numpy(), rf)
+    p1 = _synthetic_pred(1, 300, 1, seed=4, dup=False)
+    p1[..., 5:] = p1[..., 5:] * 200
+    ref = onms.non_max_suppression(p1.numpy(), conf_thres=0.05, iou_thres=0.5, multi_label=True)
+    got = mnn.non_max_suppression(p1.to(cuda_device), conf_thres=0.05, iou_thres=0.5, multi_label=True)
+    assert np.array_equal(got[0].cpu().numpy(), ref[0])
+
+
+def test_error_codes(cuda_device):
+    """The C ABI reports bad arguments through return codes + last_error, never by crashing."""
+    from maf_yolo_b200 import _lib, ops
+
+    a = ops.NHWC.empty(1, 8, 8, 16, cuda_device)
+    b = ops.NHWC.empty(1, 4, 4, 16, cuda_device)
+    w = torch.zeros(16, 64, dtype=torch.float16, device=cuda_device)
+    bias = torch.zeros(16, device=cuda_device)
+    with pytest.raises(_lib.MafError) as e:
+        ops.conv1x1([a], w, bias, "silu", b)  # spatial mismatch
+    assert e.value.code == -1 and "differ" in str(e.value)
+    with pytest.raises(_lib.MafError):
+        ops.dwconv(a, w, bias, 4, "silu", a)  # unsupported kernel size
+    with pytest.raises(_lib.MafError):
+        ops.conv3x3s2(a, w, bias, "silu", a)  # wrong output size
