@@ -313,6 +313,17 @@ extern "C" int32_t mafb200_conv1x1(const maf_tensor* srcs, int32_t n_src, const 
   if (!aligned_f16_view(dst)) return fail(MAF_E_ALIGN, "conv1x1: dst must be 16-B aligned with c_stride %% 8 == 0");
   if (act < MAF_ACT_NONE || act > MAF_ACT_SIGMOID) return fail(MAF_E_ARG, "conv1x1: bad act %d", act);
   if ((reinterpret_cast<uintptr_t>(w_packed) & 15) != 0) return fail(MAF_E_ALIGN, "conv1x1: w_packed not 16-B aligned");
+  for (int s = 0; s < n_src; ++s) {
+    const maf_tensor* t = &srcs[s];
+    if (!valid_f16_view(t)) return fail(MAF_E_ARG, "conv1x1: bad src[%d]", s);
+    if (!aligned_f16_view(t)) return fail(MAF_E_ALIGN, "conv1x1: src[%d] alignment", s);
+    if (!same_nhw(t, dst)) return fail(MAF_E_ARG, "conv1x1: src[%d] n/h/w differ from dst", s);
+  }
+  if (dst_up2x) {
+    if (!valid_f16_view(dst_up2x) || !aligned_f16_view(dst_up2x) || dst_up2x->n != dst->n ||
+        dst_up2x->h != 2 * dst->h || dst_up2x->w != 2 * dst->w || dst_up2x->c != dst->c)
+      return fail(MAF_E_ARG, "conv1x1: dst_up2x must be [n,2h,2w,c] fp16");
+  }
   int32_t rc = require_sm100();
   if (rc) return rc;
 
@@ -322,9 +333,6 @@ extern "C" int32_t mafb200_conv1x1(const maf_tensor* srcs, int32_t n_src, const 
   int total_kb = 0;
   for (int s = 0; s < n_src; ++s) {
     const maf_tensor* t = &srcs[s];
-    if (!valid_f16_view(t)) return fail(MAF_E_ARG, "conv1x1: bad src[%d]", s);
-    if (!aligned_f16_view(t)) return fail(MAF_E_ALIGN, "conv1x1: src[%d] alignment", s);
-    if (!same_nhw(t, dst)) return fail(MAF_E_ARG, "conv1x1: src[%d] n/h/w differ from dst", s);
     rc = encode_a_map_2d(&p.tmA[s], t);
     if (rc) return rc;
     chans[s] = t->c;
@@ -348,9 +356,6 @@ extern "C" int32_t mafb200_conv1x1(const maf_tensor* srcs, int32_t n_src, const 
   p.nsrc = n_src;
   p.act = act;
   if (dst_up2x) {
-    if (!valid_f16_view(dst_up2x) || !aligned_f16_view(dst_up2x) || dst_up2x->n != dst->n ||
-        dst_up2x->h != 2 * dst->h || dst_up2x->w != 2 * dst->w || dst_up2x->c != dst->c)
-      return fail(MAF_E_ARG, "conv1x1: dst_up2x must be [n,2h,2w,c] fp16");
     p.out2 = static_cast<__half*>(dst_up2x->ptr);
     p.out2_ld = dst_up2x->c_stride;
   }

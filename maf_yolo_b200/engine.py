@@ -1,0 +1,378 @@
+"""Static execution plan for the MAF-YOLO forward -> decode path on one B200.
+
+`plan_graph()` turns the resolved topology into a flat list of kernel launches over NHWC fp16
+buffers (no per-forward Python graph walking, no torch ops):
+
+  * Concat / split never move data: producers write channel slices of a shared buffer
+    (RepHDW, MPRep, SPPF — yolov6/layers/common.py:938-946,787-792,123-129) and the MAFPN fusion
+    Concats (configs/yaml/MAF-YOLO-n.yaml:18-42) become multi-source K loops of the consuming 1x1 GEMM.
+  * nn.Upsample is fused into the epilogue of the conv that produces its input (dual store).
+  * buffers get arena offsets from a liveness scan, so the working set is small and L2-friendly.
+
+`Engine` binds a plan to device memory + packed weights and replays it — eagerly or as one CUDA
+graph.  The input tensor is read directly in the reference's format (NCHW fp32/fp16/uint8) by the
+stem kernel; the result is the reference's `[B, A, 5+nc]` fp32 prediction tensor.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+from .fold import Folded
+from .ops import NHWC
+from .topology import Graph, Layer
+
+
+def _ld(c: int) -> int:
+    return (c + 7) // 8 * 8
+
+
+class _Buf:
+    __slots__ = ("h", "w", "ld", "first", "last", "offset", "name")
+
+    def __init__(self, h, w, c, name):
+        self.h, self.w, self.ld, self.name = h, w, _ld(c), name
+        self.first, self.last, self.offset = None, None, None
+
+    def touch(self, idx):
+        self.first = idx if self.first is None else min(self.first, idx)
+        self.last = idx if self.last is None else max(self.last, idx)
+
+    def nbytes(self, batch):
+        return batch * self.h * self.w * self.ld * 2
+
+
+@dataclass(frozen=True)
+class _View:
+    buf: _Buf
+    c_off: int
+    c: int
+
+    def slice(self, off, c):
+        assert off + c <= self.c
+        return _View(self.buf, self.c_off + off, c)
+
+
+@dataclass
+class _Op:
+    kind: str
+    name: str
+    reads: List[_View]
+    writes: List[_View]
+    weight: Optional[str] = None
+    act: str = "none"
+    k: int = 0
+    flops_per_image: int = 0
+    bytes_per_image: int = 0   # algorithmic: activations read once + written once (fp16), weights excluded
+
+
+class Plan:
+    """Kernel-launch schedule + buffer liveness for one (graph, H, W); batch-size independent."""
+
+    def __init__(self, graph: Graph, height: int, width: int):
+        assert height % 32 == 0 and width % 32 == 0, "input size must be a multiple of the largest stride (32)"
+        self.graph, self.height, self.width = graph, height, width
+        self.bufs: List[_Buf] = []
+        self.ops: List[_Op] = []
+        self.level_views: List[Tuple[_View, _View, _View]] = []  # (stem, cls_logits, reg) per head
+        self.layer_out: Dict[int, object] = {}  # yaml layer index -> output view(s)
+        self.anchors = 0
+        self._plan()
+
+    # ---- helpers --------------------------------------------------------------------------------
+    def _buf(self, h, w, c, name) -> _View:
+        b = _Buf(h, w, c, name)
+        self.bufs.append(b)
+        return _View(b, 0, c)
+
+    def _emit(self, kind, name, reads, writes, **kw) -> _Op:
+        idx = len(self.ops)
+        for v in list(reads) + list(writes):
+            v.buf.touch(idx)
+        op = _Op(kind, name, list(reads), list(writes), **kw)
+        px_out = writes[0].buf.h * writes[0].buf.w if writes else 0
+        op.bytes_per_image = sum(2 * v.c * v.buf.h * v.buf.w for v in reads) + sum(
+            2 * v.c * v.buf.h * v.buf.w for v in writes)
+        if kind == "conv1x1":
+            op.flops_per_image = 2 * sum(v.c for v in reads) * writes[0].c * px_out
+        elif kind == "conv3x3s2":
+            op.flops_per_image = 2 * 9 * reads[0].c * writes[0].c * px_out
+        elif kind == "dwconv":
+            op.flops_per_image = 2 * kw["k"] * kw["k"] * writes[0].c * px_out
+        self.ops.append(op)
+        return op
+
+    # ---- the schedule ----------------------------------------------------------------------------
+    def _plan(self):
+        g = self.graph
+        H, W = self.height, self.width
+        up_of: Dict[int, int] = {l.frm[0]: l.i for l in g.layers if l.kind == "upsample"}
+        out: Dict[int, object] = {}  # layer index -> _View | list[_View] | tuple (head)
+
+        def size(l: Layer):
+            return H // l.stride_total, W // l.stride_total
+
+        def srcs_of(l: Layer) -> List[_View]:
+            res: List[_View] = []
+            for s in l.frm:
+                v = out[s]
+                res.extend(v if isinstance(v, list) else [v])
+            return res
+
+        for l in g.layers:
+            i = str(l.i)
+            if l.kind == "repvgg":
+                h, w = size(l)
+                dst = self._buf(h, w, l.c_out, f"L{i}")
+                if l.frm[0] < 0:
+                    op = self._emit("stem", f"L{i}.stem3x3s2", [], [dst], weight=i, act="relu")
+                    op.flops_per_image = 2 * 27 * l.c_out * h * w
+                    op.bytes_per_image += 3 * H * W * 4  # the fp32 NCHW image
+                else:
+                    self._emit("conv3x3s2", f"L{i}.repvgg3x3s2", [out[l.frm[0]]], [dst], weight=i, act="relu")
+                out[l.i] = dst
+            elif l.kind == "convw":
+                h, w = size(l)
+                dst = self._buf(h, w, l.c_out, f"L{i}")
+                self._emit("conv3x3s2", f"L{i}.conv3x3s2", [out[l.frm[0]]], [dst], weight=i + ".block", act="silu")
+                out[l.i] = dst
+            elif l.kind == "rephdw":
+                h, w = size(l)
+                c_, mid = l.c_hidden, l.expand * l.c_hidden
+                cat = self._buf(h, w, (2 + l.depth) * c_, f"L{i}.cat")
+                self._emit("conv1x1", f"L{i}.conv1", srcs_of(l), [cat.slice(0, 2 * c_)], weight=i + ".conv1", act="silu")
+                for j in range(l.depth):
+                    t1 = self._buf(h, w, mid, f"L{i}.m{j}.expand")
+                    self._emit("conv1x1", f"L{i}.m{j}.conv1", [cat.slice((1 + j) * c_, c_)], [t1],
+                               weight=f"{i}.m.{j}.conv1", act="silu")
+                    t2 = self._buf(h, w, mid, f"L{i}.m{j}.dw")
+                    self._emit("dwconv", f"L{i}.m{j}.dw{l.k}", [t1], [t2], weight=f"{i}.m.{j}.dw", act="silu", k=l.k)
+                    self._emit("conv1x1", f"L{i}.m{j}.one_conv", [t2], [cat.slice((2 + j) * c_, c_)],
+                               weight=f"{i}.m.{j}.one_conv", act="silu")
+                dst = self._buf(h, w, l.c_out, f"L{i}")
+                writes = [dst]
+                if l.i in up_of:  # fuse the following nn.Upsample into this conv's epilogue
+                    up = self._buf(2 * h, 2 * w, l.c_out, f"L{up_of[l.i]}.up")
+                    writes.append(up)
+                    out[up_of[l.i]] = up
+                self._emit("conv1x1", f"L{i}.conv2", [cat], writes, weight=i + ".conv2", act="silu")
+                out[l.i] = dst
+            elif l.kind == "mprep":
+                h, w = size(l)
+                src = out[l.frm[0]]
+                pooled = self._buf(h, w, l.c_in[0], f"L{i}.pool")
+                self._emit("maxpool2x2", f"L{i}.maxpool", [src], [pooled])
+                dst = self._buf(h, w, l.c_out, f"L{i}")
+                half = l.c_out // 2
+                self._emit("conv1x1", f"L{i}.conv1", [pooled], [dst.slice(0, half)], weight=i + ".conv1", act="silu")
+                self._emit("conv3x3s2", f"L{i}.repvgg3x3s2", [src], [dst.slice(half, half)], weight=i + ".conv2",
+                           act="relu")
+                out[l.i] = dst
+            elif l.kind == "sppf":
+                h, w = size(l)
+                c_ = l.c_hidden
+                cat = self._buf(h, w, 4 * c_, f"L{i}.cat")
+                self._emit("conv1x1", f"L{i}.cv1", srcs_of(l), [cat.slice(0, c_)], weight=i + ".cv1", act="silu")
+                self._emit("sppf_pool", f"L{i}.pool5x3", [cat.slice(0, c_)],
+                           [cat.slice(c_, c_), cat.slice(2 * c_, c_), cat.slice(3 * c_, c_)])
+                dst = self._buf(h, w, l.c_out, f"L{i}")
+                self._emit("conv1x1", f"L{i}.cv2", [cat], [dst], weight=i + ".cv2", act="silu")
+                out[l.i] = dst
+            elif l.kind == "concat":
+                views = srcs_of(l)
+                if len(views) > 4:
+                    raise NotImplementedError("a fusion stage with more than 4 inputs is outside MAF-YOLO's topology")
+                out[l.i] = views
+            elif l.kind == "upsample":
+                if l.i not in out:  # producer could not dual-store: standalone kernel
+                    src = out[l.frm[0]]
+                    h, w = size(l)
+                    dst = self._buf(h, w, l.c_out, f"L{i}.up")
+                    self._emit("upsample2x", f"L{i}.upsample", [src], [dst])
+                    out[l.i] = dst
+            elif l.kind == "head":
+                h, w = size(l)
+                c = l.c_out
+                stem = self._buf(h, w, c, f"L{i}.stem")
+                self._emit("conv1x1", f"L{i}.stem", srcs_of(l), [stem], weight=i + ".stem", act="silu")
+                res = {}
+                for br, cout in (("cls", g.nc), ("reg", 4 * (l.reg_max + 1))):
+                    t = self._buf(h, w, c, f"L{i}.{br}_dw")
+                    self._emit("dwconv", f"L{i}.{br}_dw{l.k}", [stem], [t], weight=f"{i}.{br}_dw", act="none", k=l.k)
+                    f2 = self._buf(h, w, c, f"L{i}.{br}_s")
+                    self._emit("conv1x1", f"L{i}.{br}_s", [t], [f2], weight=f"{i}.{br}_s", act="silu")
+                    o = self._buf(h, w, cout, f"L{i}.{br}_pred")
+                    self._emit("conv1x1", f"L{i}.{br}_pred", [f2], [o], weight=f"{i}.{br}_pred", act="none")
+                    res[br] = o
+                out[l.i] = (stem, res["cls"], res["reg"])
+                self.level_views.append(out[l.i])
+                self.anchors += h * w
+            elif l.kind == "out":
+                cls = [out[s][1] for s in l.frm]
+                reg = [out[s][2] for s in l.frm]
+                op = self._emit("decode", "detect.decode", cls + reg, [])
+                op.bytes_per_image += self.anchors * (5 + g.nc) * 4
+            else:
+                raise NotImplementedError(l.kind)
+        self.layer_out = out
+
+    # ---- arena ------------------------------------------------------------------------------------
+    def assign_offsets(self, batch: int, align: int = 1024, reuse: bool = True) -> int:
+        """Greedy interval allocation: buffers whose live ranges do not overlap share memory.
+        reuse=False gives every buffer its own range (debugging: intermediates stay readable)."""
+        live: List[_Buf] = []
+        total = 0
+        for b in sorted(self.bufs, key=lambda b: (b.first, -b.nbytes(batch))):
+            if reuse:
+                live = [x for x in live if x.last >= b.first]
+            size = (b.nbytes(batch) + align - 1) // align * align
+            off = 0
+            for x in sorted(live, key=lambda x: x.offset):
+                xs = (x.nbytes(batch) + align - 1) // align * align
+                if off + size <= x.offset:
+                    break
+                off = max(off, x.offset + xs)
+            b.offset = off
+            live.append(b)
+            total = max(total, off + size)
+        return total
+
+    # ---- accounting (DESIGN.md / bench.py roofline) ---------------------------------------------------
+    def flops_per_image(self) -> int:
+        return sum(o.flops_per_image for o in self.ops)
+
+    def bytes_per_image(self) -> int:
+        return sum(o.bytes_per_image for o in self.ops)
+
+    def summary(self) -> List[dict]:
+        return [dict(name=o.name, kind=o.kind, flops=o.flops_per_image, bytes=o.bytes_per_image) for o in self.ops]
+
+
+class Engine:
+    """A plan bound to one device, one batch size and one set of folded weights."""
+
+    def __init__(self, graph: Graph, folded: Folded, batch: int, height: int = 640, width: int = 640,
+                 device: Optional[torch.device] = None, use_cuda_graph: bool = True, reuse_buffers: bool = True):
+        if not torch.cuda.is_available():
+            raise RuntimeError("maf_yolo_b200.Engine needs a B200 GPU: the hot path has no CPU fallback")
+        self.device = torch.device(device if device is not None else "cuda")
+        self.graph, self.batch, self.height, self.width = graph, batch, height, width
+        self.plan = Plan(graph, height, width)
+        self.use_cuda_graph = use_cuda_graph
+        with torch.cuda.device(self.device):
+            nbytes = self.plan.assign_offsets(batch, reuse=reuse_buffers)
+            self.arena = torch.empty(nbytes // 2, dtype=torch.float16, device=self.device)
+            self.pred = torch.empty((batch, self.plan.anchors, 5 + graph.nc), dtype=torch.float32, device=self.device)
+            self._views: Dict[Tuple[int, int, int], NHWC] = {}
+            self._weights: Dict[str, Tuple[torch.Tensor, torch.Tensor]] = {}
+            self._x: Optional[torch.Tensor] = None
+            self._calls: List[Callable[[], None]] = [self._bind(op, folded) for op in self.plan.ops]
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._graph_x_ptr = None
+        self.launches_per_forward = len(self._calls)
+
+    # ---- binding ----------------------------------------------------------------------------------
+    def view(self, v: _View) -> NHWC:
+        key = (id(v.buf), v.c_off, v.c)
+        hit = self._views.get(key)
+        if hit is None:
+            b = v.buf
+            numel = self.batch * b.h * b.w * b.ld
+            t = self.arena[b.offset // 2: b.offset // 2 + numel].view(self.batch, b.h, b.w, b.ld)
+            hit = NHWC(t, v.c_off, v.c)
+            self._views[key] = hit
+        return hit
+
+    def _bind(self, op: _Op, folded: Folded) -> Callable[[], None]:
+        dev = self.device
+        reads = [self.view(v) for v in op.reads]
+        writes = [self.view(v) for v in op.writes]
+        if op.kind == "stem":
+            w, b = ops.pack_stem(*folded[op.weight], device=dev)
+            self._weights[op.name] = (w, b)
+            return lambda: ops.stem_conv3x3s2(self._x, w, b, op.act, writes[0])
+        if op.kind == "conv1x1":
+            wt, bs = folded[op.weight]
+            w, b = ops.pack_conv1x1(wt.reshape(wt.shape[0], -1), bs, [r.c for r in reads], device=dev)
+            self._weights[op.name] = (w, b)
+            up = writes[1] if len(writes) > 1 else None
+            return lambda: ops.conv1x1(reads, w, b, op.act, writes[0], up)
+        if op.kind == "conv3x3s2":
+            w, b = ops.pack_conv3x3(*folded[op.weight], device=dev)
+            self._weights[op.name] = (w, b)
+            return lambda: ops.conv3x3s2(reads[0], w, b, op.act, writes[0])
+        if op.kind == "dwconv":
+            w, b = ops.pack_dw(*folded[op.weight], device=dev)
+            self._weights[op.name] = (w, b)
+            return lambda: ops.dwconv(reads[0], w, b, op.k, op.act, writes[0])
+        if op.kind == "maxpool2x2":
+            return lambda: ops.maxpool2x2(reads[0], writes[0])
+        if op.kind == "sppf_pool":
+            return lambda: ops.sppf_pool(reads[0], writes[0], writes[1], writes[2])
+        if op.kind == "upsample2x":
+            return lambda: ops.upsample2x(reads[0], writes[0])
+        if op.kind == "decode":
+            nl = len(reads) // 2
+            strides = [float(s) for s in self.graph.strides]
+            reg_max = self.graph.layers[self.graph.head_layers[0]].reg_max
+            return lambda: ops.head_decode(reads[:nl], reads[nl:], strides, reg_max, self.pred)
+        raise NotImplementedError(op.kind)
+
+    # ---- execution ----------------------------------------------------------------------------------
+    def _check_input(self, x: torch.Tensor):
+        if tuple(x.shape) != (self.batch, 3, self.height, self.width):
+            raise ValueError(f"engine was planned for input {(self.batch, 3, self.height, self.width)}, got {tuple(x.shape)}")
+        if x.device != self.pred.device:
+            raise ValueError(f"input is on {x.device}, engine on {self.pred.device}")
+        if x.dtype not in (torch.float32, torch.float16, torch.uint8):
+            raise TypeError(f"unsupported input dtype {x.dtype}")
+        return x if x.is_contiguous() else x.contiguous()
+
+    def run_eager(self, x: torch.Tensor) -> torch.Tensor:
+        self._x = self._check_input(x)
+        for call in self._calls:
+            call()
+        return self.pred
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """x: NCHW fp32/fp16 in [0,1] or uint8 -> pred [B, A, 5+nc] fp32 (engine-owned buffer)."""
+        if not self.use_cuda_graph:
+            return self.run_eager(x)
+        x = self._check_input(x)
+        self._x = x
+        # The stem kernel reads the caller's tensor (its address changes per call), so it is launched
+        # eagerly; everything behind it only touches engine-owned memory and is replayed as one graph.
+        self._calls[0]()
+        if self._graph is None:
+            for call in self._calls[1:]:  # warm-up outside capture (sets func attributes, loads modules)
+                call()
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for call in self._calls[1:]:
+                    call()
+            self._graph = g
+            self._calls[0]()
+        self._graph.replay()
+        return self.pred
+
+    __call__ = forward
+
+    def head_outputs(self) -> List[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]:
+        """(stem, cls_logits, reg) of each level as NCHW fp32 copies (debug / featmaps)."""
+        return [tuple(self.view(v).to_nchw() for v in lv) for lv in self.plan.level_views]
+
+    def layer_output(self, i: int) -> torch.Tensor:
+        """NCHW fp32 copy of yaml layer i's output (only meaningful with reuse_buffers=False)."""
+        v = self.plan.layer_out[i]
+        if isinstance(v, list):
+            return torch.cat([self.view(x).to_nchw() for x in v], 1)
+        if isinstance(v, tuple):
+            raise ValueError("head layers have three outputs: use head_outputs()")
+        return self.view(v).to_nchw()
+
+    def arena_bytes(self) -> int:
+        return self.arena.numel() * 2

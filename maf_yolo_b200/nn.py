@@ -71,3 +71,92 @@ def non_max_suppression(prediction: torch.Tensor, conf_thres: float = 0.25, iou_
                                             max_det, max_nms)
     counts = count.tolist()  # the one device->host sync (the reference syncs once per image)
     return [det[i, :n] for i, n in enumerate(counts)]
+
+
+# ------------------------------------------------------------------------------------------------
+# whole-model drop-in
+# ------------------------------------------------------------------------------------------------
+class B200DetectModel(torch.nn.Module):
+    """Drop-in for the reference `Model` (yolov6/models/yolo.py:122-217) in eval mode.
+
+    forward(x, val_loss=False) -> [pred, featmaps]:  pred is the `[B, A, 5+nc]` fp32 tensor of
+    Detect_yaml's eval branch (yolo.py:355-396); featmaps — unused by every caller
+    (yolov6/core/evaler.py:168, yolov6/layers/common.py:368) — is [] unless `return_featmaps`.
+    Keeps the attributes callers read: `stride`, `nc`, `names` (evaler.py:94,151,246).
+    `.half()` / `.float()` (evaler.py:112) are accepted and change nothing: the compute type is
+    fixed (fp16 operands, fp32 accumulate) and the output is fp32, as the reference's is.
+    Engines (plan + arena + CUDA graph) are built lazily per (batch, H, W, device).
+    """
+
+    def __init__(self, graph, folded, names=None, use_cuda_graph: bool = True, return_featmaps: bool = False):
+        super().__init__()
+        self.graph = graph
+        self.folded = folded
+        self.nc = graph.nc
+        self.names = names if names is not None else [str(i) for i in range(graph.nc)]
+        self.stride = torch.tensor(graph.strides)
+        self.use_cuda_graph = use_cuda_graph
+        self.return_featmaps = return_featmaps
+        self._engines = {}
+        self.training = False
+
+    # the reference evaler calls these; weights are already packed, nothing to cast
+    def half(self):
+        return self
+
+    def float(self):
+        return self
+
+    def train(self, mode: bool = True):
+        if mode:
+            raise RuntimeError("B200DetectModel is inference-only (deploy-form folded weights)")
+        return super().train(False)
+
+    def engine_for(self, x: torch.Tensor):
+        from .engine import Engine
+
+        b, _, h, w = x.shape
+        key = (b, h, w, str(x.device))
+        eng = self._engines.get(key)
+        if eng is None:
+            eng = Engine(self.graph, self.folded, b, h, w, x.device, self.use_cuda_graph)
+            self._engines[key] = eng
+        return eng
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, val_loss: bool = False):
+        if val_loss:
+            raise NotImplementedError("val_loss=True is the training-time branch (yolo.py:333-354); inference only here")
+        if not x.is_cuda:
+            raise RuntimeError("B200DetectModel needs a CUDA input tensor: there is no CPU fallback on this path")
+        eng = self.engine_for(x)
+        with torch.cuda.device(x.device):
+            pred = eng.forward(x)
+            feats = eng.head_outputs() if self.return_featmaps else []
+        return [pred, feats]
+
+
+def from_state_dict(state_dict, variant_or_yaml="n", nc: int = 80, bn_eps: float = 1e-3, **kw) -> B200DetectModel:
+    """Builds the drop-in from reference weights (train- or deploy-form `state_dict`)."""
+    from .fold import fold_state_dict
+    from .topology import build_graph
+
+    graph = build_graph(variant_or_yaml, nc)
+    return B200DetectModel(graph, fold_state_dict(graph, state_dict, bn_eps), **kw)
+
+
+def convert(model: torch.nn.Module, **kw) -> B200DetectModel:
+    """Post-construction model surgery, the reference's own extension idiom (evaler.py:101-109):
+    takes a live reference `Model` (train or deploy form, any device) and returns the B200 drop-in.
+    Reads the topology from `model.yaml` and BatchNorm eps from the modules."""
+    rows = getattr(model, "yaml", None)
+    if rows is None:
+        raise TypeError("convert() expects a yaml-built reference Model (model.yaml missing)")
+    nc = getattr(getattr(model, "detect", None), "nc", None) or kw.pop("nc", 80)
+    eps = 1e-3
+    for m in model.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            eps = m.eps
+            break
+    names = getattr(model, "names", None)
+    return from_state_dict(model.state_dict(), rows, nc, eps, names=names, **kw)

@@ -253,17 +253,7 @@ def test_head_decode(cuda_device):
     _close(pred[..., 5:], ref[..., 5:], "decode scores", rtol=0, atol=1e-6)
 
 
-def _synthetic_pred(b, a, nc, seed, dup=True):
-    g = torch.Generator().manual_seed(seed)
-    pred = torch.zeros(b, a, 5 + nc)
-    pred[..., 0:2] = torch.rand(b, a, 2, generator=g) * 640
-    pred[..., 2:4] = torch.rand(b, a, 2, generator=g) * 200 + 4
-    pred[..., 4] = 1.0
-    pred[..., 5:] = torch.sigmoid(torch.randn(b, a, nc, generator=g) * 1.5 - 8)
-    if dup and a > 120:  # exact score ties and identical boxes
-        pred[0, 100:110] = pred[0, 90:100]
-        pred[0, 110:120, 5:] = pred[0, 90:100, 5:]
-    return pred
+from tests._synthetic import synthetic_pred as _synthetic_pred  # noqa: E402
 
 
 NMS_CASES = [
