@@ -63,7 +63,8 @@ def main():
         print(f"| {k} | {f[0]} | {f[1]:.1f} | {f[1] / tot:.3f} | {f[2] / (f[1] / 1e6):.0f} | {f[2] / (f[1] / 1e6) / a.peak:.3f} | {f[3] / (f[1] / 1e6):.1f} |")
     rest = [d for d in data[start:] if "mafb200" in d["Kernel Name"]][len(plan.ops):len(plan.ops) + 2]
     for d in rest:
-        print(f"\n(next launch: {re.sub(chr(40) + '.*', '', d['Kernel Name'])} {float(d['Metric Value'].replace(',', '')) / 1e3:.1f} us)")
+        nm = d["Kernel Name"].split("(")[0]
+        print(f"\n(next launch: {nm} {float(d['Metric Value'].replace(',', '')) / 1e3:.1f} us)")
 
 
 if __name__ == "__main__":
