@@ -84,7 +84,7 @@ MAFB200_API int32_t mafb200_device_ok(int32_t device);
 
 /* ---- packed-weight geometry (pure host arithmetic; usable without a GPU) -------------------
  * A conv with `cout` output channels is computed as ceil-split N tiles of `tile_n` columns
- * (tile_n % 16 == 0, tile_n <= 256).  Packed weights are fp16 [n_tiles*tile_n][k_packed],
+ * (tile_n % 16 == 0, tile_n <= 128).  Packed weights are fp16 [n_tiles*tile_n][k_packed],
  * row = output channel (zero rows beyond cout), columns = for each source s (1x1) or each tap
  * (ky,kx) row-major (3x3) a zero-padded block of round_up(C, 64) input channels.
  * Bias is fp32 [n_tiles*tile_n], zero padded. */

@@ -92,8 +92,8 @@ __global__ void __launch_bounds__(128)
     for (int r = 0; r < R; ++r) {
       const int x = x0 + r;
       if (x >= W) continue;
-      const float a = apply_act(acc[i][r].x, act);
-      const float c = apply_act(acc[i][r].y, act);
+      const float a = apply_act_fast(acc[i][r].x, act);
+      const float c = apply_act_fast(acc[i][r].y, act);
       *reinterpret_cast<__half2*>(out_b + (static_cast<size_t>(y) * W + x) * out_ld) = __floats2half2_rn(a, c);
     }
   }

@@ -13,10 +13,13 @@
 // One CTA computes one 128 x tile_n output tile:
 //   warp 0 / lane 0 : TMA producer (A tile 128x64 + W tile tile_n x 64 per stage, SWIZZLE_128B)
 //   warp 1 / lane 0 : tcgen05.mma issuer (UMMA 128 x tile_n x 16, 4 per stage), commits free the stage
-//   all 4 warps     : epilogue — tcgen05.ld 32x32b (one output row per thread) -> +bias -> act ->
-//                     fp16 -> 16-byte global stores (optionally also the x2 nearest-upsampled copy)
-// Several CTAs are resident per SM (smem <= ~100 KB, TMEM <= 256 columns each), so one CTA's
-// epilogue overlaps its neighbours' loads; K is tiny here (1-12 blocks), the kernel is HBM-bound.
+//   all 8 warps     : epilogue — warp w owns TMEM lanes 32*(w%4).. (one output row per thread) and
+//                     every other 32-column group (w/4): tcgen05.ld 32x32b.x32 -> +bias -> act
+//                     (fast-math SiLU: 2 MUFU/element) -> fp16 -> 4 x 16-byte global stores
+//                     (optionally also the x2 nearest-upsampled copy)
+// K is tiny here (1-12 blocks of 64) and N <= 128 per tile, so the kernel is epilogue/HBM-bound:
+// tiles are capped at 128 columns (<= 128 TMEM columns) so that 4 CTAs = 32 epilogue warps are
+// resident per SM and one CTA's epilogue overlaps its neighbours' TMA loads and MMAs.
 #include <string.h>
 
 #include "common.cuh"
@@ -46,7 +49,7 @@ struct GemmParams {
 };
 
 template <bool kIm2col>
-__global__ void __launch_bounds__(128) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+__global__ void __launch_bounds__(256) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -147,15 +150,17 @@ __global__ void __launch_bounds__(128) gemm_tc_kernel(const __grid_constant__ Ge
     tc_commit(tmem_full_bar);
   }
 
-  // ---- epilogue (all 128 threads; thread t owns output row m0 + t == TMEM lane t) ----------------
+  // ---- epilogue (all 256 threads; thread t owns output row m0 + (t % 128) == TMEM lane t % 128) ----
   __syncwarp();
   mbar_wait(tmem_full_bar, 0);
   tc_fence_after_sync();
 
-  const int row = warp * 32 + lane;
+  const int quarter = warp & 3;        // TMEM lane quarter this warp may access
+  const int col_group = warp >> 2;     // which 32-column groups (even / odd) this warp handles
+  const int row = quarter * 32 + lane;
   const int m = m0 + row;
   const bool row_ok = m < p.M;
-  const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
   __half* orow = p.out + static_cast<size_t>(row_ok ? m : 0) * p.out_ld;
   __half* urow = nullptr;
   if (p.out2 != nullptr && row_ok) {
@@ -168,50 +173,52 @@ __global__ void __launch_bounds__(128) gemm_tc_kernel(const __grid_constant__ Ge
   }
   const size_t up_dx = p.out2_ld;
   const size_t up_dy = static_cast<size_t>(2) * p.out_w * p.out2_ld;
+  const int act = p.act;
 
 #pragma unroll 1
-  for (int c = 0; c < p.tile_n; c += 16) {
-    uint32_t r[16];
+  for (int c = col_group * 32; c < p.tile_n; c += 64) {
+    uint32_t r[32];
     __syncwarp();  // tcgen05.ld is .sync.aligned: the warp must be converged here
-    tmem_ld_32x32b_x16(taddr + c, r);
+    tmem_ld_32x32b_x32(taddr + c, r);
     tmem_ld_wait();
     const int n = n0 + c;
     if (row_ok && n < p.N) {
-    float v[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = apply_act(__uint_as_float(r[j]) + s_bias[c + j], p.act);
+      for (int g = 0; g < 4; ++g) {
+        const int ng = n + 8 * g;
+        if (c + 8 * g >= p.tile_n) break;  // tile_n is a multiple of 16: the upper half of the last group may be unused
+        float v[8];
 #pragma unroll
-    for (int g = 0; g < 2; ++g) {
-      const int ng = n + 8 * g;
-      if (ng + 8 <= p.N) {
-        uint4 pk;
-        pk.x = pack_half2(v[8 * g + 0], v[8 * g + 1]);
-        pk.y = pack_half2(v[8 * g + 2], v[8 * g + 3]);
-        pk.z = pack_half2(v[8 * g + 4], v[8 * g + 5]);
-        pk.w = pack_half2(v[8 * g + 6], v[8 * g + 7]);
-        *reinterpret_cast<uint4*>(orow + ng) = pk;
-        if (urow != nullptr) {
-          *reinterpret_cast<uint4*>(urow + ng) = pk;
-          *reinterpret_cast<uint4*>(urow + up_dx + ng) = pk;
-          *reinterpret_cast<uint4*>(urow + up_dy + ng) = pk;
-          *reinterpret_cast<uint4*>(urow + up_dy + up_dx + ng) = pk;
-        }
-      } else {
+        for (int j = 0; j < 8; ++j) v[j] = apply_act_fast(__uint_as_float(r[8 * g + j]) + s_bias[c + 8 * g + j], act);
+        if (ng + 8 <= p.N) {
+          uint4 pk;
+          pk.x = pack_half2(v[0], v[1]);
+          pk.y = pack_half2(v[2], v[3]);
+          pk.z = pack_half2(v[4], v[5]);
+          pk.w = pack_half2(v[6], v[7]);
+          *reinterpret_cast<uint4*>(orow + ng) = pk;
+          if (urow != nullptr) {
+            *reinterpret_cast<uint4*>(urow + ng) = pk;
+            *reinterpret_cast<uint4*>(urow + up_dx + ng) = pk;
+            *reinterpret_cast<uint4*>(urow + up_dy + ng) = pk;
+            *reinterpret_cast<uint4*>(urow + up_dy + up_dx + ng) = pk;
+          }
+        } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (ng + j < p.N) {
-            const __half hv = __float2half_rn(v[8 * g + j]);
-            orow[ng + j] = hv;
-            if (urow != nullptr) {
-              urow[ng + j] = hv;
-              urow[up_dx + ng + j] = hv;
-              urow[up_dy + ng + j] = hv;
-              urow[up_dy + up_dx + ng + j] = hv;
+          for (int j = 0; j < 8; ++j) {
+            if (ng + j < p.N) {
+              const __half hv = __float2half_rn(v[j]);
+              orow[ng + j] = hv;
+              if (urow != nullptr) {
+                urow[ng + j] = hv;
+                urow[up_dx + ng + j] = hv;
+                urow[up_dy + ng + j] = hv;
+                urow[up_dy + up_dx + ng + j] = hv;
+              }
             }
           }
         }
       }
-    }
     }
   }
 
@@ -297,7 +304,7 @@ static int32_t launch_gemm(GemmParams& p, int n_tiles, int total_kb, cudaStream_
     configured[kIm2col] = 200 * 1024;
   }
   dim3 grid(n_tiles, ceil_div(p.M, kBlockM));
-  gemm_tc_kernel<kIm2col><<<grid, 128, smem, stream>>>(p);
+  gemm_tc_kernel<kIm2col><<<grid, 256, smem, stream>>>(p);
   return check_launch(kIm2col ? "conv3x3s2 kernel launch" : "conv1x1 kernel launch");
 }
 

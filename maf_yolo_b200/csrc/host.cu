@@ -90,7 +90,7 @@ int32_t mafb200_device_ok(int32_t device) {
 
 int32_t mafb200_gemm_tiling(int32_t cout, int32_t* n_tiles, int32_t* tile_n) {
   if (cout <= 0 || !n_tiles || !tile_n) return mafb200::fail(MAF_E_ARG, "gemm_tiling: bad arguments");
-  int nt = (cout + 255) / 256;
+  int nt = (cout + 127) / 128;  // <= 128 columns per tile: 4 CTAs (32 epilogue warps) fit one SM's TMEM
   int tn = ((cout + nt - 1) / nt + 15) / 16 * 16;
   *n_tiles = nt;
   *tile_n = tn;

@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const T* __restrict__ x,
       acc[7] = fmaf(v[t], w1.w, acc[7]);
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = apply_act(acc[j], act);
+    for (int j = 0; j < 8; ++j) acc[j] = apply_act_fast(acc[j], act);
     if (c0 + 8 <= cout) {
       uint4 pk;
       pk.x = pack_half2(acc[0], acc[1]);

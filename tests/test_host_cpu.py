@@ -30,8 +30,8 @@ def test_tiling_and_packed_k():
     # every cout of the N/S/M graphs splits into <=256-wide, 16-aligned tiles that cover it
     for cout in [24, 48, 68, 72, 80, 96, 128, 144, 192, 256, 288, 384, 512, 576, 768, 1152, 1536]:
         nt, tn = _lib.gemm_tiling(cout)
-        assert tn % 16 == 0 and 16 <= tn <= 256 and nt * tn >= cout and (nt - 1) * tn < cout
-    assert _lib.gemm_tiling(288) == (2, 144) and _lib.gemm_tiling(24) == (1, 32)
+        assert tn % 16 == 0 and 16 <= tn <= 128 and nt * tn >= cout and (nt - 1) * tn < cout
+    assert _lib.gemm_tiling(288) == (3, 96) and _lib.gemm_tiling(24) == (1, 32) and _lib.gemm_tiling(192) == (2, 96)
     assert _lib.packed_k_1x1([96, 384]) == 128 + 384 and _lib.packed_k_1x1([24, 24, 24]) == 192
     assert _lib.packed_k_3x3(24) == 576 and _lib.packed_k_3x3(192) == 1728
 
