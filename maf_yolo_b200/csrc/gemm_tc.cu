@@ -10,16 +10,18 @@
 //     fetched by an im2col-mode TMA descriptor (traversal stride 2, bounding-box corners -1/-1,
 //     zero fill = the padding), K = 9 * Cin.
 //
-// One CTA computes one 128 x tile_n output tile:
-//   warp 0 / lane 0 : TMA producer (A tile 128x64 + W tile tile_n x 64 per stage, SWIZZLE_128B)
-//   warp 1 / lane 0 : tcgen05.mma issuer (UMMA 128 x tile_n x 16, 4 per stage), commits free the stage
-//   all 8 warps     : epilogue — warp w owns TMEM lanes 32*(w%4).. (one output row per thread) and
-//                     every other 32-column group (w/4): tcgen05.ld 32x32b.x32 -> +bias -> act
-//                     (fast-math SiLU: 2 MUFU/element) -> fp16 -> 4 x 16-byte global stores
-//                     (optionally also the x2 nearest-upsampled copy)
-// K is tiny here (1-12 blocks of 64) and N <= 128 per tile, so the kernel is epilogue/HBM-bound:
-// tiles are capped at 128 columns (<= 128 TMEM columns) so that 4 CTAs = 32 epilogue warps are
-// resident per SM and one CTA's epilogue overlaps its neighbours' TMA loads and MMAs.
+// Persistent, warp-specialised CTAs (2 per SM) loop over 128 x tile_n output tiles (n fastest):
+//   warp 0 / lane 0 : TMA producer — runs ahead across tiles through a ring of smem stages
+//                     (A tile 128x64 + W tile tile_n x 64 per stage, SWIZZLE_128B)
+//   warp 1 / lane 0 : tcgen05.mma issuer (UMMA 128 x tile_n x 16, 4 per stage) into one of TWO TMEM
+//                     accumulators; commits free the smem stage / publish the accumulator
+//   warps 2..9      : epilogue of the previous tile, overlapped with the loads+MMAs of the next:
+//                     warp w owns TMEM lanes 32*(w%4).. (one output row per thread) and every other
+//                     32-column group: tcgen05.ld 32x32b.x32 -> +bias -> act (fast-math SiLU,
+//                     2 MUFU/element) -> fp16 -> 4 x 16-byte global stores (optionally also the x2
+//                     nearest-upsampled copy)
+// K is tiny here (1-12 blocks of 64) and N <= 128 per tile, so the kernel is epilogue/HBM-bound, not
+// tensor-bound: the design goal is to keep 16 epilogue warps per SM busy while TMA streams ahead.
 #include <string.h>
 
 #include "common.cuh"
@@ -44,14 +46,19 @@ struct GemmParams {
   int32_t kblocks[MAF_MAX_SRC];  // 1x1: 64-wide K blocks of each source; 3x3: kblocks[0] = blocks per tap
   int32_t act;
   int32_t stages;
-  int32_t tmem_cols;
+  int32_t tmem_cols;  // total TMEM columns allocated: two accumulator buffers
+  int32_t n_tiles;
   uint32_t idesc;
 };
 
+constexpr int kEpiWarps = 8;
+constexpr int kGemmThreads = 32 * (2 + kEpiWarps);  // TMA warp + MMA warp + epilogue warps
+
 template <bool kIm2col>
-__global__ void __launch_bounds__(256) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+__global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // keep the shared address space (no generic-pointer arithmetic): pad up to the 1024-B swizzle alignment
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -61,12 +68,13 @@ __global__ void __launch_bounds__(256) gemm_tc_kernel(const __grid_constant__ Ge
 
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
   uint64_t* empty_bar = full_bar + stages;
-  uint64_t* tmem_full_bar = empty_bar + stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-  float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);
+  uint64_t* tmem_full_bar = empty_bar + stages;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);  // [n_tiles * tile_n]
 
-  const int n0 = blockIdx.x * p.tile_n;
-  const int m0 = blockIdx.y * kBlockM;
+  const int n_tiles = p.n_tiles;
+  const int total_tiles = n_tiles * ceil_div(p.M, kBlockM);
 
   int total_kb;
   if (kIm2col) {
@@ -84,141 +92,170 @@ __global__ void __launch_bounds__(256) gemm_tc_kernel(const __grid_constant__ Ge
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], kEpiWarps);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
     tmem_alloc(tmem_slot, p.tmem_cols);
     tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < p.tile_n; i += blockDim.x) s_bias[i] = p.bias[n0 + i];
+  for (int i = threadIdx.x; i < n_tiles * p.tile_n; i += blockDim.x) s_bias[i] = p.bias[i];
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t acc_cols = p.tmem_cols >> 1;  // columns of one accumulator buffer
 
-  // ---- producer ---------------------------------------------------------------------------------
-  if (warp == 0 && lane == 0) {
-    int q0 = 0, p0 = 0, img = 0;
-    if (kIm2col) {
-      const int hw = p.out_h * p.out_w;
-      img = m0 / hw;
-      const int rem = m0 - img * hw;
-      p0 = rem / p.out_w;
-      q0 = rem - p0 * p.out_w;
-    }
-    int kb = 0;
-    int wk = 0;  // column in the packed weights
-    const int n_outer = kIm2col ? 9 : p.nsrc;
-    for (int o = 0; o < n_outer; ++o) {
-      const int nblk = kIm2col ? p.kblocks[0] : p.kblocks[o];
-      for (int j = 0; j < nblk; ++j, ++kb, wk += kBlockK) {
-        const int stage = kb % stages;
-        const uint32_t phase = (kb / stages) & 1;
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * stage_bytes;
-        uint8_t* sb = sa + kABytes;
-        mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+  if (warp == 0) {
+    // ---- TMA producer ---------------------------------------------------------------------------
+    if (lane == 0) {
+      int kb = 0;  // running k-block counter across tiles (ring position)
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n0 = (tile % n_tiles) * p.tile_n;
+        const int m0 = (tile / n_tiles) * kBlockM;
+        int q0 = 0, p0 = 0, img = 0;
         if (kIm2col) {
-          const int ky = o / 3, kx = o - ky * 3;
-          tma_load_im2col_4d(sa, &p.tmA[0], &full_bar[stage], j * kBlockK, 2 * q0 - 1, 2 * p0 - 1, img,
-                             static_cast<uint16_t>(kx), static_cast<uint16_t>(ky));
-        } else {
-          tma_load_2d(sa, &p.tmA[o], &full_bar[stage], j * kBlockK, m0);
+          const int hw = p.out_h * p.out_w;
+          img = m0 / hw;
+          const int rem = m0 - img * hw;
+          p0 = rem / p.out_w;
+          q0 = rem - p0 * p.out_w;
         }
-        tma_load_2d(sb, &p.tmW, &full_bar[stage], wk, n0);
+        int wk = 0;  // column in the packed weights
+        const int n_outer = kIm2col ? 9 : p.nsrc;
+        for (int o = 0; o < n_outer; ++o) {
+          const int nblk = kIm2col ? p.kblocks[0] : p.kblocks[o];
+          for (int j = 0; j < nblk; ++j, ++kb, wk += kBlockK) {
+            const int stage = kb % stages;
+            const uint32_t phase = (kb / stages) & 1;
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * stage_bytes;
+            uint8_t* sb = sa + kABytes;
+            mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+            if (kIm2col) {
+              const int ky = o / 3, kx = o - ky * 3;
+              tma_load_im2col_4d(sa, &p.tmA[0], &full_bar[stage], j * kBlockK, 2 * q0 - 1, 2 * p0 - 1, img,
+                                 static_cast<uint16_t>(kx), static_cast<uint16_t>(ky));
+            } else {
+              tma_load_2d(sa, &p.tmA[o], &full_bar[stage], j * kBlockK, m0);
+            }
+            tma_load_2d(sb, &p.tmW, &full_bar[stage], wk, n0);
+          }
+        }
       }
     }
-  }
-  // ---- MMA issuer -------------------------------------------------------------------------------
-  else if (warp == 1 && lane == 0) {
-    for (int kb = 0; kb < total_kb; ++kb) {
-      const int stage = kb % stages;
-      const uint32_t phase = (kb / stages) & 1;
-      mbar_wait(&full_bar[stage], phase);
-      tc_fence_after_sync();
-      const uint32_t sa = smem_u32(smem + stage * stage_bytes);
-      const uint64_t da = umma_smem_desc_sw128(sa);
-      const uint64_t db = umma_smem_desc_sw128(sa + kABytes);
+  } else if (warp == 1) {
+    // ---- MMA issuer -----------------------------------------------------------------------------
+    if (lane == 0) {
+      int kb = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        mbar_wait(&tmem_empty_bar[as], ((it >> 1) & 1) ^ 1);  // epilogue drained this accumulator
+        tc_fence_after_sync();
+        const uint32_t tmem_d = tmem_base + as * acc_cols;
+        for (int k2 = 0; k2 < total_kb; ++k2, ++kb) {
+          const int stage = kb % stages;
+          const uint32_t phase = (kb / stages) & 1;
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+          const uint64_t da = umma_smem_desc_sw128(sa);
+          const uint64_t db = umma_smem_desc_sw128(sa + kABytes);
 #pragma unroll
-      for (int k = 0; k < kBlockK / 16; ++k) {
-        // advance 16 fp16 = 32 B inside the 128-B swizzle row: +2 in the (addr >> 4) field
-        tc_mma_f16(tmem_base, da + 2 * k, db + 2 * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // advance 16 fp16 = 32 B inside the 128-B swizzle row: +2 in the (addr >> 4) field
+            tc_mma_f16(tmem_d, da + 2 * k, db + 2 * k, p.idesc, (k2 | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[stage]);
+        }
+        tc_commit(&tmem_full_bar[as]);
       }
-      tc_commit(&empty_bar[stage]);
     }
-    tc_commit(tmem_full_bar);
-  }
-
-  // ---- epilogue (all 256 threads; thread t owns output row m0 + (t % 128) == TMEM lane t % 128) ----
-  __syncwarp();
-  mbar_wait(tmem_full_bar, 0);
-  tc_fence_after_sync();
-
-  const int quarter = warp & 3;        // TMEM lane quarter this warp may access
-  const int col_group = warp >> 2;     // which 32-column groups (even / odd) this warp handles
-  const int row = quarter * 32 + lane;
-  const int m = m0 + row;
-  const bool row_ok = m < p.M;
-  const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-  __half* orow = p.out + static_cast<size_t>(row_ok ? m : 0) * p.out_ld;
-  __half* urow = nullptr;
-  if (p.out2 != nullptr && row_ok) {
-    const int hw = p.out_h * p.out_w;
-    const int img = m / hw;
-    const int rem = m - img * hw;
-    const int y = rem / p.out_w;
-    const int x = rem - y * p.out_w;
-    urow = p.out2 + ((static_cast<size_t>(img) * 2 * p.out_h + 2 * y) * (2 * p.out_w) + 2 * x) * p.out2_ld;
-  }
-  const size_t up_dx = p.out2_ld;
-  const size_t up_dy = static_cast<size_t>(2) * p.out_w * p.out2_ld;
-  const int act = p.act;
+  } else {
+    // ---- epilogue warps ---------------------------------------------------------------------------
+    const int ew = warp - 2;
+    const int quarter = warp & 3;    // TMEM lanes this warp may access: 32 * (warp id % 4)
+    const int col_group = ew >> 2;   // even / odd 32-column groups
+    const int row = quarter * 32 + lane;
+    const int act = p.act;
+    const size_t up_dx = p.out2_ld;
+    const size_t up_dy = static_cast<size_t>(2) * p.out_w * p.out2_ld;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const int nt = tile % n_tiles;
+      const int n0 = nt * p.tile_n;
+      const int m = (tile / n_tiles) * kBlockM + row;
+      const bool row_ok = m < p.M;
+      mbar_wait(&tmem_full_bar[as], (it >> 1) & 1);
+      tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + as * acc_cols + (static_cast<uint32_t>(quarter * 32) << 16);
+      __half* orow = p.out + static_cast<size_t>(row_ok ? m : 0) * p.out_ld;
+      __half* urow = nullptr;
+      if (p.out2 != nullptr && row_ok) {
+        const int hw = p.out_h * p.out_w;
+        const int img = m / hw;
+        const int rem = m - img * hw;
+        const int y = rem / p.out_w;
+        const int x = rem - y * p.out_w;
+        urow = p.out2 + ((static_cast<size_t>(img) * 2 * p.out_h + 2 * y) * (2 * p.out_w) + 2 * x) * p.out2_ld;
+      }
+      const float* bias_t = s_bias + nt * p.tile_n;
 
 #pragma unroll 1
-  for (int c = col_group * 32; c < p.tile_n; c += 64) {
-    uint32_t r[32];
-    __syncwarp();  // tcgen05.ld is .sync.aligned: the warp must be converged here
-    tmem_ld_32x32b_x32(taddr + c, r);
-    tmem_ld_wait();
-    const int n = n0 + c;
-    if (row_ok && n < p.N) {
+      for (int c = col_group * 32; c < p.tile_n; c += 64) {
+        uint32_t r[32];
+        __syncwarp();  // tcgen05.ld is .sync.aligned: the warp must be converged here
+        tmem_ld_32x32b_x32(taddr + c, r);
+        tmem_ld_wait();
+        const int n = n0 + c;
+        if (row_ok && n < p.N) {
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int ng = n + 8 * g;
-        if (c + 8 * g >= p.tile_n) break;  // tile_n is a multiple of 16: the upper half of the last group may be unused
-        float v[8];
+          for (int g = 0; g < 4; ++g) {
+            const int ng = n + 8 * g;
+            if (c + 8 * g >= p.tile_n) break;  // tile_n % 16 == 0: the upper half of the last group may be unused
+            float v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = apply_act_fast(__uint_as_float(r[8 * g + j]) + s_bias[c + 8 * g + j], act);
-        if (ng + 8 <= p.N) {
-          uint4 pk;
-          pk.x = pack_half2(v[0], v[1]);
-          pk.y = pack_half2(v[2], v[3]);
-          pk.z = pack_half2(v[4], v[5]);
-          pk.w = pack_half2(v[6], v[7]);
-          *reinterpret_cast<uint4*>(orow + ng) = pk;
-          if (urow != nullptr) {
-            *reinterpret_cast<uint4*>(urow + ng) = pk;
-            *reinterpret_cast<uint4*>(urow + up_dx + ng) = pk;
-            *reinterpret_cast<uint4*>(urow + up_dy + ng) = pk;
-            *reinterpret_cast<uint4*>(urow + up_dy + up_dx + ng) = pk;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (ng + j < p.N) {
-              const __half hv = __float2half_rn(v[j]);
-              orow[ng + j] = hv;
+            for (int j = 0; j < 8; ++j) v[j] = apply_act_fast(__uint_as_float(r[8 * g + j]) + bias_t[c + 8 * g + j], act);
+            if (ng + 8 <= p.N) {
+              uint4 pk;
+              pk.x = pack_half2(v[0], v[1]);
+              pk.y = pack_half2(v[2], v[3]);
+              pk.z = pack_half2(v[4], v[5]);
+              pk.w = pack_half2(v[6], v[7]);
+              *reinterpret_cast<uint4*>(orow + ng) = pk;
               if (urow != nullptr) {
-                urow[ng + j] = hv;
-                urow[up_dx + ng + j] = hv;
-                urow[up_dy + ng + j] = hv;
-                urow[up_dy + up_dx + ng + j] = hv;
+                *reinterpret_cast<uint4*>(urow + ng) = pk;
+                *reinterpret_cast<uint4*>(urow + up_dx + ng) = pk;
+                *reinterpret_cast<uint4*>(urow + up_dy + ng) = pk;
+                *reinterpret_cast<uint4*>(urow + up_dy + up_dx + ng) = pk;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                if (ng + j < p.N) {
+                  const __half hv = __float2half_rn(v[j]);
+                  orow[ng + j] = hv;
+                  if (urow != nullptr) {
+                    urow[ng + j] = hv;
+                    urow[up_dx + ng + j] = hv;
+                    urow[up_dy + ng + j] = hv;
+                    urow[up_dy + up_dx + ng + j] = hv;
+                  }
+                }
               }
             }
           }
         }
       }
+      // all of this warp's TMEM reads of accumulator `as` are complete (wait::ld above): hand it back
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
     }
   }
 
@@ -287,24 +324,45 @@ static int pow2_cols(int n) {
   return c;
 }
 
+static int sm_count() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      cached = 148;
+  }
+  return cached;
+}
+
 template <bool kIm2col>
 static int32_t launch_gemm(GemmParams& p, int n_tiles, int total_kb, cudaStream_t stream) {
   const int stage_bytes = kABytes + p.tile_n * kBlockK * 2;
-  int stages = total_kb < 4 ? total_kb : 4;
-  while (stages > 1 && stages * stage_bytes > 112 * 1024) --stages;
+  const int m_tiles = ceil_div(p.M, kBlockM);
+  const int total_tiles = m_tiles * n_tiles;
+  const int grid = total_tiles < 2 * sm_count() ? total_tiles : 2 * sm_count();  // persistent: 2 CTAs per SM
+  const int tiles_per_cta = ceil_div(total_tiles, grid);
+  // enough stages to hold ~2 tiles' worth of k-blocks (the producer runs ahead), within ~100 KB per CTA
+  int stages = total_kb * (tiles_per_cta > 1 ? 2 : 1);
+  if (stages > 6) stages = 6;
+  while (stages > 1 && stages * stage_bytes > 100 * 1024) --stages;
   p.stages = stages;
-  p.tmem_cols = pow2_cols(p.tile_n);
+  p.n_tiles = n_tiles;
+  p.tmem_cols = 2 * pow2_cols(p.tile_n);
   p.idesc = umma_idesc_f16(kBlockM, p.tile_n);
-  const size_t smem = static_cast<size_t>(stages) * stage_bytes + (2 * stages + 1) * 8 + 16 + p.tile_n * 4 + 1024;
-  static size_t configured[2] = {0, 0};
-  if (smem > configured[kIm2col]) {
+  const size_t smem = static_cast<size_t>(stages) * stage_bytes + (2 * stages + 4) * 8 + 16 +
+                      static_cast<size_t>(n_tiles) * p.tile_n * 4 + 1024;
+  static bool configured[2] = {false, false};
+  if (!configured[kIm2col]) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<kIm2col>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          200 * 1024);
     if (e != cudaSuccess) return fail(MAF_E_CUDA, "cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e));
-    configured[kIm2col] = 200 * 1024;
+    configured[kIm2col] = true;
   }
-  dim3 grid(n_tiles, ceil_div(p.M, kBlockM));
-  gemm_tc_kernel<kIm2col><<<grid, 256, smem, stream>>>(p);
+  if (smem > 200 * 1024) return fail(MAF_E_ARG, "gemm: %zu B of shared memory needed (cout too large)", smem);
+  gemm_tc_kernel<kIm2col><<<grid, kGemmThreads, smem, stream>>>(p);
   return check_launch(kIm2col ? "conv3x3s2 kernel launch" : "conv1x1 kernel launch");
 }
 
