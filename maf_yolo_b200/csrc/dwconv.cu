@@ -1,5 +1,5 @@
 // K3 — depth-wise k x k convolution (k in {3,5,7,9}, stride 1, pad k/2), NHWC fp16 in/out,
-// fp32 weights / bias / accumulation, fused bias + {none | SiLU}.
+// fp32 weights / bias / accumulation, fused bias + {none | SiLU | ReLU}.
 //
 // This is the deploy form of the reference's "RepHConv": DilatedReparamBlock merged into one
 // depth-wise kernel and folded with the outer BN of UniRepLKNetBlock
@@ -7,116 +7,186 @@
 // or by nothing in Head_DepthUni (common.py:1328,1334).  It is the op for which the reference
 // authors wanted a native large-kernel DW implementation (common.py:2601-2609).
 //
-// Arithmetic intensity is 4.5-37 flop/B -> CUDA cores, not tensor cores.
-// Mapping: one thread = 2 channels (one half2 -> float2) x R consecutive output columns x TY
-// consecutive output rows.  Lanes of a warp walk consecutive channel pairs, so every global
-// load is a fully coalesced 128-B row segment; the (TY+k-1) x (R+k-1) input window is held in
-// registers and reused k*k times; neighbouring threads' halos hit L1.
+// Arithmetic intensity is 4.5-37 flop/B -> CUDA cores, not tensor cores; the
+// kernel is FFMA-issue-bound, so everything else is kept out of the inner loop:
+//   * one TMA tiled load (cp.async.bulk.tensor.4d) brings the (10+k-1) x (20+k-1) x CB halo tile of
+//     a 10 x 20 output tile into shared memory; out-of-bounds zero fill IS the conv padding and the
+//     channel tail, so there is not a single bounds check or address computation per tap;
+//   * weights of the CB channels are staged once per CTA as fp32 [k*k][CB];
+//   * a thread owns 2 channels (half2 -> float2) x 5 x 5 outputs: 50 independent fp32 accumulators,
+//     every shared-memory operand address is (thread base + compile-time immediate);
+//   * one tile per CTA with 3-5 CTAs resident per SM measured FASTER than persistent CTAs with a
+//     two-stage TMA ring (857 vs 920 us per forward): the inner loop is co-limited by the FFMA pipe and
+//     shared-memory bandwidth (fp32 weights: 8 B per lane per tap), so resident warps matter most;
+//   * CB = 64 channels per CTA when C % 64 == 0, else 32 (lanes then split into two 5-column strips
+//     whose smem rows fall in disjoint banks because the strip width 5 is odd).
+#include <string.h>
+
 #include "common.cuh"
 #include "host.h"
 
 namespace mafb200 {
 
-template <int K, int R, int TY>
+constexpr int kDwR = 5;     // output columns per thread
+constexpr int kDwTY = 5;    // output rows per thread
+constexpr int kDwTXB = 20;  // output tile per CTA
+constexpr int kDwTYB = 10;
+
+__device__ __forceinline__ void tma_load_tile_4d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int32_t c0,
+                                                 int32_t c1, int32_t c2, int32_t c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+        "r"(c3)
+      : "memory");
+}
+
+template <int K, int CB>
 __global__ void __launch_bounds__(128)
-    dwconv_kernel(const __half* __restrict__ in, int in_ld, __half* __restrict__ out, int out_ld,
-                  const float* __restrict__ wgt, const float* __restrict__ bias, int B, int H, int W, int C, int act) {
+    dwconv_kernel(const __grid_constant__ CUtensorMap tm_in, __half* __restrict__ out, int out_ld,
+                  const float* __restrict__ wgt, const float* __restrict__ bias, int H, int W, int C, int act,
+                  int tiles_x) {
   constexpr int P = K / 2;
-  const int cp = C >> 1;                 // channel pairs
-  const int nstrip = ceil_div(W, R);
-  const int nty = ceil_div(H, TY);
-  const long long total = static_cast<long long>(B) * nty * nstrip * cp;
-  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (t >= total) return;
-  const int pair = static_cast<int>(t % cp);
-  long long rest = t / cp;
-  const int strip = static_cast<int>(rest % nstrip);
-  rest /= nstrip;
-  const int ty = static_cast<int>(rest % nty);
-  const int b = static_cast<int>(rest / nty);
-  const int x0 = strip * R;
-  const int y0 = ty * TY;
-  const int ch = pair * 2;
+  constexpr int TW = kDwTXB + K - 1;        // halo tile width (pixels)
+  constexpr int TH = kDwTYB + K - 1;
+  constexpr int PAIRS = CB / 2;             // channel pairs per CTA
+  constexpr int XS = 32 / PAIRS;            // 5-column strips a warp covers side by side
+  constexpr int UX = kDwTXB / (kDwR * XS);  // warp units along x
+  constexpr int UY = kDwTYB / kDwTY;
+  constexpr int UNITS = UX * UY;
+  constexpr uint32_t kTileBytes = TH * TW * CB * 2;
 
-  float2 acc[TY][R];
-  {
-    const float2 bv = *reinterpret_cast<const float2*>(bias + ch);
-#pragma unroll
-    for (int i = 0; i < TY; ++i)
-#pragma unroll
-      for (int r = 0; r < R; ++r) acc[i][r] = bv;
+  extern __shared__ __align__(128) uint8_t smem_dw[];
+  __half* s_in = reinterpret_cast<__half*>(smem_dw);                        // [TH][TW][CB]
+  float* s_w = reinterpret_cast<float*>(smem_dw + kTileBytes);              // [K*K][CB]
+  float* s_b = s_w + K * K * CB;                                            // [CB]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(s_b + CB);
+
+  const int tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
+  const int c0 = blockIdx.y * CB;
+  const int img = blockIdx.z;
+  const int x0 = tile_x * kDwTXB, y0 = tile_y * kDwTYB;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+    mbar_arrive_expect_tx(bar, kTileBytes);
+    tma_load_tile_4d(s_in, &tm_in, bar, c0, x0 - P, y0 - P, img);
   }
+  for (int i = threadIdx.x; i < K * K * CB; i += blockDim.x) {
+    const int t = i / CB, c = i - t * CB;
+    s_w[i] = (c0 + c < C) ? __ldg(wgt + static_cast<size_t>(t) * C + c0 + c) : 0.0f;
+  }
+  for (int i = threadIdx.x; i < CB; i += blockDim.x) s_b[i] = (c0 + i < C) ? __ldg(bias + c0 + i) : 0.0f;
+  __syncthreads();
+  mbar_wait(bar, 0);
 
-  const __half* in_b = in + static_cast<size_t>(b) * H * W * in_ld + ch;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = lane % PAIRS;
+  const int xsel = lane / PAIRS;
+  const bool ch_ok = c0 + 2 * pair < C;
+  const float2 bv = *reinterpret_cast<const float2*>(s_b + 2 * pair);
+  const float* wbase = s_w + 2 * pair;
+
+#pragma unroll 1
+  for (int u = warp; u < UNITS; u += 4) {
+    const int uy = u / UX, ux = u - uy * UX;
+    const int oy0 = uy * kDwTY;
+    const int ox0 = (ux * XS + xsel) * kDwR;
+    const __half* ibase = s_in + (oy0 * TW + ox0) * CB + 2 * pair;
+
+    float2 acc[kDwTY][kDwR];
 #pragma unroll
-  for (int d = 0; d < TY + K - 1; ++d) {
-    const int iy = y0 - P + d;
-    if (iy < 0 || iy >= H) continue;
-    float2 win[R + K - 1];
-    const __half* in_row = in_b + static_cast<size_t>(iy) * W * in_ld;
+    for (int i = 0; i < kDwTY; ++i)
 #pragma unroll
-    for (int j = 0; j < R + K - 1; ++j) {
-      const int ix = x0 - P + j;
-      if (ix >= 0 && ix < W) {
-        const __half2 hv = __ldg(reinterpret_cast<const __half2*>(in_row + static_cast<size_t>(ix) * in_ld));
-        win[j] = __half22float2(hv);
-      } else {
-        win[j] = make_float2(0.f, 0.f);
+      for (int r = 0; r < kDwR; ++r) acc[i][r] = bv;
+
+#pragma unroll
+    for (int d = 0; d < kDwTY + K - 1; ++d) {
+      float2 win[kDwR + K - 1];
+#pragma unroll
+      for (int j = 0; j < kDwR + K - 1; ++j)
+        win[j] = __half22float2(*reinterpret_cast<const __half2*>(ibase + (d * TW + j) * CB));
+#pragma unroll
+      for (int i = 0; i < kDwTY; ++i) {
+        const int ky = d - i;  // compile-time after unrolling
+        if (ky < 0 || ky >= K) continue;
+        float2 wv[K];
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) wv[kx] = *reinterpret_cast<const float2*>(wbase + (ky * K + kx) * CB);
+#pragma unroll
+        for (int r = 0; r < kDwR; ++r) {
+#pragma unroll
+          for (int kx = 0; kx < K; ++kx) {
+            acc[i][r].x = fmaf(win[r + kx].x, wv[kx].x, acc[i][r].x);
+            acc[i][r].y = fmaf(win[r + kx].y, wv[kx].y, acc[i][r].y);
+          }
+        }
       }
     }
+
+    if (ch_ok) {
+      __half* obase = out + (static_cast<size_t>(img) * H * W) * out_ld + c0 + 2 * pair;
 #pragma unroll
-    for (int i = 0; i < TY; ++i) {
-      const int ky = d - i;  // compile-time after unrolling
-      if (ky < 0 || ky >= K) continue;
-      float2 wv[K];
+      for (int i = 0; i < kDwTY; ++i) {
+        const int y = y0 + oy0 + i;
+        if (y >= H) continue;
 #pragma unroll
-      for (int kx = 0; kx < K; ++kx)
-        wv[kx] = __ldg(reinterpret_cast<const float2*>(wgt + static_cast<size_t>(ky * K + kx) * C + ch));
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-#pragma unroll
-        for (int kx = 0; kx < K; ++kx) {
-          acc[i][r].x = fmaf(win[r + kx].x, wv[kx].x, acc[i][r].x);
-          acc[i][r].y = fmaf(win[r + kx].y, wv[kx].y, acc[i][r].y);
+        for (int r = 0; r < kDwR; ++r) {
+          const int x = x0 + ox0 + r;
+          if (x >= W) continue;
+          const float a = apply_act_fast(acc[i][r].x, act);
+          const float c = apply_act_fast(acc[i][r].y, act);
+          *reinterpret_cast<__half2*>(obase + (static_cast<size_t>(y) * W + x) * out_ld) = __floats2half2_rn(a, c);
         }
       }
     }
   }
-
-  __half* out_b = out + static_cast<size_t>(b) * H * W * out_ld + ch;
-#pragma unroll
-  for (int i = 0; i < TY; ++i) {
-    const int y = y0 + i;
-    if (y >= H) continue;
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int x = x0 + r;
-      if (x >= W) continue;
-      const float a = apply_act_fast(acc[i][r].x, act);
-      const float c = apply_act_fast(acc[i][r].y, act);
-      *reinterpret_cast<__half2*>(out_b + (static_cast<size_t>(y) * W + x) * out_ld) = __floats2half2_rn(a, c);
-    }
-  }
 }
 
-template <int K, int R, int TY>
+template <int K, int CB>
 static int32_t launch_dw(const maf_tensor* src, const float* w, const float* bias, int act, const maf_tensor* dst,
                          cudaStream_t st) {
-  const long long total = static_cast<long long>(src->n) * ceil_div(src->h, TY) * ceil_div(src->w, R) * (src->c / 2);
-  const unsigned blocks = static_cast<unsigned>((total + 127) / 128);
-  dwconv_kernel<K, R, TY><<<blocks, 128, 0, st>>>(static_cast<const __half*>(src->ptr), src->c_stride,
-                                                  static_cast<__half*>(dst->ptr), dst->c_stride, w, bias, src->n,
-                                                  src->h, src->w, src->c, act);
+  constexpr int TW = kDwTXB + K - 1, TH = kDwTYB + K - 1;
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return fail(MAF_E_ARCH, "cuTensorMapEncodeTiled entry point not available");
+  CUtensorMap tm;
+  const cuuint64_t px = static_cast<cuuint64_t>(src->c_stride) * 2;
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(src->c), static_cast<cuuint64_t>(src->w),
+                        static_cast<cuuint64_t>(src->h), static_cast<cuuint64_t>(src->n)};
+  cuuint64_t strides[3] = {px, px * src->w, px * src->w * src->h};
+  cuuint32_t box[4] = {CB, TW, TH, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, src->ptr, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(MAF_E_CUDA, "dwconv: cuTensorMapEncodeTiled(c=%d w=%d h=%d n=%d) failed: %d", src->c, src->w, src->h,
+                src->n, (int)r);
+  const size_t smem = static_cast<size_t>(TH) * TW * CB * 2 + static_cast<size_t>(K * K + 1) * CB * 4 + 16;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e =
+        cudaFuncSetAttribute(dwconv_kernel<K, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e != cudaSuccess) return fail(MAF_E_CUDA, "dwconv: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  const int tiles_x = ceil_div(src->w, kDwTXB), tiles_y = ceil_div(src->h, kDwTYB);
+  dim3 grid(tiles_x * tiles_y, ceil_div(src->c, CB), src->n);
+  dwconv_kernel<K, CB><<<grid, 128, smem, st>>>(tm, static_cast<__half*>(dst->ptr), dst->c_stride, w, bias, src->h,
+                                                src->w, src->c, act, tiles_x);
   return check_launch("dwconv kernel launch");
 }
 
 template <int K>
 static int32_t dispatch_dw(const maf_tensor* src, const float* w, const float* bias, int act, const maf_tensor* dst,
                            cudaStream_t st) {
-  // Column strip R: 4 divides every map width of the 640x640 pyramid (160/80/40/20) and keeps the
-  // register window (R+K-1) small; 5-wide strips for widths that are multiples of 5 but not 4.
-  if (src->w % 4 == 0 || src->w % 5 != 0) return launch_dw<K, 4, 4>(src, w, bias, act, dst, st);
-  return launch_dw<K, 5, 4>(src, w, bias, act, dst, st);
+  // 64-channel CTAs when they tile C exactly and the halo tile stays small enough for >= 3 CTAs/SM,
+  // else 32-channel CTAs (<= 25 % idle lanes in the worst case, C = 72).
+  if (src->c % 64 == 0 && K <= 5) return launch_dw<K, 64>(src, w, bias, act, dst, st);
+  return launch_dw<K, 32>(src, w, bias, act, dst, st);
 }
 
 }  // namespace mafb200
@@ -128,11 +198,12 @@ extern "C" int32_t mafb200_dwconv(const maf_tensor* src, const float* weight, co
   if (!valid_f16_view(src) || !valid_f16_view(dst)) return fail(MAF_E_ARG, "dwconv: bad src/dst");
   if (!weight || !bias) return fail(MAF_E_ARG, "dwconv: null weight/bias");
   if (!same_nhw(src, dst) || src->c != dst->c) return fail(MAF_E_ARG, "dwconv: src/dst shape mismatch");
-  if ((src->c & 1) || (src->c_stride & 1) || (dst->c_stride & 1) || (reinterpret_cast<uintptr_t>(src->ptr) & 3) ||
-      (reinterpret_cast<uintptr_t>(dst->ptr) & 3) || (reinterpret_cast<uintptr_t>(weight) & 7) ||
-      (reinterpret_cast<uintptr_t>(bias) & 7))
-    return fail(MAF_E_ALIGN, "dwconv: channels / strides must be even, pointers 4-B (data) and 8-B (weights) aligned");
+  if ((src->c & 1) || (dst->c_stride & 1) || (reinterpret_cast<uintptr_t>(dst->ptr) & 3))
+    return fail(MAF_E_ALIGN, "dwconv: channels and dst stride must be even, dst 4-B aligned");
+  if (!aligned_f16_view(src)) return fail(MAF_E_ALIGN, "dwconv: src must be 16-B aligned with c_stride %% 8 == 0 (TMA)");
+  if (src->n > 65535) return fail(MAF_E_ARG, "dwconv: batch %d > 65535", src->n);
   if (act != MAF_ACT_NONE && act != MAF_ACT_SILU && act != MAF_ACT_RELU) return fail(MAF_E_ARG, "dwconv: bad act");
+  if (k != 3 && k != 5 && k != 7 && k != 9) return fail(MAF_E_ARG, "dwconv: kernel size %d not in {3,5,7,9}", k);
   int32_t rc = require_sm100();
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -140,7 +211,6 @@ extern "C" int32_t mafb200_dwconv(const maf_tensor* src, const float* weight, co
     case 3: return dispatch_dw<3>(src, weight, bias, act, dst, st);
     case 5: return dispatch_dw<5>(src, weight, bias, act, dst, st);
     case 7: return dispatch_dw<7>(src, weight, bias, act, dst, st);
-    case 9: return dispatch_dw<9>(src, weight, bias, act, dst, st);
-    default: return fail(MAF_E_ARG, "dwconv: kernel size %d not in {3,5,7,9}", k);
+    default: return dispatch_dw<9>(src, weight, bias, act, dst, st);
   }
 }
