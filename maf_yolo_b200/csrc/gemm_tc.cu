@@ -10,18 +10,23 @@
 //     fetched by an im2col-mode TMA descriptor (traversal stride 2, bounding-box corners -1/-1,
 //     zero fill = the padding), K = 9 * Cin.
 //
-// Persistent, warp-specialised CTAs (2 per SM) loop over 128 x tile_n output tiles (n fastest):
-//   warp 0 / lane 0 : TMA producer — runs ahead across tiles through a ring of smem stages
-//                     (A tile 128x64 + W tile tile_n x 64 per stage, SWIZZLE_128B)
-//   warp 1 / lane 0 : tcgen05.mma issuer (UMMA 128 x tile_n x 16, 4 per stage) into one of TWO TMEM
-//                     accumulators; commits free the smem stage / publish the accumulator
-//   warps 2..9      : epilogue of the previous tile, overlapped with the loads+MMAs of the next:
-//                     warp w owns TMEM lanes 32*(w%4).. (one output row per thread) and every other
-//                     32-column group: tcgen05.ld 32x32b.x32 -> +bias -> act (fast-math SiLU,
-//                     2 MUFU/element) -> fp16 -> 4 x 16-byte global stores (optionally also the x2
-//                     nearest-upsampled copy)
-// K is tiny here (1-12 blocks of 64) and N <= 128 per tile, so the kernel is epilogue/HBM-bound, not
-// tensor-bound: the design goal is to keep 16 epilogue warps per SM busy while TMA streams ahead.
+// Persistent, warp-specialised CTAs (2 per SM); a CTA owns ONE column tile (n) and loops over row
+// tiles (m) of 128 pixels:
+//   warp 0 / lane 0 : TMA producer.  When the whole weight panel of the column tile fits
+//                     (K_packed * tile_n * 2 B <= 48 KB — every layer of the N variant but four) it is
+//                     loaded ONCE and stays resident; the ring then carries only A tiles (16 KB each),
+//                     so the producer runs 3-6 row tiles ahead of the tensor core.  Otherwise A and W
+//                     k-blocks stream together through the ring.
+//   warp 1 / lane 0 : tcgen05.mma issuer (UMMA 128 x tile_n x 16, 4 per k-block) into one of TWO TMEM
+//                     accumulators; commits free the ring slot / publish the accumulator.
+//   warps 2..9      : epilogue of tile i while tile i+1 is loaded and multiplied: tcgen05.ld 32x32b.x32
+//                     (one output row per thread) -> +bias -> activation (fast-math SiLU) -> fp16 ->
+//                     4 x 16-byte global stores per 32 columns (64 contiguous bytes per thread), plus
+//                     the x2 nearest-upsampled copy for the two layers that feed an nn.Upsample.
+//                     (A shared-memory staged TMA tensor store was measured SLOWER: one-row-per-thread
+//                     writes into a dense row-major staging tile are 8-32-way bank conflicted.)
+// K is tiny here (1-12 blocks of 64) and N <= 128 per tile: the kernel is HBM/epilogue-bound, not
+// tensor-bound, so the design keeps loads deep in flight and the store path off the LSU.
 #include <string.h>
 
 #include "common.cuh"
@@ -32,6 +37,9 @@ namespace mafb200 {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB
+constexpr int kEpiWarps = 8;
+constexpr int kGemmThreads = 32 * (2 + kEpiWarps);  // TMA warp + MMA warp + epilogue warps
+constexpr int kMaxResidentW = 48 * 1024;
 
 struct GemmParams {
   CUtensorMap tmA[MAF_MAX_SRC];
@@ -44,15 +52,15 @@ struct GemmParams {
   int32_t out_h, out_w;  // spatial size of the output map (for out2 and im2col tile origin)
   int32_t nsrc;
   int32_t kblocks[MAF_MAX_SRC];  // 1x1: 64-wide K blocks of each source; 3x3: kblocks[0] = blocks per tap
+  int32_t total_kb;
   int32_t act;
-  int32_t stages;
-  int32_t tmem_cols;  // total TMEM columns allocated: two accumulator buffers
+  int32_t stages;      // ring slots
+  int32_t w_resident;  // 1: weight panel loaded once, ring slots hold A only
+  int32_t tmem_cols;   // total TMEM columns allocated: two accumulator buffers
   int32_t n_tiles;
+  int32_t m_stride;    // row-tile step of a CTA = gridDim.x / n_tiles
   uint32_t idesc;
 };
-
-constexpr int kEpiWarps = 8;
-constexpr int kGemmThreads = 32 * (2 + kEpiWarps);  // TMA warp + MMA warp + epilogue warps
 
 template <bool kIm2col>
 __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
@@ -62,27 +70,28 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int b_bytes = p.tile_n * kBlockK * 2;
-  const int stage_bytes = kABytes + b_bytes;
+  const int total_kb = p.total_kb;
+  const int b_bytes = p.tile_n * kBlockK * 2;  // one k-block of the W tile
+  const bool w_res = p.w_resident != 0;
+  const int slot_bytes = w_res ? kABytes : kABytes + b_bytes;
   const int stages = p.stages;
 
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
+  // layout: [W panel (resident mode)] [ring slots] [barriers] [bias]
+  uint8_t* s_wpanel = smem;
+  uint8_t* s_ring = smem + (w_res ? total_kb * b_bytes : 0);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_ring + stages * slot_bytes);
   uint64_t* empty_bar = full_bar + stages;
-  uint64_t* tmem_full_bar = empty_bar + stages;   // [2]
-  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-  float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);  // [n_tiles * tile_n]
+  uint64_t* tmem_full_bar = empty_bar + stages;  // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;  // [2]
+  uint64_t* w_bar = tmem_empty_bar + 2;          // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);  // [tile_n]
 
-  const int n_tiles = p.n_tiles;
-  const int total_tiles = n_tiles * ceil_div(p.M, kBlockM);
-
-  int total_kb;
-  if (kIm2col) {
-    total_kb = 9 * p.kblocks[0];
-  } else {
-    total_kb = 0;
-    for (int s = 0; s < p.nsrc; ++s) total_kb += p.kblocks[s];
-  }
+  const int m_tiles = ceil_div(p.M, kBlockM);
+  const int nt = blockIdx.x % p.n_tiles;  // this CTA's column tile
+  const int n0 = nt * p.tile_n;
+  const int mt0 = blockIdx.x / p.n_tiles;
+  const int mt_step = p.m_stride;
 
   // ---- one-time setup -------------------------------------------------------------------------
   if (warp == 0 && lane == 0) {
@@ -96,13 +105,14 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
       mbar_init(&tmem_full_bar[i], 1);
       mbar_init(&tmem_empty_bar[i], kEpiWarps);
     }
+    mbar_init(w_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
     tmem_alloc(tmem_slot, p.tmem_cols);
     tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < n_tiles * p.tile_n; i += blockDim.x) s_bias[i] = p.bias[i];
+  for (int i = threadIdx.x; i < p.tile_n; i += blockDim.x) s_bias[i] = p.bias[n0 + i];
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -111,11 +121,14 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
 
   if (warp == 0) {
     // ---- TMA producer ---------------------------------------------------------------------------
-    if (lane == 0) {
-      int kb = 0;  // running k-block counter across tiles (ring position)
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n0 = (tile % n_tiles) * p.tile_n;
-        const int m0 = (tile / n_tiles) * kBlockM;
+    if (lane == 0 && mt0 < m_tiles) {
+      if (w_res) {
+        mbar_arrive_expect_tx(w_bar, total_kb * b_bytes);
+        for (int k = 0; k < total_kb; ++k) tma_load_2d(s_wpanel + k * b_bytes, &p.tmW, w_bar, k * kBlockK, n0);
+      }
+      int kb = 0;  // running ring position across tiles
+      for (int mt = mt0; mt < m_tiles; mt += mt_step) {
+        const int m0 = mt * kBlockM;
         int q0 = 0, p0 = 0, img = 0;
         if (kIm2col) {
           const int hw = p.out_h * p.out_w;
@@ -129,48 +142,52 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
         for (int o = 0; o < n_outer; ++o) {
           const int nblk = kIm2col ? p.kblocks[0] : p.kblocks[o];
           for (int j = 0; j < nblk; ++j, ++kb, wk += kBlockK) {
-            const int stage = kb % stages;
+            const int slot = kb % stages;
             const uint32_t phase = (kb / stages) & 1;
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* sa = smem + stage * stage_bytes;
-            uint8_t* sb = sa + kABytes;
-            mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+            mbar_wait(&empty_bar[slot], phase ^ 1);
+            uint8_t* sa = s_ring + slot * slot_bytes;
+            mbar_arrive_expect_tx(&full_bar[slot], slot_bytes);
             if (kIm2col) {
               const int ky = o / 3, kx = o - ky * 3;
-              tma_load_im2col_4d(sa, &p.tmA[0], &full_bar[stage], j * kBlockK, 2 * q0 - 1, 2 * p0 - 1, img,
+              tma_load_im2col_4d(sa, &p.tmA[0], &full_bar[slot], j * kBlockK, 2 * q0 - 1, 2 * p0 - 1, img,
                                  static_cast<uint16_t>(kx), static_cast<uint16_t>(ky));
             } else {
-              tma_load_2d(sa, &p.tmA[o], &full_bar[stage], j * kBlockK, m0);
+              tma_load_2d(sa, &p.tmA[o], &full_bar[slot], j * kBlockK, m0);
             }
-            tma_load_2d(sb, &p.tmW, &full_bar[stage], wk, n0);
+            if (!w_res) tma_load_2d(sa + kABytes, &p.tmW, &full_bar[slot], wk, n0);
           }
         }
       }
     }
   } else if (warp == 1) {
     // ---- MMA issuer -----------------------------------------------------------------------------
-    if (lane == 0) {
+    if (lane == 0 && mt0 < m_tiles) {
+      if (w_res) {
+        mbar_wait(w_bar, 0);
+        tc_fence_after_sync();
+      }
       int kb = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int mt = mt0; mt < m_tiles; mt += mt_step, ++it) {
         const int as = it & 1;
         mbar_wait(&tmem_empty_bar[as], ((it >> 1) & 1) ^ 1);  // epilogue drained this accumulator
         tc_fence_after_sync();
         const uint32_t tmem_d = tmem_base + as * acc_cols;
         for (int k2 = 0; k2 < total_kb; ++k2, ++kb) {
-          const int stage = kb % stages;
+          const int slot = kb % stages;
           const uint32_t phase = (kb / stages) & 1;
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait(&full_bar[slot], phase);
           tc_fence_after_sync();
-          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+          const uint32_t sa = smem_u32(s_ring + slot * slot_bytes);
+          const uint32_t sb = w_res ? smem_u32(s_wpanel + k2 * b_bytes) : sa + kABytes;
           const uint64_t da = umma_smem_desc_sw128(sa);
-          const uint64_t db = umma_smem_desc_sw128(sa + kABytes);
+          const uint64_t db = umma_smem_desc_sw128(sb);
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // advance 16 fp16 = 32 B inside the 128-B swizzle row: +2 in the (addr >> 4) field
             tc_mma_f16(tmem_d, da + 2 * k, db + 2 * k, p.idesc, (k2 | k) != 0 ? 1u : 0u);
           }
-          tc_commit(&empty_bar[stage]);
+          tc_commit(&empty_bar[slot]);
         }
         tc_commit(&tmem_full_bar[as]);
       }
@@ -178,18 +195,16 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
   } else {
     // ---- epilogue warps ---------------------------------------------------------------------------
     const int ew = warp - 2;
-    const int quarter = warp & 3;    // TMEM lanes this warp may access: 32 * (warp id % 4)
-    const int col_group = ew >> 2;   // even / odd 32-column groups
+    const int quarter = warp & 3;     // TMEM lanes this warp may access: 32 * (warp id % 4)
+    const int col_group = ew >> 2;    // even / odd 32-column groups
     const int row = quarter * 32 + lane;
     const int act = p.act;
     const size_t up_dx = p.out2_ld;
     const size_t up_dy = static_cast<size_t>(2) * p.out_w * p.out2_ld;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int mt = mt0; mt < m_tiles; mt += mt_step, ++it) {
       const int as = it & 1;
-      const int nt = tile % n_tiles;
-      const int n0 = nt * p.tile_n;
-      const int m = (tile / n_tiles) * kBlockM + row;
+      const int m = mt * kBlockM + row;
       const bool row_ok = m < p.M;
       mbar_wait(&tmem_full_bar[as], (it >> 1) & 1);
       tc_fence_after_sync();
@@ -204,7 +219,6 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
         const int x = rem - y * p.out_w;
         urow = p.out2 + ((static_cast<size_t>(img) * 2 * p.out_h + 2 * y) * (2 * p.out_w) + 2 * x) * p.out2_ld;
       }
-      const float* bias_t = s_bias + nt * p.tile_n;
 
 #pragma unroll 1
       for (int c = col_group * 32; c < p.tile_n; c += 64) {
@@ -214,31 +228,34 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
         tmem_ld_wait();
         const int n = n0 + c;
         if (row_ok && n < p.N) {
+          // 32 independent bias+activation chains first (MUFU latency overlaps), then pack + store
+          const int valid = min(32, p.tile_n - c);  // 32 or 16 (tile_n % 16 == 0)
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float a = apply_act_fast(__uint_as_float(r[2 * j]) + s_bias[c + 2 * j], act);
+            const float b = apply_act_fast(__uint_as_float(r[2 * j + 1]) + s_bias[c + 2 * j + 1], act);
+            pk[j] = pack_half2(a, b);
+          }
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const int ng = n + 8 * g;
-            if (c + 8 * g >= p.tile_n) break;  // tile_n % 16 == 0: the upper half of the last group may be unused
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = apply_act_fast(__uint_as_float(r[8 * g + j]) + bias_t[c + 8 * g + j], act);
+            if (8 * g >= valid) break;
             if (ng + 8 <= p.N) {
-              uint4 pk;
-              pk.x = pack_half2(v[0], v[1]);
-              pk.y = pack_half2(v[2], v[3]);
-              pk.z = pack_half2(v[4], v[5]);
-              pk.w = pack_half2(v[6], v[7]);
-              *reinterpret_cast<uint4*>(orow + ng) = pk;
+              const uint4 q = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+              *reinterpret_cast<uint4*>(orow + ng) = q;
               if (urow != nullptr) {
-                *reinterpret_cast<uint4*>(urow + ng) = pk;
-                *reinterpret_cast<uint4*>(urow + up_dx + ng) = pk;
-                *reinterpret_cast<uint4*>(urow + up_dy + ng) = pk;
-                *reinterpret_cast<uint4*>(urow + up_dy + up_dx + ng) = pk;
+                *reinterpret_cast<uint4*>(urow + ng) = q;
+                *reinterpret_cast<uint4*>(urow + up_dx + ng) = q;
+                *reinterpret_cast<uint4*>(urow + up_dy + ng) = q;
+                *reinterpret_cast<uint4*>(urow + up_dy + up_dx + ng) = q;
               }
             } else {
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 if (ng + j < p.N) {
-                  const __half hv = __float2half_rn(v[j]);
+                  const uint32_t w2 = pk[4 * g + (j >> 1)];
+                  const __half hv = __ushort_as_half(static_cast<unsigned short>((j & 1) ? (w2 >> 16) : (w2 & 0xffffu)));
                   orow[ng + j] = hv;
                   if (urow != nullptr) {
                     urow[ng + j] = hv;
@@ -268,35 +285,32 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-static int32_t encode_w_map(CUtensorMap* tm, const void* w, int k_packed, int rows, int tile_n) {
+static int32_t encode_2d(CUtensorMap* tm, const void* base, cuuint64_t inner, cuuint64_t rows, cuuint64_t row_bytes,
+                         cuuint32_t box_inner, cuuint32_t box_rows, CUtensorMapSwizzle swz, CUtensorMapL2promotion l2,
+                         const char* what) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return fail(MAF_E_ARCH, "cuTensorMapEncodeTiled entry point not available");
-  cuuint64_t dims[2] = {static_cast<cuuint64_t>(k_packed), static_cast<cuuint64_t>(rows)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(k_packed) * 2};
-  cuuint32_t box[2] = {kBlockK, static_cast<cuuint32_t>(tile_n)};
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {row_bytes};
+  cuuint32_t box[2] = {box_inner, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(MAF_E_CUDA, "cuTensorMapEncodeTiled(W %dx%d) failed: %d", rows, k_packed, (int)r);
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, l2, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(MAF_E_CUDA, "cuTensorMapEncodeTiled(%s: inner=%llu rows=%llu pitch=%llu) failed: %d", what,
+                (unsigned long long)inner, (unsigned long long)rows, (unsigned long long)row_bytes, (int)r);
   return MAF_OK;
 }
 
+static int32_t encode_w_map(CUtensorMap* tm, const void* w, int k_packed, int rows, int tile_n) {
+  return encode_2d(tm, w, k_packed, rows, static_cast<cuuint64_t>(k_packed) * 2, kBlockK, tile_n,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "W");
+}
+
 static int32_t encode_a_map_2d(CUtensorMap* tm, const maf_tensor* t) {
-  EncodeTiledFn enc = encode_tiled_fn();
-  if (!enc) return fail(MAF_E_ARCH, "cuTensorMapEncodeTiled entry point not available");
   const cuuint64_t M = static_cast<cuuint64_t>(t->n) * t->h * t->w;
-  cuuint64_t dims[2] = {static_cast<cuuint64_t>(t->c), M};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(t->c_stride) * 2};
-  cuuint32_t box[2] = {kBlockK, kBlockM};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, t->ptr, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS)
-    return fail(MAF_E_CUDA, "cuTensorMapEncodeTiled(A c=%d ld=%d M=%llu) failed: %d", t->c, t->c_stride,
-                (unsigned long long)M, (int)r);
-  return MAF_OK;
+  return encode_2d(tm, t->ptr, t->c, M, static_cast<cuuint64_t>(t->c_stride) * 2, kBlockK, kBlockM,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "A");
 }
 
 static int32_t encode_a_map_im2col(CUtensorMap* tm, const maf_tensor* t) {
@@ -339,21 +353,38 @@ static int sm_count() {
 
 template <bool kIm2col>
 static int32_t launch_gemm(GemmParams& p, int n_tiles, int total_kb, cudaStream_t stream) {
-  const int stage_bytes = kABytes + p.tile_n * kBlockK * 2;
+  const int b_bytes = p.tile_n * kBlockK * 2;
   const int m_tiles = ceil_div(p.M, kBlockM);
-  const int total_tiles = m_tiles * n_tiles;
-  const int grid = total_tiles < 2 * sm_count() ? total_tiles : 2 * sm_count();  // persistent: 2 CTAs per SM
-  const int tiles_per_cta = ceil_div(total_tiles, grid);
-  // enough stages to hold ~2 tiles' worth of k-blocks (the producer runs ahead), within ~100 KB per CTA
-  int stages = total_kb * (tiles_per_cta > 1 ? 2 : 1);
-  if (stages > 6) stages = 6;
-  while (stages > 1 && stages * stage_bytes > 100 * 1024) --stages;
+  // persistent grid: 2 CTAs per SM, a multiple of n_tiles (each CTA owns one column tile)
+  int per_n = (2 * sm_count()) / n_tiles;
+  if (per_n < 1) per_n = 1;
+  if (per_n > m_tiles) per_n = m_tiles;
+  const int grid = per_n * n_tiles;
+  const int budget = 104 * 1024;  // ring + resident panel, so that 2 CTAs share one SM
+  const int panel = total_kb * b_bytes;
+  int stages;
+  if (panel <= kMaxResidentW && panel + 2 * kABytes <= budget) {
+    p.w_resident = 1;
+    stages = (budget - panel) / kABytes;
+    const int want = total_kb * 4 > 3 ? total_kb * 4 : 3;  // ~4 row tiles in flight
+    if (stages > want) stages = want;
+    if (stages > 8) stages = 8;
+  } else {
+    p.w_resident = 0;
+    stages = budget / (kABytes + b_bytes);
+    if (stages > 2 * total_kb) stages = 2 * total_kb;
+    if (stages > 6) stages = 6;
+  }
+  if (stages < 1) stages = 1;
+  const int slot_bytes = p.w_resident ? kABytes : kABytes + b_bytes;
   p.stages = stages;
+  p.total_kb = total_kb;
   p.n_tiles = n_tiles;
+  p.m_stride = per_n;
   p.tmem_cols = 2 * pow2_cols(p.tile_n);
   p.idesc = umma_idesc_f16(kBlockM, p.tile_n);
-  const size_t smem = static_cast<size_t>(stages) * stage_bytes + (2 * stages + 4) * 8 + 16 +
-                      static_cast<size_t>(n_tiles) * p.tile_n * 4 + 1024;
+  const size_t smem = static_cast<size_t>(p.w_resident ? panel : 0) + static_cast<size_t>(stages) * slot_bytes +
+                      (2 * stages + 5) * 8 + 16 + static_cast<size_t>(p.tile_n) * 4 + 1024;
   static bool configured[2] = {false, false};
   if (!configured[kIm2col]) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<kIm2col>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -361,7 +392,7 @@ static int32_t launch_gemm(GemmParams& p, int n_tiles, int total_kb, cudaStream_
     if (e != cudaSuccess) return fail(MAF_E_CUDA, "cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e));
     configured[kIm2col] = true;
   }
-  if (smem > 200 * 1024) return fail(MAF_E_ARG, "gemm: %zu B of shared memory needed (cout too large)", smem);
+  if (smem > 200 * 1024) return fail(MAF_E_ARG, "gemm: %zu B of shared memory needed", smem);
   gemm_tc_kernel<kIm2col><<<grid, kGemmThreads, smem, stream>>>(p);
   return check_launch(kIm2col ? "conv3x3s2 kernel launch" : "conv1x1 kernel launch");
 }
