@@ -163,6 +163,7 @@ __global__ void __launch_bounds__(1024) nms_select_kernel(const NmsParams p) {
   float* c_box = k_box + static_cast<size_t>(round_up(p.max_det, 2)) * 5;      // chunk: [kChunk][5] (8-B aligned)
   unsigned long long* c_mask = reinterpret_cast<unsigned long long*>(c_box + kChunk * 5);  // [kChunk][4]
   int* c_alive = reinterpret_cast<int*>(c_mask + kChunk * 4);                  // [kChunk]
+  int* c_kept = c_alive + kChunk;                                              // [kChunk] chunk-local indices kept
   __shared__ int s_nk;
   __shared__ int s_done;
 
@@ -253,7 +254,8 @@ __global__ void __launch_bounds__(1024) nms_select_kernel(const NmsParams p) {
       c_mask[t] = bits;
     }
     __syncthreads();
-    // (4) sequential resolve (one thread), appends to the kept list and writes the output rows
+    // (4) sequential resolve: one thread, shared memory and registers only (no global access on the
+    //     critical path); records which chunk entries are kept
     if (threadIdx.x == 0) {
       unsigned long long rem[4] = {0ull, 0ull, 0ull, 0ull};
       int nk = nk0;
@@ -263,8 +265,20 @@ __global__ void __launch_bounds__(1024) nms_select_kernel(const NmsParams p) {
         rem[1] |= c_mask[i * 4 + 1];
         rem[2] |= c_mask[i * 4 + 2];
         rem[3] |= c_mask[i * 4 + 3];
+        c_kept[nk - nk0] = i;
+        ++nk;
+      }
+      s_nk = nk;
+      s_done = nk >= p.max_det ? 1 : 0;
+    }
+    __syncthreads();
+    // (5) parallel: append the kept boxes to the kept list and write their output rows
+    {
+      const int nk1 = s_nk;
+      for (int t = threadIdx.x; t < nk1 - nk0; t += blockDim.x) {
+        const int i = c_kept[t];
         const float* cb = c_box + i * 5;
-        float* kb = k_box + nk * 5;
+        float* kb = k_box + (nk0 + t) * 5;
         kb[0] = cb[0];
         kb[1] = cb[1];
         kb[2] = cb[2];
@@ -276,17 +290,14 @@ __global__ void __launch_bounds__(1024) nms_select_kernel(const NmsParams p) {
         const int a = idx / p.nc, c = idx - a * p.nc;
         const float* row = pred_b + static_cast<size_t>(a) * no;
         const float cx = row[0], cy = row[1], w = row[2], h = row[3];
-        float* o = det + static_cast<size_t>(nk) * 6;
+        float* o = det + static_cast<size_t>(nk0 + t) * 6;
         o[0] = __fsub_rn(cx, __fdiv_rn(w, 2.0f));
         o[1] = __fsub_rn(cy, __fdiv_rn(h, 2.0f));
         o[2] = __fadd_rn(cx, __fdiv_rn(w, 2.0f));
         o[3] = __fadd_rn(cy, __fdiv_rn(h, 2.0f));
         o[4] = __uint_as_float(~static_cast<unsigned>(key >> 32));
         o[5] = static_cast<float>(c);
-        ++nk;
       }
-      s_nk = nk;
-      s_done = nk >= p.max_det ? 1 : 0;
     }
     __syncthreads();
     if (s_done) break;
@@ -360,7 +371,7 @@ extern "C" int32_t mafb200_nms(const float* pred, int32_t batch, int32_t anchors
 
   const size_t smem = static_cast<size_t>(kSortSmemKeys) * 8 + static_cast<size_t>(round_up(max_det, 2)) * 5 * 4 +
                       kChunk * 5 * 4 +
-                      kChunk * 4 * 8 + kChunk * 4;
+                      kChunk * 4 * 8 + kChunk * 4 * 2;
   static bool configured = false;
   if (!configured) {
     e = cudaFuncSetAttribute(nms_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);

@@ -255,13 +255,20 @@ class Engine:
     """A plan bound to one device, one batch size and one set of folded weights."""
 
     def __init__(self, graph: Graph, folded: Folded, batch: int, height: int = 640, width: int = 640,
-                 device: Optional[torch.device] = None, use_cuda_graph: bool = True, reuse_buffers: bool = True):
+                 device: Optional[torch.device] = None, use_cuda_graph: bool = True, reuse_buffers: Optional[bool] = None,
+                 n_streams: int = 4):
         if not torch.cuda.is_available():
             raise RuntimeError("maf_yolo_b200.Engine needs a B200 GPU: the hot path has no CPU fallback")
         self.device = torch.device(device if device is not None else "cuda")
         self.graph, self.batch, self.height, self.width = graph, batch, height, width
         self.plan = Plan(graph, height, width)
         self.use_cuda_graph = use_cuda_graph
+        # Branch-level concurrency (captured into the CUDA graph): independent chains of the yaml graph —
+        # the three heads and their cls / reg towers, the MAFPN down-sampling convs — run on side streams.
+        # Aliased arena buffers would serialise unrelated branches, so multi-stream plans do not reuse memory.
+        self.n_streams = max(1, n_streams) if use_cuda_graph else 1
+        if reuse_buffers is None:
+            reuse_buffers = self.n_streams == 1
         with torch.cuda.device(self.device):
             nbytes = self.plan.assign_offsets(batch, reuse=reuse_buffers)
             self.arena = torch.empty(nbytes // 2, dtype=torch.float16, device=self.device)
@@ -273,6 +280,8 @@ class Engine:
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._graph_x_ptr = None
         self.launches_per_forward = len(self._calls)
+        self._schedule = self._make_schedule() if self.n_streams > 1 else None
+        self._side_streams = [torch.cuda.Stream(device=self.device) for _ in range(self.n_streams - 1)]
 
     # ---- binding ----------------------------------------------------------------------------------
     def view(self, v: _View) -> NHWC:
@@ -321,6 +330,75 @@ class Engine:
             return lambda: ops.head_decode(reads[:nl], reads[nl:], strides, reg_max, self.pred)
         raise NotImplementedError(op.kind)
 
+    # ---- multi-stream schedule ------------------------------------------------------------------------
+    def _make_schedule(self):
+        """Dependencies from buffer overlap (RAW / WAR / WAW on arena byte ranges), then greedy list
+        scheduling onto `n_streams` streams: an op continues the stream of one of its producers when that
+        producer is still the stream's tail, otherwise takes the least-recently-used stream."""
+        ops_ = self.plan.ops
+
+        def ranges(views):
+            return [(v.buf.offset, v.buf.offset + v.buf.nbytes(self.batch)) for v in views]
+
+        rd = [ranges(o.reads) for o in ops_]
+        wr = [ranges(o.writes) for o in ops_]
+        for j, o in enumerate(ops_):
+            if o.kind == "decode":
+                wr[j] = wr[j] + [(-2, -1)]  # the pred tensor (outside the arena)
+
+        def hit(a, b):
+            return any(x0 < y1 and y0 < x1 for x0, x1 in a for y0, y1 in b)
+
+        deps = []
+        for j in range(len(ops_)):
+            d = {i for i in range(j) if hit(wr[i], rd[j]) or hit(rd[i], wr[j]) or hit(wr[i], wr[j])}
+            deps.append(d)
+        n = self.n_streams
+        tail = [-1] * n
+        stream_of, waits = [], []
+        for j in range(len(ops_)):
+            if j == 0:
+                s = 0
+            else:
+                cands = [t for t in range(n) if tail[t] in deps[j]]
+                s = max(cands, key=lambda t: tail[t]) if cands else min(range(n), key=lambda t: tail[t])
+            w = []
+            for t in range(n):
+                if t == s:
+                    continue
+                on_t = [i for i in deps[j] if stream_of[i] == t]
+                if on_t:
+                    w.append(max(on_t))
+            stream_of.append(s)
+            waits.append(w)
+            tail[s] = j
+        need_event = {i for w in waits for i in w}
+        return stream_of, waits, need_event
+
+    def _launch_scheduled(self, first: int):
+        """Launches ops[first:] over the main stream + side streams with event dependencies."""
+        stream_of, waits, need_event = self._schedule
+        main = torch.cuda.current_stream(self.device)
+        streams = [main] + self._side_streams
+        fork = torch.cuda.Event()
+        fork.record(main)
+        for st in self._side_streams:
+            st.wait_event(fork)
+        events = {}
+        for j in range(first, len(self._calls)):
+            st = streams[stream_of[j]]
+            for i in waits[j]:
+                if i >= first:
+                    st.wait_event(events[i])
+            with torch.cuda.stream(st):
+                self._calls[j]()
+            if j in need_event:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                events[j] = ev
+        for st in self._side_streams:
+            main.wait_stream(st)
+
     # ---- execution ----------------------------------------------------------------------------------
     def _check_input(self, x: torch.Tensor):
         if tuple(x.shape) != (self.batch, 3, self.height, self.width):
@@ -352,8 +430,11 @@ class Engine:
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                for call in self._calls[1:]:
-                    call()
+                if self._schedule is not None:
+                    self._launch_scheduled(1)
+                else:
+                    for call in self._calls[1:]:
+                        call()
             self._graph = g
             self._calls[0]()
         self._graph.replay()

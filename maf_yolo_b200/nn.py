@@ -88,7 +88,8 @@ class B200DetectModel(torch.nn.Module):
     Engines (plan + arena + CUDA graph) are built lazily per (batch, H, W, device).
     """
 
-    def __init__(self, graph, folded, names=None, use_cuda_graph: bool = True, return_featmaps: bool = False):
+    def __init__(self, graph, folded, names=None, use_cuda_graph: bool = True, return_featmaps: bool = False,
+                 n_streams: int = 4):
         super().__init__()
         self.graph = graph
         self.folded = folded
@@ -97,6 +98,7 @@ class B200DetectModel(torch.nn.Module):
         self.stride = torch.tensor(graph.strides)
         self.use_cuda_graph = use_cuda_graph
         self.return_featmaps = return_featmaps
+        self.n_streams = n_streams
         self._engines = {}
         self.training = False
 
@@ -119,7 +121,7 @@ class B200DetectModel(torch.nn.Module):
         key = (b, h, w, str(x.device))
         eng = self._engines.get(key)
         if eng is None:
-            eng = Engine(self.graph, self.folded, b, h, w, x.device, self.use_cuda_graph)
+            eng = Engine(self.graph, self.folded, b, h, w, x.device, self.use_cuda_graph, n_streams=self.n_streams)
             self._engines[key] = eng
         return eng
 
