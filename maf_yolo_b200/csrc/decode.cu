@@ -36,6 +36,7 @@ struct DecodeParams {
 
 __global__ void __launch_bounds__(256) head_decode_kernel(const __grid_constant__ DecodeParams p) {
   __shared__ float s_box[kAnchorsPerCta][4];
+  __shared__ __align__(16) __half s_reg[kAnchorsPerCta * 264];  // up to 4*(63+1)=256 (+pad) halves per anchor
   const int b = blockIdx.y;
   int lvl = 0;
   while (lvl + 1 < p.n_levels && static_cast<int>(blockIdx.x) >= p.cta_off[lvl + 1]) ++lvl;
@@ -43,6 +44,28 @@ __global__ void __launch_bounds__(256) head_decode_kernel(const __grid_constant_
   const int a0 = (blockIdx.x - p.cta_off[lvl]) * kAnchorsPerCta;
   const int na = min(kAnchorsPerCta, L - a0);
   const int no = 5 + p.nc;
+  const int reg_ld = p.reg_ld[lvl];
+  const int nreg = 4 * p.bins;
+
+  // ---- phase 0: stage the reg rows of the CTA's anchors (rows are contiguous: coalesced 16-B loads) ----
+  const __half* reg_src = p.reg[lvl] + (static_cast<size_t>(b) * L + a0) * reg_ld;
+  const bool fast = (reg_ld & 7) == 0 && (reinterpret_cast<uintptr_t>(reg_src) & 15) == 0 && reg_ld <= 264;
+  const int pitch = fast ? reg_ld : nreg;  // smem row pitch (halves)
+  {
+    const __half* src = reg_src;
+    if (fast) {
+      const int nvec = na * reg_ld / 8;
+      const uint4* s4 = reinterpret_cast<const uint4*>(src);
+      uint4* d4 = reinterpret_cast<uint4*>(s_reg);
+      for (int i = threadIdx.x; i < nvec; i += blockDim.x) d4[i] = __ldg(s4 + i);
+    } else {
+      for (int i = threadIdx.x; i < na * nreg; i += blockDim.x) {
+        const int al = i / nreg, j = i - al * nreg;
+        s_reg[al * pitch + j] = __ldg(src + static_cast<size_t>(al) * reg_ld + j);
+      }
+    }
+  }
+  __syncthreads();
 
   // ---- phase 1: DFL expectation per (anchor, side); 4 consecutive lanes = one anchor ------------
   {
@@ -50,12 +73,12 @@ __global__ void __launch_bounds__(256) head_decode_kernel(const __grid_constant_
     const int a = a0 + al;
     float dist = 0.f;
     if (al < na) {
-      const __half* r = p.reg[lvl] + (static_cast<size_t>(b) * L + a) * p.reg_ld[lvl] + side * p.bins;
+      const __half* r = s_reg + al * pitch + side * p.bins;
       float mx = -INFINITY;
-      for (int i = 0; i < p.bins; ++i) mx = fmaxf(mx, __half2float(__ldg(r + i)));
+      for (int i = 0; i < p.bins; ++i) mx = fmaxf(mx, __half2float(r[i]));
       float s = 0.f, e = 0.f;
       for (int i = 0; i < p.bins; ++i) {
-        const float ex = expf(__half2float(__ldg(r + i)) - mx);
+        const float ex = __expf(__half2float(r[i]) - mx);
         s += ex;
         e = fmaf(static_cast<float>(i), ex, e);
       }
@@ -80,22 +103,26 @@ __global__ void __launch_bounds__(256) head_decode_kernel(const __grid_constant_
   }
   __syncthreads();
 
-  // ---- phase 2: stream the [na, 5+nc] rows -----------------------------------------------------
-  float* dst = p.pred + (static_cast<size_t>(b) * p.total_anchors + p.anchor_off[lvl] + a0) * no;
-  const __half* cls = p.cls[lvl] + (static_cast<size_t>(b) * L + a0) * p.cls_ld[lvl];
-  const int count = na * no;
-  for (int i = threadIdx.x; i < count; i += blockDim.x) {
-    const int al = i / no, j = i - al * no;
-    float v;
-    if (j < 4) {
-      v = s_box[al][j];
-    } else if (j == 4) {
-      v = 1.0f;
-    } else {
-      const float z = __half2float(__ldg(cls + static_cast<size_t>(al) * p.cls_ld[lvl] + (j - 5)));
-      v = 1.0f / (1.0f + expf(-z));
+  // ---- phase 2: one warp per output row (anchor), lanes stride the 5+nc columns: contiguous fp32
+  //      stores, contiguous fp16 class-logit loads, no integer division ---------------------------------
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* dst0 = p.pred + (static_cast<size_t>(b) * p.total_anchors + p.anchor_off[lvl] + a0) * no;
+  const __half* cls0 = p.cls[lvl] + (static_cast<size_t>(b) * L + a0) * p.cls_ld[lvl];
+  for (int al = warp; al < na; al += 8) {
+    float* dst = dst0 + static_cast<size_t>(al) * no;
+    const __half* cls = cls0 + static_cast<size_t>(al) * p.cls_ld[lvl];
+    for (int j = lane; j < no; j += 32) {
+      float v;
+      if (j < 4) {
+        v = s_box[al][j];
+      } else if (j == 4) {
+        v = 1.0f;
+      } else {
+        const float z = __half2float(__ldg(cls + (j - 5)));
+        v = __fdividef(1.0f, 1.0f + __expf(-z));
+      }
+      dst[j] = v;
     }
-    dst[i] = v;
   }
 }
 
@@ -107,7 +134,7 @@ extern "C" int32_t mafb200_head_decode(const maf_tensor* cls_logits, const maf_t
                                        int32_t n_levels, int32_t reg_max, float* pred, void* stream) {
   if (!cls_logits || !reg || !strides || !pred) return fail(MAF_E_ARG, "head_decode: null pointer");
   if (n_levels < 1 || n_levels > kMaxLevels) return fail(MAF_E_ARG, "head_decode: n_levels=%d (1..%d)", n_levels, kMaxLevels);
-  if (reg_max < 1 || reg_max > 63) return fail(MAF_E_ARG, "head_decode: reg_max=%d", reg_max);
+  if (reg_max < 1 || reg_max > 63) return fail(MAF_E_ARG, "head_decode: reg_max=%d (1..63)", reg_max);
   DecodeParams p;
   memset(&p, 0, sizeof(p));
   const int nc = cls_logits[0].c, n = cls_logits[0].n;

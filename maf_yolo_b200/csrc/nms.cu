@@ -164,6 +164,7 @@ __global__ void __launch_bounds__(1024) nms_select_kernel(const NmsParams p) {
   unsigned long long* c_mask = reinterpret_cast<unsigned long long*>(c_box + kChunk * 5);  // [kChunk][4]
   int* c_alive = reinterpret_cast<int*>(c_mask + kChunk * 4);                  // [kChunk]
   int* c_kept = c_alive + kChunk;                                              // [kChunk] chunk-local indices kept
+  unsigned* c_alive_bits = reinterpret_cast<unsigned*>(c_kept + kChunk);       // [kChunk / 32]
   __shared__ int s_nk;
   __shared__ int s_done;
 
@@ -237,36 +238,52 @@ __global__ void __launch_bounds__(1024) nms_select_kernel(const NmsParams p) {
         if (dead) c_alive[ci] = 0;
       }
     }
-    // (3) intra-chunk IoU bit matrix: bit j of row i set if i suppresses j (j > i)
+    __syncthreads();
+    // alive bitmap of the chunk (one ballot per warp of the first 256 threads)
+    if (threadIdx.x < kChunk) {
+      const unsigned bal = __ballot_sync(0xffffffffu, threadIdx.x < cn && c_alive[threadIdx.x] != 0);
+      if ((threadIdx.x & 31) == 0) c_alive_bits[threadIdx.x >> 5] = bal;
+    }
+    // (3) intra-chunk IoU bit matrix: bit j of row i set if i suppresses j (j > i).  Rows of candidates
+    //     already dead and 64-column words entirely at or below the diagonal are skipped.
     for (int t = threadIdx.x; t < kChunk * 4; t += blockDim.x) {
       const int i = t >> 2, wq = t & 3;
-      if (i >= cn) continue;
-      const float* ib = c_box + i * 5;
-      unsigned long long bits = 0ull;
       const int j0 = wq * 64;
-      for (int jj = 0; jj < 64; ++jj) {
-        const int j = j0 + jj;
-        if (j > i && j < cn) {
-          const float* jb = c_box + j * 5;
-          if (iou_gt(ib[0], ib[1], ib[2], ib[3], ib[4], jb[0], jb[1], jb[2], jb[3], jb[4], p.iou)) bits |= 1ull << jj;
-        }
+      if (i >= cn || !c_alive[i] || j0 + 63 <= i) continue;  // c_mask was zeroed in (1)
+      const float* ib = c_box + i * 5;
+      const float i0 = ib[0], i1 = ib[1], i2 = ib[2], i3 = ib[3], i4 = ib[4];
+      unsigned long long bits = 0ull;
+      const int jlo = max(j0, i + 1), jhi = min(j0 + 64, cn);
+      for (int j = jlo; j < jhi; ++j) {
+        const float* jb = c_box + j * 5;
+        if (iou_gt(i0, i1, i2, i3, i4, jb[0], jb[1], jb[2], jb[3], jb[4], p.iou)) bits |= 1ull << (j - j0);
       }
       c_mask[t] = bits;
     }
     __syncthreads();
-    // (4) sequential resolve: one thread, shared memory and registers only (no global access on the
-    //     critical path); records which chunk entries are kept
+    // (4) sequential resolve by one thread: walks only the SET bits of (alive & ~removed), so the cost is
+    //     per kept box (<= max_det per image), shared memory and registers only
     if (threadIdx.x == 0) {
       unsigned long long rem[4] = {0ull, 0ull, 0ull, 0ull};
       int nk = nk0;
-      for (int i = 0; i < cn && nk < p.max_det; ++i) {
-        if (!c_alive[i] || ((rem[i >> 6] >> (i & 63)) & 1ull)) continue;
-        rem[0] |= c_mask[i * 4 + 0];
-        rem[1] |= c_mask[i * 4 + 1];
-        rem[2] |= c_mask[i * 4 + 2];
-        rem[3] |= c_mask[i * 4 + 3];
-        c_kept[nk - nk0] = i;
-        ++nk;
+#pragma unroll
+      for (int wi = 0; wi < 4; ++wi) {
+        const unsigned long long alive =
+            static_cast<unsigned long long>(c_alive_bits[2 * wi]) | (static_cast<unsigned long long>(c_alive_bits[2 * wi + 1]) << 32);
+        unsigned long long todo = alive;
+        while (nk < p.max_det) {
+          const unsigned long long avail = todo & ~rem[wi];
+          if (avail == 0ull) break;
+          const int bpos = __ffsll(static_cast<long long>(avail)) - 1;
+          const int i = wi * 64 + bpos;
+          todo &= ~((2ull << bpos) - 1ull);  // everything up to and including bpos is decided
+          rem[0] |= c_mask[i * 4 + 0];
+          rem[1] |= c_mask[i * 4 + 1];
+          rem[2] |= c_mask[i * 4 + 2];
+          rem[3] |= c_mask[i * 4 + 3];
+          c_kept[nk - nk0] = i;
+          ++nk;
+        }
       }
       s_nk = nk;
       s_done = nk >= p.max_det ? 1 : 0;
@@ -371,7 +388,7 @@ extern "C" int32_t mafb200_nms(const float* pred, int32_t batch, int32_t anchors
 
   const size_t smem = static_cast<size_t>(kSortSmemKeys) * 8 + static_cast<size_t>(round_up(max_det, 2)) * 5 * 4 +
                       kChunk * 5 * 4 +
-                      kChunk * 4 * 8 + kChunk * 4 * 2;
+                      kChunk * 4 * 8 + kChunk * 4 * 2 + (kChunk / 32) * 4;
   static bool configured = false;
   if (!configured) {
     e = cudaFuncSetAttribute(nms_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);

@@ -3,9 +3,16 @@
 //
 // Reads the reference's input tensor as it is — NCHW, fp32/fp16 in [0,1] or raw uint8 (the
 // `imgs.float(); imgs /= 255` of yolov6/core/evaler.py:161-163 is folded in) — and writes NHWC fp16.
-// K = 27 is far too small for a tensor-core tile, and the layer is pure bandwidth
-// (4.9 MB fp32 in + 4.9 MB fp16 out per image at N width), so it runs on CUDA cores:
-// one thread per output pixel, 8 output channels at a time, weights broadcast from smem.
+//
+// K = 27 taps is too small for TMA-fed tiles but a CUDA-core version of this layer is FFMA-bound
+// (648 FMA per output pixel, measured 170 us at bs32 against a 48 us HBM floor), so the multiply runs on
+// the tensor core with a SOFTWARE im2col: each of the CTA's 128 threads gathers the 27 inputs of one
+// output pixel, converts to fp16 and writes one row of the A operand directly in the UMMA no-swizzle
+// K-major canonical layout (8x16-byte core matrices; K padded to 32); one thread issues two
+// tcgen05.mma (128 x Cout x 16); the same thread-per-pixel mapping reads the TMEM row back, adds bias,
+// applies the activation and stores Cout contiguous fp16.  The gather itself is 9 coalesced pair loads
+// + 9 warp shuffles per thread (taps kx=1,2 are the aligned pixel pair 2*ox, 2*ox+1; tap kx=0 comes from
+// the neighbouring lane).
 #include "common.cuh"
 #include "host.h"
 
@@ -26,77 +33,189 @@ __device__ __forceinline__ float load_px<uint8_t>(const uint8_t* p) {
   return static_cast<float>(__ldg(p)) / 255.0f;  // same fp32 division the reference performs
 }
 
+// (x[2*ox], x[2*ox+1]) as one aligned vector load: lanes of a warp read one contiguous row segment
 template <typename T>
-__global__ void __launch_bounds__(256) stem_conv_kernel(const T* __restrict__ x, const float* __restrict__ wgt,
-                                                         const float* __restrict__ bias, __half* __restrict__ out,
-                                                         int n, int h, int w, int cout, int out_ld, int act) {
-  extern __shared__ float s_w[];  // [27][cout_pad8] then bias[cout_pad8]
-  const int cpad = round_up(cout, 8);
-  float* s_b = s_w + 27 * cpad;
-  for (int i = threadIdx.x; i < 27 * cpad; i += blockDim.x) {
-    const int tap = i / cpad, co = i - tap * cpad;
-    // wgt is [co][ky][kx][ci]; tap index here is (ci*9 + ky*3 + kx) to match the load order below
-    const int ci = tap / 9, kk = tap - ci * 9;
-    s_w[i] = co < cout ? wgt[(co * 9 + kk) * 3 + ci] : 0.0f;
-  }
-  for (int i = threadIdx.x; i < cpad; i += blockDim.x) s_b[i] = i < cout ? bias[i] : 0.0f;
-  __syncthreads();
+__device__ __forceinline__ float2 load_pair(const T* p);
+template <>
+__device__ __forceinline__ float2 load_pair<float>(const float* p) {
+  return __ldg(reinterpret_cast<const float2*>(p));
+}
+template <>
+__device__ __forceinline__ float2 load_pair<__half>(const __half* p) {
+  return __half22float2(__ldg(reinterpret_cast<const __half2*>(p)));
+}
+template <>
+__device__ __forceinline__ float2 load_pair<uint8_t>(const uint8_t* p) {
+  const uchar2 u = __ldg(reinterpret_cast<const uchar2*>(p));
+  return make_float2(static_cast<float>(u.x) / 255.0f, static_cast<float>(u.y) / 255.0f);
+}
 
+constexpr int kStemK = 32;                 // 27 taps padded to 2 x UMMA_K
+constexpr uint32_t kStemLBO = 128;         // bytes between the two 8-element K chunks of one core-matrix row group
+constexpr uint32_t kStemSBO = 4 * 128;     // bytes between 8-row groups (4 K-chunks of 128 B each)
+
+// No-swizzle K-major smem matrix descriptor (layout type 0): start>>4 | LBO>>4 @16 | SBO>>4 @32 | version 1 @46
+__device__ __forceinline__ uint64_t umma_smem_desc_noswz(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(kStemLBO >> 4) << 16;
+  d |= static_cast<uint64_t>(kStemSBO >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  return d;
+}
+
+// byte offset of (row r, K-chunk kc) in the canonical layout above
+__device__ __forceinline__ uint32_t stem_off(int r, int kc) { return (r >> 3) * kStemSBO + kc * kStemLBO + (r & 7) * 16; }
+
+template <typename T>
+__global__ void __launch_bounds__(128) stem_conv_kernel(const T* __restrict__ x, const float* __restrict__ wgt,
+                                                         const float* __restrict__ bias, __half* __restrict__ out,
+                                                         int n, int h, int w, int cout, int tile_n, int tmem_cols,
+                                                         uint32_t idesc, int out_ld, int act) {
+  __shared__ __align__(128) uint8_t s_a[128 * kStemK * 2];   // 8 KB: A operand, 128 pixels x 32 k
+  __shared__ __align__(128) uint8_t s_b[64 * kStemK * 2];    // 4 KB: B operand, <= 64 output channels x 32 k
+  __shared__ float s_bias[64];
+  __shared__ uint64_t s_bar;
+  __shared__ uint32_t s_tmem;
+
+  const int t = threadIdx.x;
+  const int warp = t >> 5;
   const int ho = h >> 1, wo = w >> 1;
   const long long total = static_cast<long long>(n) * ho * wo;
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int ox = static_cast<int>(idx % wo);
-  const int oy = static_cast<int>((idx / wo) % ho);
-  const int b = static_cast<int>(idx / (static_cast<long long>(wo) * ho));
+  const long long n_tiles = (total + 127) / 128;
 
-  float v[27];
-  const T* xb = x + static_cast<size_t>(b) * 3 * h * w;
+  if (t == 0) {
+    mbar_init(&s_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&s_tmem, tmem_cols);
+    tmem_relinquish();
+  }
+  // B operand: row = output channel, k = (ky*3 + kx)*3 + ci == the flat index of weight[co][ky][kx][ci]
+  for (int i = t; i < tile_n * 4; i += 128) {
+    const int co = i >> 2, kc = i & 3;
+    uint32_t pk[4];
 #pragma unroll
-  for (int ci = 0; ci < 3; ++ci) {
+    for (int j = 0; j < 4; ++j) {
+      const int k0 = kc * 8 + 2 * j;
+      const float a = (co < cout && k0 < 27) ? __ldg(wgt + co * 27 + k0) : 0.0f;
+      const float b = (co < cout && k0 + 1 < 27) ? __ldg(wgt + co * 27 + k0 + 1) : 0.0f;
+      pk[j] = pack_half2(a, b);
+    }
+    *reinterpret_cast<uint4*>(s_b + stem_off(co, kc)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+  if (t < 64) s_bias[t] = t < cout ? __ldg(bias + t) : 0.0f;
+
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = s_tmem;
+  const uint64_t da = umma_smem_desc_noswz(smem_u32(s_a));
+  const uint64_t db = umma_smem_desc_noswz(smem_u32(s_b));
+  const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+
+  // Persistent CTA: TMEM, barrier and the B operand are set up once; loop over 128-pixel tiles.
+  uint32_t phase = 0;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, phase ^= 1) {
+  const long long idx = tile * 128 + t;
+  // A operand: one output pixel per thread, 27 taps in (ky, kx, ci) order
+  {
+    float v[kStemK];
+#pragma unroll
+    for (int k = 27; k < kStemK; ++k) v[k] = 0.0f;
+    // Taps kx = 1,2 of output pixel ox are the aligned pair (2*ox, 2*ox+1); tap kx = 0 (pixel 2*ox-1) is
+    // the left neighbour lane's second element (warp shuffle) — 9 coalesced vector loads per thread
+    // instead of 27 strided scalar ones.  (w is even, so the pair never crosses the row end.)
+    const bool live = idx < total;
+    const long long cidx = live ? idx : total - 1;
+    const int ox = static_cast<int>(cidx % wo);
+    const int oy = static_cast<int>((cidx / wo) % ho);
+    const int b = static_cast<int>(cidx / (static_cast<long long>(wo) * ho));
+    const int lane = t & 31;
+    const bool from_lane = lane > 0 && ox > 0;  // lane-1 then holds output pixel ox-1 of the same row
+    const T* xb = x + static_cast<size_t>(b) * 3 * h * w;
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
       const int iy = 2 * oy + ky - 1;
+      const bool row_ok = iy >= 0 && iy < h;
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int ix = 2 * ox + kx - 1;
-        const bool ok = iy >= 0 && iy < h && ix >= 0 && ix < w;
-        v[ci * 9 + ky * 3 + kx] = ok ? load_px<T>(xb + (static_cast<size_t>(ci) * h + iy) * w + ix) : 0.0f;
+      for (int ci = 0; ci < 3; ++ci) {
+        const T* rowp = xb + (static_cast<size_t>(ci) * h + (row_ok ? iy : 0)) * w + 2 * ox;
+        float2 pr = make_float2(0.f, 0.f);
+        if (row_ok) pr = load_pair<T>(rowp);
+        float left = __shfl_up_sync(0xffffffffu, pr.y, 1);
+        if (!from_lane) left = (row_ok && ox > 0) ? load_px<T>(rowp - 1) : 0.0f;
+        v[(ky * 3 + 0) * 3 + ci] = left;
+        v[(ky * 3 + 1) * 3 + ci] = pr.x;
+        v[(ky * 3 + 2) * 3 + ci] = pr.y;
+      }
+    }
+    (void)live;
+#pragma unroll
+    for (int kc = 0; kc < 4; ++kc) {
+      *reinterpret_cast<uint4*>(s_a + stem_off(t, kc)) =
+          make_uint4(pack_half2(v[8 * kc], v[8 * kc + 1]), pack_half2(v[8 * kc + 2], v[8 * kc + 3]),
+                     pack_half2(v[8 * kc + 4], v[8 * kc + 5]), pack_half2(v[8 * kc + 6], v[8 * kc + 7]));
+    }
+  }
+  fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+
+  if (t == 0) {
+#pragma unroll
+    for (int k = 0; k < kStemK / 16; ++k) {
+      // 16 k-elements = two 8-element chunks = 2 * LBO bytes further: +((2*LBO) >> 4) in the address field
+      tc_mma_f16(tmem_base, da + k * ((2 * kStemLBO) >> 4), db + k * ((2 * kStemLBO) >> 4), idesc, k != 0 ? 1u : 0u);
+    }
+    tc_commit(&s_bar);
+  }
+  __syncwarp();
+  mbar_wait(&s_bar, phase);
+  tc_fence_after_sync();
+
+  // epilogue: thread t == TMEM lane t == output pixel idx
+  __half* orow = out + static_cast<size_t>(idx < total ? idx : 0) * out_ld;
+#pragma unroll 1
+  for (int c = 0; c < tile_n; c += 16) {
+    uint32_t r[16];
+    __syncwarp();
+    tmem_ld_32x32b_x16(taddr + c, r);
+    tmem_ld_wait();
+    if (idx < total && c < cout) {
+      uint32_t pk[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        pk[j] = pack_half2(apply_act_fast(__uint_as_float(r[2 * j]) + s_bias[c + 2 * j], act),
+                           apply_act_fast(__uint_as_float(r[2 * j + 1]) + s_bias[c + 2 * j + 1], act));
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        const int c8 = c + 8 * g;
+        if (c8 + 8 <= cout) {
+          *reinterpret_cast<uint4*>(orow + c8) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+        } else {
+          for (int j = 0; j < 8; ++j) {
+            if (c8 + j < cout) {
+              const uint32_t w2 = pk[4 * g + (j >> 1)];
+              orow[c8 + j] = __ushort_as_half(static_cast<unsigned short>((j & 1) ? (w2 >> 16) : (w2 & 0xffffu)));
+            }
+          }
+        }
       }
     }
   }
 
-  __half* orow = out + static_cast<size_t>(idx) * out_ld;
-  for (int c0 = 0; c0 < cout; c0 += 8) {
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = s_b[c0 + j];
-#pragma unroll
-    for (int t = 0; t < 27; ++t) {
-      const float4 w0 = *reinterpret_cast<const float4*>(&s_w[t * cpad + c0]);
-      const float4 w1 = *reinterpret_cast<const float4*>(&s_w[t * cpad + c0 + 4]);
-      acc[0] = fmaf(v[t], w0.x, acc[0]);
-      acc[1] = fmaf(v[t], w0.y, acc[1]);
-      acc[2] = fmaf(v[t], w0.z, acc[2]);
-      acc[3] = fmaf(v[t], w0.w, acc[3]);
-      acc[4] = fmaf(v[t], w1.x, acc[4]);
-      acc[5] = fmaf(v[t], w1.y, acc[5]);
-      acc[6] = fmaf(v[t], w1.z, acc[6]);
-      acc[7] = fmaf(v[t], w1.w, acc[7]);
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = apply_act_fast(acc[j], act);
-    if (c0 + 8 <= cout) {
-      uint4 pk;
-      pk.x = pack_half2(acc[0], acc[1]);
-      pk.y = pack_half2(acc[2], acc[3]);
-      pk.z = pack_half2(acc[4], acc[5]);
-      pk.w = pack_half2(acc[6], acc[7]);
-      *reinterpret_cast<uint4*>(orow + c0) = pk;
-    } else {
-      for (int j = 0; j < 8 && c0 + j < cout; ++j) orow[c0 + j] = __float2half_rn(acc[j]);
-    }
-  }
+  // the next tile's gather overwrites s_a and its MMA overwrites the accumulator: all reads must be done
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  }  // tile loop
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
 }  // namespace mafb200
@@ -111,28 +230,38 @@ extern "C" int32_t mafb200_stem_conv3x3s2(const void* x_nchw, int32_t x_dtype, i
   if (!aligned_f16_view(dst)) return fail(MAF_E_ALIGN, "stem_conv: dst alignment");
   if (n <= 0 || h <= 0 || w <= 0 || (h & 1) || (w & 1)) return fail(MAF_E_ARG, "stem_conv: need even h,w (got %dx%d)", h, w);
   if (dst->n != n || dst->h != h / 2 || dst->w != w / 2) return fail(MAF_E_ARG, "stem_conv: dst must be [n,h/2,w/2,c]");
-  if (dst->c > 256) return fail(MAF_E_ARG, "stem_conv: cout %d > 256", dst->c);
+  if (dst->c > 64) return fail(MAF_E_ARG, "stem_conv: cout %d > 64 (MAF-YOLO N/S/M use 24/32/48)", dst->c);
   if (act < MAF_ACT_NONE || act > MAF_ACT_SIGMOID) return fail(MAF_E_ARG, "stem_conv: bad act");
+  {
+    const uintptr_t need = x_dtype == MAF_F32 ? 7 : (x_dtype == MAF_F16 ? 3 : 1);  // pixel pairs are loaded as one vector
+    if (reinterpret_cast<uintptr_t>(x_nchw) & need) return fail(MAF_E_ALIGN, "stem_conv: input pointer must be aligned to two pixels");
+  }
   int32_t rc = require_sm100();
   if (rc) return rc;
-  const int cpad = round_up(dst->c, 8);
-  const size_t smem = static_cast<size_t>(28) * cpad * sizeof(float);
+  const int tile_n = round_up(dst->c, 16);
+  int tmem_cols = 32;
+  while (tmem_cols < tile_n) tmem_cols <<= 1;
+  const uint32_t idesc = umma_idesc_f16(128, tile_n);
   const long long total = static_cast<long long>(n) * (h / 2) * (w / 2);
-  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  const long long tiles = (total + 127) / 128;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const unsigned blocks = static_cast<unsigned>(tiles < 8ll * sms ? tiles : 8ll * sms);  // persistent, 8 CTAs / SM
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   __half* out = static_cast<__half*>(dst->ptr);
   switch (x_dtype) {
     case MAF_F32:
-      stem_conv_kernel<float><<<blocks, 256, smem, st>>>(static_cast<const float*>(x_nchw), weight, bias, out, n, h, w,
-                                                         dst->c, dst->c_stride, act);
+      stem_conv_kernel<float><<<blocks, 128, 0, st>>>(static_cast<const float*>(x_nchw), weight, bias, out, n, h, w,
+                                                      dst->c, tile_n, tmem_cols, idesc, dst->c_stride, act);
       break;
     case MAF_F16:
-      stem_conv_kernel<__half><<<blocks, 256, smem, st>>>(static_cast<const __half*>(x_nchw), weight, bias, out, n, h,
-                                                          w, dst->c, dst->c_stride, act);
+      stem_conv_kernel<__half><<<blocks, 128, 0, st>>>(static_cast<const __half*>(x_nchw), weight, bias, out, n, h, w,
+                                                       dst->c, tile_n, tmem_cols, idesc, dst->c_stride, act);
       break;
     case MAF_U8:
-      stem_conv_kernel<uint8_t><<<blocks, 256, smem, st>>>(static_cast<const uint8_t*>(x_nchw), weight, bias, out, n,
-                                                           h, w, dst->c, dst->c_stride, act);
+      stem_conv_kernel<uint8_t><<<blocks, 128, 0, st>>>(static_cast<const uint8_t*>(x_nchw), weight, bias, out, n, h,
+                                                        w, dst->c, tile_n, tmem_cols, idesc, dst->c_stride, act);
       break;
     default:
       return fail(MAF_E_ARG, "stem_conv: unsupported input dtype %d", x_dtype);
