@@ -131,9 +131,11 @@ MAFB200_API int32_t mafb200_nhwc_f16_to_nchw(const maf_tensor* src, void* dst, i
  * For each of `n_levels` pyramid levels: cls_logits[l] [n,h_l,w_l,nc] (raw cls_pred output, the
  * sigmoid of common.py:1332 is applied here) and reg[l] [n,h_l,w_l,4*(reg_max+1)] (raw reg_pred
  * output, side-major: ch = side*(reg_max+1)+bin, yolo.py:377).  Writes pred fp32
- * [n, sum(h_l*w_l), 5+nc] = (cx, cy, w, h in input pixels, 1.0, class probabilities). */
+ * [n, sum(h_l*w_l), 5+nc] = (cx, cy, w, h in input pixels, 1.0, class probabilities).
+ * cls_is_prob != 0: `cls_logits` already holds sigmoid outputs (what the reference's Head_DepthUni
+ * returns, common.py:1332) and is copied through — used by the per-block Detect_yaml drop-in. */
 MAFB200_API int32_t mafb200_head_decode(const maf_tensor* cls_logits, const maf_tensor* reg, const float* strides,
-                            int32_t n_levels, int32_t reg_max, float* pred, void* stream);
+                            int32_t n_levels, int32_t reg_max, int32_t cls_is_prob, float* pred, void* stream);
 
 /* ---- batched NMS ------------------------------------------------------------------------------
  * Same result as yolov6/utils/nms.py:31-105 on the same `pred` ([B, A, 5+nc] fp32), without its

@@ -59,7 +59,7 @@ _SIGNATURES = {
     "mafb200_upsample2x": (C.c_int32, [_P(MafTensor), _P(MafTensor), C.c_void_p]),
     "mafb200_nchw_to_nhwc_f16": (C.c_int32, [C.c_void_p, C.c_int32, _P(MafTensor), C.c_void_p]),
     "mafb200_nhwc_f16_to_nchw": (C.c_int32, [_P(MafTensor), C.c_void_p, C.c_int32, C.c_void_p]),
-    "mafb200_head_decode": (C.c_int32, [_P(MafTensor), _P(MafTensor), _P(C.c_float), C.c_int32, C.c_int32,
+    "mafb200_head_decode": (C.c_int32, [_P(MafTensor), _P(MafTensor), _P(C.c_float), C.c_int32, C.c_int32, C.c_int32,
                                         C.c_void_p, C.c_void_p]),
     "mafb200_nms_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "mafb200_nms": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32,

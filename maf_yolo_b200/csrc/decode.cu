@@ -30,7 +30,7 @@ struct DecodeParams {
   int32_t anchor_off[kMaxLevels];  // first anchor index of the level in the concatenated list
   int32_t cta_off[kMaxLevels + 1]; // first CTA (per image) of the level
   float stride[kMaxLevels];
-  int32_t n_levels, nc, bins, total_anchors;
+  int32_t n_levels, nc, bins, total_anchors, cls_is_prob;
   float* pred;
 };
 
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256) head_decode_kernel(const __grid_constant_
         v = 1.0f;
       } else {
         const float z = __half2float(__ldg(cls + (j - 5)));
-        v = __fdividef(1.0f, 1.0f + __expf(-z));
+        v = p.cls_is_prob ? z : __fdividef(1.0f, 1.0f + __expf(-z));
       }
       dst[j] = v;
     }
@@ -131,7 +131,8 @@ __global__ void __launch_bounds__(256) head_decode_kernel(const __grid_constant_
 using namespace mafb200;
 
 extern "C" int32_t mafb200_head_decode(const maf_tensor* cls_logits, const maf_tensor* reg, const float* strides,
-                                       int32_t n_levels, int32_t reg_max, float* pred, void* stream) {
+                                       int32_t n_levels, int32_t reg_max, int32_t cls_is_prob, float* pred,
+                                       void* stream) {
   if (!cls_logits || !reg || !strides || !pred) return fail(MAF_E_ARG, "head_decode: null pointer");
   if (n_levels < 1 || n_levels > kMaxLevels) return fail(MAF_E_ARG, "head_decode: n_levels=%d (1..%d)", n_levels, kMaxLevels);
   if (reg_max < 1 || reg_max > 63) return fail(MAF_E_ARG, "head_decode: reg_max=%d (1..63)", reg_max);
@@ -162,6 +163,7 @@ extern "C" int32_t mafb200_head_decode(const maf_tensor* cls_logits, const maf_t
   p.nc = nc;
   p.bins = reg_max + 1;
   p.total_anchors = anchors;
+  p.cls_is_prob = cls_is_prob != 0;
   p.pred = pred;
   if (n > 65535) return fail(MAF_E_ARG, "head_decode: batch %d > 65535", n);
   int32_t rc = require_sm100();

@@ -72,13 +72,19 @@ class _Op:
 class Plan:
     """Kernel-launch schedule + buffer liveness for one (graph, H, W); batch-size independent."""
 
-    def __init__(self, graph: Graph, height: int, width: int):
-        assert height % 32 == 0 and width % 32 == 0, "input size must be a multiple of the largest stride (32)"
+    def __init__(self, graph: Graph, height: int, width: int, only_layer: Optional[int] = None,
+                 head_sigmoid: bool = False):
+        """only_layer: plan a single yaml layer (block-level drop-in); its sources become input buffers
+        (`self.inputs`), (height, width) is then the spatial size of those sources."""
+        if only_layer is None:
+            assert height % 32 == 0 and width % 32 == 0, "input size must be a multiple of the largest stride (32)"
         self.graph, self.height, self.width = graph, height, width
+        self.only_layer, self.head_sigmoid = only_layer, head_sigmoid
         self.bufs: List[_Buf] = []
         self.ops: List[_Op] = []
         self.level_views: List[Tuple[_View, _View, _View]] = []  # (stem, cls_logits, reg) per head
         self.layer_out: Dict[int, object] = {}  # yaml layer index -> output view(s)
+        self.inputs: List[_View] = []
         self.anchors = 0
         self._plan()
 
@@ -111,8 +117,21 @@ class Plan:
         H, W = self.height, self.width
         up_of: Dict[int, int] = {l.frm[0]: l.i for l in g.layers if l.kind == "upsample"}
         out: Dict[int, object] = {}  # layer index -> _View | list[_View] | tuple (head)
+        layers = g.layers
+        if self.only_layer is not None:
+            lay = g.layers[self.only_layer]
+            layers = [lay]
+            up_of = {}
+            for s_idx, c in zip(lay.frm, lay.c_in):
+                if s_idx >= 0:
+                    v = self._buf(H, W, c, f"in{s_idx}")
+                    out[s_idx] = v
+                    self.inputs.append(v)
 
         def size(l: Layer):
+            if self.only_layer is not None:  # (H, W) is the block's input size
+                down = 2 if l.kind in ("repvgg", "convw", "mprep") else 1
+                return H // down, W // down
             return H // l.stride_total, W // l.stride_total
 
         def srcs_of(l: Layer) -> List[_View]:
@@ -122,7 +141,7 @@ class Plan:
                 res.extend(v if isinstance(v, list) else [v])
             return res
 
-        for l in g.layers:
+        for l in layers:
             i = str(l.i)
             if l.kind == "repvgg":
                 h, w = size(l)
@@ -205,7 +224,8 @@ class Plan:
                     f2 = self._buf(h, w, c, f"L{i}.{br}_s")
                     self._emit("conv1x1", f"L{i}.{br}_s", [t], [f2], weight=f"{i}.{br}_s", act="silu")
                     o = self._buf(h, w, cout, f"L{i}.{br}_pred")
-                    self._emit("conv1x1", f"L{i}.{br}_pred", [f2], [o], weight=f"{i}.{br}_pred", act="none")
+                    self._emit("conv1x1", f"L{i}.{br}_pred", [f2], [o], weight=f"{i}.{br}_pred",
+                               act="sigmoid" if (br == "cls" and self.head_sigmoid) else "none")
                     res[br] = o
                 out[l.i] = (stem, res["cls"], res["reg"])
                 self.level_views.append(out[l.i])

@@ -171,13 +171,13 @@ def nhwc_to_nchw(src: NHWC, out: torch.Tensor) -> None:
 
 
 def head_decode(cls_logits: Sequence[NHWC], reg: Sequence[NHWC], strides: Sequence[float], reg_max: int,
-                pred: torch.Tensor) -> None:
+                pred: torch.Tensor, cls_is_prob: bool = False) -> None:
     nl = len(cls_logits)
     assert pred.dtype == torch.float32 and pred.is_contiguous() and pred.is_cuda
     ca = (MafTensor * nl)(*[t.maf() for t in cls_logits])
     ra = (MafTensor * nl)(*[t.maf() for t in reg])
     st = (C.c_float * nl)(*[float(s) for s in strides])
-    check(lib().mafb200_head_decode(ca, ra, st, nl, reg_max, pred.data_ptr(), _stream()))
+    check(lib().mafb200_head_decode(ca, ra, st, nl, reg_max, int(cls_is_prob), pred.data_ptr(), _stream()))
 
 
 def nms_workspace_bytes(batch: int, anchors: int, nc: int) -> int:

@@ -174,3 +174,22 @@ def test_yaml_loader_accepts_reference_schema(tmp_path):
         bad = topology.variant_rows("n")
         bad["backbone"][2] = [-1, 1, "BotNet", [48]]
         topology.resolve(bad)
+
+
+@pytest.mark.skipif(not __import__("oracle.ref_loader", fromlist=["x"]).available(), reason="reference tree not present")
+def test_convert_blocks_surgery_on_reference_model():
+    """convert_blocks() on a live reference Model: supported blocks are replaced in place, executor
+    attributes (.i/.f) survive, Concat/Upsample/Out stay (no GPU needed until forward)."""
+    import maf_yolo_b200 as mb
+    from oracle import ref_loader
+
+    m = ref_loader.build_model("n")
+    before = [(mod.i, mod.f) for mod in m.backbone]
+    mb.convert_blocks(m)
+    kinds = [type(mod).__name__ for mod in m.backbone]
+    assert kinds.count("B200Block") == 26 and kinds[11] == "Concat" and kinds[13] == "Upsample" and kinds[34] == "Out"
+    assert [(mod.i, mod.f) for mod in m.backbone] == before
+    assert type(m.detect).__name__ == "B200Detect" and m.detect.nc == 80
+    m.float()  # reference Model._apply touches detect.stride / detect.grid (yolo.py:211-215)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 3, 64, 64))
