@@ -59,8 +59,16 @@ struct GemmParams {
   int32_t tmem_cols;   // total TMEM columns allocated: two accumulator buffers
   int32_t n_tiles;
   int32_t m_stride;    // row-tile step of a CTA = gridDim.x / n_tiles
+  int32_t st256;       // 1: every 16-column group of every output row starts 32-B aligned -> 256-bit stores
   uint32_t idesc;
 };
+
+// 256-bit global store (SASS STG.E.ENL2.256): one full 32-byte sector per instruction
+__device__ __forceinline__ void st_global_256(void* ptr, const uint32_t* v) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
 
 template <bool kIm2col>
 __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
@@ -237,31 +245,37 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
             const float b = apply_act_fast(__uint_as_float(r[2 * j + 1]) + s_bias[c + 2 * j + 1], act);
             pk[j] = pack_half2(a, b);
           }
+          if (p.st256 && urow == nullptr && n + valid <= p.N) {
+            // full 32-byte sectors: 2 (or 1) x 256-bit stores for this thread's 64 (32) contiguous bytes
+            st_global_256(orow + n, pk);
+            if (valid > 16) st_global_256(orow + n + 16, pk + 8);
+          } else {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int ng = n + 8 * g;
-            if (8 * g >= valid) break;
-            if (ng + 8 <= p.N) {
-              const uint4 q = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-              *reinterpret_cast<uint4*>(orow + ng) = q;
-              if (urow != nullptr) {
-                *reinterpret_cast<uint4*>(urow + ng) = q;
-                *reinterpret_cast<uint4*>(urow + up_dx + ng) = q;
-                *reinterpret_cast<uint4*>(urow + up_dy + ng) = q;
-                *reinterpret_cast<uint4*>(urow + up_dy + up_dx + ng) = q;
-              }
-            } else {
+            for (int g = 0; g < 4; ++g) {
+              const int ng = n + 8 * g;
+              if (8 * g >= valid) break;
+              if (ng + 8 <= p.N) {
+                const uint4 q = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+                *reinterpret_cast<uint4*>(orow + ng) = q;
+                if (urow != nullptr) {
+                  *reinterpret_cast<uint4*>(urow + ng) = q;
+                  *reinterpret_cast<uint4*>(urow + up_dx + ng) = q;
+                  *reinterpret_cast<uint4*>(urow + up_dy + ng) = q;
+                  *reinterpret_cast<uint4*>(urow + up_dy + up_dx + ng) = q;
+                }
+              } else {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                if (ng + j < p.N) {
-                  const uint32_t w2 = pk[4 * g + (j >> 1)];
-                  const __half hv = __ushort_as_half(static_cast<unsigned short>((j & 1) ? (w2 >> 16) : (w2 & 0xffffu)));
-                  orow[ng + j] = hv;
-                  if (urow != nullptr) {
-                    urow[ng + j] = hv;
-                    urow[up_dx + ng + j] = hv;
-                    urow[up_dy + ng + j] = hv;
-                    urow[up_dy + up_dx + ng + j] = hv;
+                for (int j = 0; j < 8; ++j) {
+                  if (ng + j < p.N) {
+                    const uint32_t w2 = pk[4 * g + (j >> 1)];
+                    const __half hv = __ushort_as_half(static_cast<unsigned short>((j & 1) ? (w2 >> 16) : (w2 & 0xffffu)));
+                    orow[ng + j] = hv;
+                    if (urow != nullptr) {
+                      urow[ng + j] = hv;
+                      urow[up_dx + ng + j] = hv;
+                      urow[up_dy + ng + j] = hv;
+                      urow[up_dy + up_dx + ng + j] = hv;
+                    }
                   }
                 }
               }
@@ -383,6 +397,7 @@ static int32_t launch_gemm(GemmParams& p, int n_tiles, int total_kb, cudaStream_
   p.m_stride = per_n;
   p.tmem_cols = 2 * pow2_cols(p.tile_n);
   p.idesc = umma_idesc_f16(kBlockM, p.tile_n);
+  p.st256 = ((reinterpret_cast<uintptr_t>(p.out) & 31) == 0 && (p.out_ld % 16) == 0 && (p.tile_n % 16) == 0) ? 1 : 0;
   const size_t smem = static_cast<size_t>(p.w_resident ? panel : 0) + static_cast<size_t>(stages) * slot_bytes +
                       (2 * stages + 5) * 8 + 16 + static_cast<size_t>(p.tile_n) * 4 + 1024;
   static bool configured[2] = {false, false};
