@@ -89,6 +89,15 @@ __global__ void __launch_bounds__(128)
   const bool ch_ok = c0 + 2 * pair < C;
   const float2 bv = *reinterpret_cast<const float2*>(s_b + 2 * pair);
   const float* wbase = s_w + 2 * pair;
+  // k <= 5: the thread's k*k weights (2 channels) live in registers for the whole tile, which removes the
+  // weight LDS.64 traffic that co-limits the inner loop with the FFMA pipe (for k = 5 it equals the FFMA
+  // issue time).  k = 7 / 9 would need 98 / 162 registers and keep reading weights from shared memory.
+  constexpr bool kRegW = K <= 5;
+  float2 wreg[kRegW ? K * K : 1];
+  if (kRegW) {
+#pragma unroll
+    for (int t = 0; t < K * K; ++t) wreg[t] = *reinterpret_cast<const float2*>(wbase + t * CB);
+  }
 
 #pragma unroll 1
   for (int u = warp; u < UNITS; u += 4) {
@@ -115,7 +124,8 @@ __global__ void __launch_bounds__(128)
         if (ky < 0 || ky >= K) continue;
         float2 wv[K];
 #pragma unroll
-        for (int kx = 0; kx < K; ++kx) wv[kx] = *reinterpret_cast<const float2*>(wbase + (ky * K + kx) * CB);
+        for (int kx = 0; kx < K; ++kx)
+          wv[kx] = kRegW ? wreg[ky * K + kx] : *reinterpret_cast<const float2*>(wbase + (ky * K + kx) * CB);
 #pragma unroll
         for (int r = 0; r < kDwR; ++r) {
 #pragma unroll

@@ -245,10 +245,22 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
             const float b = apply_act_fast(__uint_as_float(r[2 * j + 1]) + s_bias[c + 2 * j + 1], act);
             pk[j] = pack_half2(a, b);
           }
-          if (p.st256 && urow == nullptr && n + valid <= p.N) {
+          if (p.st256 && n + valid <= p.N) {
             // full 32-byte sectors: 2 (or 1) x 256-bit stores for this thread's 64 (32) contiguous bytes
             st_global_256(orow + n, pk);
             if (valid > 16) st_global_256(orow + n + 16, pk + 8);
+            if (urow != nullptr) {  // x2 nearest-upsampled copy: the same sectors to the four target pixels
+              st_global_256(urow + n, pk);
+              st_global_256(urow + up_dx + n, pk);
+              st_global_256(urow + up_dy + n, pk);
+              st_global_256(urow + up_dy + up_dx + n, pk);
+              if (valid > 16) {
+                st_global_256(urow + n + 16, pk + 8);
+                st_global_256(urow + up_dx + n + 16, pk + 8);
+                st_global_256(urow + up_dy + n + 16, pk + 8);
+                st_global_256(urow + up_dy + up_dx + n + 16, pk + 8);
+              }
+            }
           } else {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -397,7 +409,10 @@ static int32_t launch_gemm(GemmParams& p, int n_tiles, int total_kb, cudaStream_
   p.m_stride = per_n;
   p.tmem_cols = 2 * pow2_cols(p.tile_n);
   p.idesc = umma_idesc_f16(kBlockM, p.tile_n);
-  p.st256 = ((reinterpret_cast<uintptr_t>(p.out) & 31) == 0 && (p.out_ld % 16) == 0 && (p.tile_n % 16) == 0) ? 1 : 0;
+  p.st256 = ((reinterpret_cast<uintptr_t>(p.out) & 31) == 0 && (p.out_ld % 16) == 0 && (p.tile_n % 16) == 0 &&
+             (p.out2 == nullptr || ((reinterpret_cast<uintptr_t>(p.out2) & 31) == 0 && (p.out2_ld % 16) == 0)))
+                 ? 1
+                 : 0;
   const size_t smem = static_cast<size_t>(p.w_resident ? panel : 0) + static_cast<size_t>(stages) * slot_bytes +
                       (2 * stages + 5) * 8 + 16 + static_cast<size_t>(p.tile_n) * 4 + 1024;
   static bool configured[2] = {false, false};

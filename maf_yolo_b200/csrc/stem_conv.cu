@@ -71,7 +71,7 @@ template <typename T>
 __global__ void __launch_bounds__(128) stem_conv_kernel(const T* __restrict__ x, const float* __restrict__ wgt,
                                                          const float* __restrict__ bias, __half* __restrict__ out,
                                                          int n, int h, int w, int cout, int tile_n, int tmem_cols,
-                                                         uint32_t idesc, int out_ld, int act) {
+                                                         uint32_t idesc, int out_ld, int act, int st256) {
   __shared__ __align__(128) uint8_t s_a[128 * kStemK * 2];   // 8 KB: A operand, 128 pixels x 32 k
   __shared__ __align__(128) uint8_t s_b[64 * kStemK * 2];    // 4 KB: B operand, <= 64 output channels x 32 k
   __shared__ float s_bias[64];
@@ -190,16 +190,23 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const T* __restrict__ x,
       for (int j = 0; j < 8; ++j)
         pk[j] = pack_half2(apply_act_fast(__uint_as_float(r[2 * j]) + s_bias[c + 2 * j], act),
                            apply_act_fast(__uint_as_float(r[2 * j + 1]) + s_bias[c + 2 * j + 1], act));
+      if (st256 && c + 16 <= cout) {
+        // 16 valid channels starting on a 32-byte boundary: one whole-sector 256-bit store
+        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(orow + c), "r"(pk[0]), "r"(pk[1]),
+                     "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
+                     : "memory");
+      } else {
 #pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        const int c8 = c + 8 * g;
-        if (c8 + 8 <= cout) {
-          *reinterpret_cast<uint4*>(orow + c8) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-        } else {
-          for (int j = 0; j < 8; ++j) {
-            if (c8 + j < cout) {
-              const uint32_t w2 = pk[4 * g + (j >> 1)];
-              orow[c8 + j] = __ushort_as_half(static_cast<unsigned short>((j & 1) ? (w2 >> 16) : (w2 & 0xffffu)));
+        for (int g = 0; g < 2; ++g) {
+          const int c8 = c + 8 * g;
+          if (c8 + 8 <= cout) {
+            *reinterpret_cast<uint4*>(orow + c8) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+          } else {
+            for (int j = 0; j < 8; ++j) {
+              if (c8 + j < cout) {
+                const uint32_t w2 = pk[4 * g + (j >> 1)];
+                orow[c8 + j] = __ushort_as_half(static_cast<unsigned short>((j & 1) ? (w2 >> 16) : (w2 & 0xffffu)));
+              }
             }
           }
         }
@@ -250,18 +257,20 @@ extern "C" int32_t mafb200_stem_conv3x3s2(const void* x_nchw, int32_t x_dtype, i
   const unsigned blocks = static_cast<unsigned>(tiles < 8ll * sms ? tiles : 8ll * sms);  // persistent, 8 CTAs / SM
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   __half* out = static_cast<__half*>(dst->ptr);
+  // 256-bit stores for every full 16-channel group when pixel rows start on 32-byte boundaries
+  const int st256 = ((dst->c_stride % 16) == 0 && (reinterpret_cast<uintptr_t>(dst->ptr) & 31) == 0) ? 1 : 0;
   switch (x_dtype) {
     case MAF_F32:
       stem_conv_kernel<float><<<blocks, 128, 0, st>>>(static_cast<const float*>(x_nchw), weight, bias, out, n, h, w,
-                                                      dst->c, tile_n, tmem_cols, idesc, dst->c_stride, act);
+                                                      dst->c, tile_n, tmem_cols, idesc, dst->c_stride, act, st256);
       break;
     case MAF_F16:
       stem_conv_kernel<__half><<<blocks, 128, 0, st>>>(static_cast<const __half*>(x_nchw), weight, bias, out, n, h, w,
-                                                       dst->c, tile_n, tmem_cols, idesc, dst->c_stride, act);
+                                                       dst->c, tile_n, tmem_cols, idesc, dst->c_stride, act, st256);
       break;
     case MAF_U8:
       stem_conv_kernel<uint8_t><<<blocks, 128, 0, st>>>(static_cast<const uint8_t*>(x_nchw), weight, bias, out, n, h,
-                                                        w, dst->c, tile_n, tmem_cols, idesc, dst->c_stride, act);
+                                                        w, dst->c, tile_n, tmem_cols, idesc, dst->c_stride, act, st256);
       break;
     default:
       return fail(MAF_E_ARG, "stem_conv: unsupported input dtype %d", x_dtype);
