@@ -39,7 +39,6 @@ constexpr int kBlockK = 64;
 constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB
 constexpr int kEpiWarps = 8;
 constexpr int kGemmThreads = 32 * (2 + kEpiWarps);  // TMA warp + MMA warp + epilogue warps
-constexpr int kMaxResidentW = 48 * 1024;
 
 struct GemmParams {
   CUtensorMap tmA[MAF_MAX_SRC];
@@ -381,27 +380,31 @@ template <bool kIm2col>
 static int32_t launch_gemm(GemmParams& p, int n_tiles, int total_kb, cudaStream_t stream) {
   const int b_bytes = p.tile_n * kBlockK * 2;
   const int m_tiles = ceil_div(p.M, kBlockM);
-  // persistent grid: 2 CTAs per SM, a multiple of n_tiles (each CTA owns one column tile)
-  int per_n = (2 * sm_count()) / n_tiles;
-  if (per_n < 1) per_n = 1;
-  if (per_n > m_tiles) per_n = m_tiles;
-  const int grid = per_n * n_tiles;
-  const int budget = 104 * 1024;  // ring + resident panel, so that 2 CTAs share one SM
+  // Two shapes of persistent CTA (2 per SM): weight panel resident + A-only ring when it fits, else A and W
+  // k-blocks stream together.  (A 1-CTA/SM ~216 KB shape for the 54-72 KB panels of the small-Cin 3x3
+  // layers was measured slower: those layers are bound by the im2col TMA's per-pixel-row request rate —
+  // ~0.35 us per 128-row im2col box regardless of Cin — not by weight re-streaming or ring depth.)
   const int panel = total_kb * b_bytes;
+  const int ctas_per_sm = 2;
+  const int budget = 104 * 1024;
   int stages;
-  if (panel <= kMaxResidentW && panel + 2 * kABytes <= budget) {
-    p.w_resident = 1;
+  p.w_resident = (panel + 3 * kABytes <= budget) ? 1 : 0;
+  if (p.w_resident) {
     stages = (budget - panel) / kABytes;
     const int want = total_kb * 4 > 3 ? total_kb * 4 : 3;  // ~4 row tiles in flight
     if (stages > want) stages = want;
-    if (stages > 8) stages = 8;
+    if (stages > 12) stages = 12;
   } else {
-    p.w_resident = 0;
     stages = budget / (kABytes + b_bytes);
     if (stages > 2 * total_kb) stages = 2 * total_kb;
     if (stages > 6) stages = 6;
   }
   if (stages < 1) stages = 1;
+  // persistent grid: a multiple of n_tiles (each CTA owns one column tile)
+  int per_n = (ctas_per_sm * sm_count()) / n_tiles;
+  if (per_n < 1) per_n = 1;
+  if (per_n > m_tiles) per_n = m_tiles;
+  const int grid = per_n * n_tiles;
   const int slot_bytes = p.w_resident ? kABytes : kABytes + b_bytes;
   p.stages = stages;
   p.total_kb = total_kb;
@@ -418,11 +421,11 @@ static int32_t launch_gemm(GemmParams& p, int n_tiles, int total_kb, cudaStream_
   static bool configured[2] = {false, false};
   if (!configured[kIm2col]) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<kIm2col>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         200 * 1024);
+                                         227 * 1024);
     if (e != cudaSuccess) return fail(MAF_E_CUDA, "cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e));
     configured[kIm2col] = true;
   }
-  if (smem > 200 * 1024) return fail(MAF_E_ARG, "gemm: %zu B of shared memory needed", smem);
+  if (smem > 227 * 1024) return fail(MAF_E_ARG, "gemm: %zu B of shared memory needed", smem);
   gemm_tc_kernel<kIm2col><<<grid, kGemmThreads, smem, stream>>>(p);
   return check_launch(kIm2col ? "conv3x3s2 kernel launch" : "conv1x1 kernel launch");
 }
