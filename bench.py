@@ -159,6 +159,23 @@ def measured_hbm_peak():
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
+def profiled_traffic(kind: str, variant: str, batch: int):
+    """DRAM bytes per launch of a kernel family from the committed ncu capture (tools/traffic_table.py):
+    dram__bytes_read.sum + dram__bytes_write.sum, averaged over the family's launches of one forward."""
+    pdir = os.path.join(ROOT, "profiles")
+    if not os.path.isdir(pdir):
+        return None
+    for name in sorted(os.listdir(pdir), reverse=True):
+        if name.endswith("_traffic.json"):
+            try:
+                d = json.load(open(os.path.join(pdir, name)))
+                if d.get("variant") == variant and d.get("batch") == batch and kind in d["families"]:
+                    return int(d["families"][kind]["traffic_bytes_per_launch"])
+            except Exception:
+                continue
+    return None
+
+
 def kernel_profile(engine, x, reps: int = 5):
     """Eager pass with a CUDA-event pair around every launch: per-kernel-family time and algorithmic bytes."""
     engine.run_eager(x)
@@ -309,7 +326,7 @@ def run_ours(a):
                     "maxpool2x2": "maxpool2x2_kernel", "sppf_pool": "sppf_pool_kernel", "decode": "head_decode_kernel"}
     roofline = {
         "bound": "hbm", "kernel": kernel_names.get(top, top), "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-        "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+        "frac": round(achieved / peak, 4), "traffic": profiled_traffic(top, a.variant, B), "peak_source": peak_src,
         "bytes_per_launch": int(ft["bytes"] / ft["launches"]), "avg_launch_us": round(1e3 * ft["ms"] / ft["launches"], 2),
         "share_of_forward": round(ft["ms"] / tot_ms, 3),
         "families": {k: {"share": round(v["ms"] / tot_ms, 3), "GB/s": round(v["bytes"] / 1e9 / (v["ms"] / 1e3), 1),

@@ -26,7 +26,14 @@
 //                     (A shared-memory staged TMA tensor store was measured SLOWER: one-row-per-thread
 //                     writes into a dense row-major staging tile are 8-32-way bank conflicted.)
 // K is tiny here (1-12 blocks of 64) and N <= 128 per tile: the kernel is HBM/epilogue-bound, not
-// tensor-bound, so the design keeps loads deep in flight and the store path off the LSU.
+// tensor-bound, so the design keeps loads deep in flight and writes whole 32-byte sectors.
+//
+// Measured and rejected for the 3x3 producer (profiles/r01_notes.md): (1) a software im2col by four LSU
+// gather warps (8 lanes x 16 B per pixel row, SW128 layout written by hand): 2.6x slower than the im2col
+// TMA (1132 vs 432 us per forward) because each slot is a dependent load -> st.shared -> fence round trip;
+// (2) a 1-CTA/SM 216 KB shape keeping the 54-72 KB weight panels of the small-Cin layers resident: slower.
+// The im2col TMA itself costs ~0.35-0.55 us per 128-pixel box almost independently of the channel count
+// (one L2 request per pixel row), which is what bounds the 3x3 layers today.
 #include <string.h>
 
 #include "common.cuh"
@@ -69,6 +76,153 @@ __device__ __forceinline__ void st_global_256(void* ptr, const uint32_t* v) {
                : "memory");
 }
 
+struct GemmSmem {
+  uint8_t* wpanel;
+  uint8_t* ring;
+  uint64_t *full_bar, *empty_bar, *tmem_full_bar, *tmem_empty_bar, *w_bar;
+  float* bias;
+  int slot_bytes, b_bytes;
+  bool w_res;
+};
+
+// ---- MMA issuer (one elected lane) -------------------------------------------------------------
+__device__ __forceinline__ void gemm_mma_loop(const GemmParams& p, const GemmSmem& sm, uint32_t tmem_base,
+                                              uint32_t acc_cols, int mt0, int mt_step, int m_tiles) {
+  const int total_kb = p.total_kb, stages = p.stages;
+  if (sm.w_res) {
+    mbar_wait(sm.w_bar, 0);
+    tc_fence_after_sync();
+  }
+  int kb = 0;
+  int it = 0;
+  for (int mt = mt0; mt < m_tiles; mt += mt_step, ++it) {
+    const int as = it & 1;
+    mbar_wait(&sm.tmem_empty_bar[as], ((it >> 1) & 1) ^ 1);  // epilogue drained this accumulator
+    tc_fence_after_sync();
+    const uint32_t tmem_d = tmem_base + as * acc_cols;
+    for (int k2 = 0; k2 < total_kb; ++k2, ++kb) {
+      const int slot = kb % stages;
+      const uint32_t phase = (kb / stages) & 1;
+      mbar_wait(&sm.full_bar[slot], phase);
+      tc_fence_after_sync();
+      const uint32_t sa = smem_u32(sm.ring + slot * sm.slot_bytes);
+      const uint32_t sb = sm.w_res ? smem_u32(sm.wpanel + k2 * sm.b_bytes) : sa + kABytes;
+      const uint64_t da = umma_smem_desc_sw128(sa);
+      const uint64_t db = umma_smem_desc_sw128(sb);
+#pragma unroll
+      for (int k = 0; k < kBlockK / 16; ++k) {
+        // advance 16 fp16 = 32 B inside the 128-B swizzle row: +2 in the (addr >> 4) field
+        tc_mma_f16(tmem_d, da + 2 * k, db + 2 * k, p.idesc, (k2 | k) != 0 ? 1u : 0u);
+      }
+      tc_commit(&sm.empty_bar[slot]);
+    }
+    tc_commit(&sm.tmem_full_bar[as]);
+  }
+}
+
+// ---- epilogue (8 warps; `ew` = 0..7 index of this warp among them) ---------------------------------
+__device__ __forceinline__ void gemm_epilogue_loop(const GemmParams& p, const GemmSmem& sm, uint32_t tmem_base,
+                                                   uint32_t acc_cols, int mt0, int mt_step, int m_tiles, int n0,
+                                                   int warp, int lane, int ew) {
+  const float* s_bias = sm.bias;
+  const int quarter = warp & 3;     // TMEM lanes this warp may access: 32 * (warp id % 4)
+  const int col_group = ew >> 2;    // even / odd 32-column groups
+  const int row = quarter * 32 + lane;
+  const int act = p.act;
+  const size_t up_dx = p.out2_ld;
+  const size_t up_dy = static_cast<size_t>(2) * p.out_w * p.out2_ld;
+  int it = 0;
+  for (int mt = mt0; mt < m_tiles; mt += mt_step, ++it) {
+    const int as = it & 1;
+    const int m = mt * kBlockM + row;
+    const bool row_ok = m < p.M;
+    mbar_wait(&sm.tmem_full_bar[as], (it >> 1) & 1);
+    tc_fence_after_sync();
+    const uint32_t taddr = tmem_base + as * acc_cols + (static_cast<uint32_t>(quarter * 32) << 16);
+    __half* orow = p.out + static_cast<size_t>(row_ok ? m : 0) * p.out_ld;
+    __half* urow = nullptr;
+    if (p.out2 != nullptr && row_ok) {
+      const int hw = p.out_h * p.out_w;
+      const int img = m / hw;
+      const int rem = m - img * hw;
+      const int y = rem / p.out_w;
+      const int x = rem - y * p.out_w;
+      urow = p.out2 + ((static_cast<size_t>(img) * 2 * p.out_h + 2 * y) * (2 * p.out_w) + 2 * x) * p.out2_ld;
+    }
+#pragma unroll 1
+    for (int c = col_group * 32; c < p.tile_n; c += 64) {
+      uint32_t r[32];
+      __syncwarp();  // tcgen05.ld is .sync.aligned: the warp must be converged here
+      tmem_ld_32x32b_x32(taddr + c, r);
+      tmem_ld_wait();
+      const int n = n0 + c;
+      if (row_ok && n < p.N) {
+        // 32 independent bias+activation chains first (MUFU latency overlaps), then pack + store
+        const int valid = min(32, p.tile_n - c);  // 32 or 16 (tile_n % 16 == 0)
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float a = apply_act_fast(__uint_as_float(r[2 * j]) + s_bias[c + 2 * j], act);
+          const float b = apply_act_fast(__uint_as_float(r[2 * j + 1]) + s_bias[c + 2 * j + 1], act);
+          pk[j] = pack_half2(a, b);
+        }
+        if (p.st256 && n + valid <= p.N) {
+          // full 32-byte sectors: 2 (or 1) x 256-bit stores for this thread's 64 (32) contiguous bytes
+          st_global_256(orow + n, pk);
+          if (valid > 16) st_global_256(orow + n + 16, pk + 8);
+          if (urow != nullptr) {  // x2 nearest-upsampled copy: the same sectors to the four target pixels
+            st_global_256(urow + n, pk);
+            st_global_256(urow + up_dx + n, pk);
+            st_global_256(urow + up_dy + n, pk);
+            st_global_256(urow + up_dy + up_dx + n, pk);
+            if (valid > 16) {
+              st_global_256(urow + n + 16, pk + 8);
+              st_global_256(urow + up_dx + n + 16, pk + 8);
+              st_global_256(urow + up_dy + n + 16, pk + 8);
+              st_global_256(urow + up_dy + up_dx + n + 16, pk + 8);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int ng = n + 8 * g;
+            if (8 * g >= valid) break;
+            if (ng + 8 <= p.N) {
+              const uint4 q = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+              *reinterpret_cast<uint4*>(orow + ng) = q;
+              if (urow != nullptr) {
+                *reinterpret_cast<uint4*>(urow + ng) = q;
+                *reinterpret_cast<uint4*>(urow + up_dx + ng) = q;
+                *reinterpret_cast<uint4*>(urow + up_dy + ng) = q;
+                *reinterpret_cast<uint4*>(urow + up_dy + up_dx + ng) = q;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                if (ng + j < p.N) {
+                  const uint32_t w2 = pk[4 * g + (j >> 1)];
+                  const __half hv = __ushort_as_half(static_cast<unsigned short>((j & 1) ? (w2 >> 16) : (w2 & 0xffffu)));
+                  orow[ng + j] = hv;
+                  if (urow != nullptr) {
+                    urow[ng + j] = hv;
+                    urow[up_dx + ng + j] = hv;
+                    urow[up_dy + ng + j] = hv;
+                    urow[up_dy + up_dx + ng + j] = hv;
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+    // all of this warp's TMEM reads of accumulator `as` are complete (wait::ld above): hand it back
+    tc_fence_before_sync();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.tmem_empty_bar[as]);
+  }
+}
+
 template <bool kIm2col>
 __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -93,6 +247,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
   uint64_t* w_bar = tmem_empty_bar + 2;          // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);  // [tile_n]
+  const GemmSmem sm{s_wpanel, s_ring, full_bar, empty_bar, tmem_full_bar, tmem_empty_bar, w_bar, s_bias, slot_bytes, b_bytes, w_res};
 
   const int m_tiles = ceil_div(p.M, kBlockM);
   const int nt = blockIdx.x % p.n_tiles;  // this CTA's column tile
@@ -167,138 +322,9 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
       }
     }
   } else if (warp == 1) {
-    // ---- MMA issuer -----------------------------------------------------------------------------
-    if (lane == 0 && mt0 < m_tiles) {
-      if (w_res) {
-        mbar_wait(w_bar, 0);
-        tc_fence_after_sync();
-      }
-      int kb = 0;
-      int it = 0;
-      for (int mt = mt0; mt < m_tiles; mt += mt_step, ++it) {
-        const int as = it & 1;
-        mbar_wait(&tmem_empty_bar[as], ((it >> 1) & 1) ^ 1);  // epilogue drained this accumulator
-        tc_fence_after_sync();
-        const uint32_t tmem_d = tmem_base + as * acc_cols;
-        for (int k2 = 0; k2 < total_kb; ++k2, ++kb) {
-          const int slot = kb % stages;
-          const uint32_t phase = (kb / stages) & 1;
-          mbar_wait(&full_bar[slot], phase);
-          tc_fence_after_sync();
-          const uint32_t sa = smem_u32(s_ring + slot * slot_bytes);
-          const uint32_t sb = w_res ? smem_u32(s_wpanel + k2 * b_bytes) : sa + kABytes;
-          const uint64_t da = umma_smem_desc_sw128(sa);
-          const uint64_t db = umma_smem_desc_sw128(sb);
-#pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            // advance 16 fp16 = 32 B inside the 128-B swizzle row: +2 in the (addr >> 4) field
-            tc_mma_f16(tmem_d, da + 2 * k, db + 2 * k, p.idesc, (k2 | k) != 0 ? 1u : 0u);
-          }
-          tc_commit(&empty_bar[slot]);
-        }
-        tc_commit(&tmem_full_bar[as]);
-      }
-    }
+    if (lane == 0 && mt0 < m_tiles) gemm_mma_loop(p, sm, tmem_base, acc_cols, mt0, mt_step, m_tiles);
   } else {
-    // ---- epilogue warps ---------------------------------------------------------------------------
-    const int ew = warp - 2;
-    const int quarter = warp & 3;     // TMEM lanes this warp may access: 32 * (warp id % 4)
-    const int col_group = ew >> 2;    // even / odd 32-column groups
-    const int row = quarter * 32 + lane;
-    const int act = p.act;
-    const size_t up_dx = p.out2_ld;
-    const size_t up_dy = static_cast<size_t>(2) * p.out_w * p.out2_ld;
-    int it = 0;
-    for (int mt = mt0; mt < m_tiles; mt += mt_step, ++it) {
-      const int as = it & 1;
-      const int m = mt * kBlockM + row;
-      const bool row_ok = m < p.M;
-      mbar_wait(&tmem_full_bar[as], (it >> 1) & 1);
-      tc_fence_after_sync();
-      const uint32_t taddr = tmem_base + as * acc_cols + (static_cast<uint32_t>(quarter * 32) << 16);
-      __half* orow = p.out + static_cast<size_t>(row_ok ? m : 0) * p.out_ld;
-      __half* urow = nullptr;
-      if (p.out2 != nullptr && row_ok) {
-        const int hw = p.out_h * p.out_w;
-        const int img = m / hw;
-        const int rem = m - img * hw;
-        const int y = rem / p.out_w;
-        const int x = rem - y * p.out_w;
-        urow = p.out2 + ((static_cast<size_t>(img) * 2 * p.out_h + 2 * y) * (2 * p.out_w) + 2 * x) * p.out2_ld;
-      }
-
-#pragma unroll 1
-      for (int c = col_group * 32; c < p.tile_n; c += 64) {
-        uint32_t r[32];
-        __syncwarp();  // tcgen05.ld is .sync.aligned: the warp must be converged here
-        tmem_ld_32x32b_x32(taddr + c, r);
-        tmem_ld_wait();
-        const int n = n0 + c;
-        if (row_ok && n < p.N) {
-          // 32 independent bias+activation chains first (MUFU latency overlaps), then pack + store
-          const int valid = min(32, p.tile_n - c);  // 32 or 16 (tile_n % 16 == 0)
-          uint32_t pk[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float a = apply_act_fast(__uint_as_float(r[2 * j]) + s_bias[c + 2 * j], act);
-            const float b = apply_act_fast(__uint_as_float(r[2 * j + 1]) + s_bias[c + 2 * j + 1], act);
-            pk[j] = pack_half2(a, b);
-          }
-          if (p.st256 && n + valid <= p.N) {
-            // full 32-byte sectors: 2 (or 1) x 256-bit stores for this thread's 64 (32) contiguous bytes
-            st_global_256(orow + n, pk);
-            if (valid > 16) st_global_256(orow + n + 16, pk + 8);
-            if (urow != nullptr) {  // x2 nearest-upsampled copy: the same sectors to the four target pixels
-              st_global_256(urow + n, pk);
-              st_global_256(urow + up_dx + n, pk);
-              st_global_256(urow + up_dy + n, pk);
-              st_global_256(urow + up_dy + up_dx + n, pk);
-              if (valid > 16) {
-                st_global_256(urow + n + 16, pk + 8);
-                st_global_256(urow + up_dx + n + 16, pk + 8);
-                st_global_256(urow + up_dy + n + 16, pk + 8);
-                st_global_256(urow + up_dy + up_dx + n + 16, pk + 8);
-              }
-            }
-          } else {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int ng = n + 8 * g;
-              if (8 * g >= valid) break;
-              if (ng + 8 <= p.N) {
-                const uint4 q = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-                *reinterpret_cast<uint4*>(orow + ng) = q;
-                if (urow != nullptr) {
-                  *reinterpret_cast<uint4*>(urow + ng) = q;
-                  *reinterpret_cast<uint4*>(urow + up_dx + ng) = q;
-                  *reinterpret_cast<uint4*>(urow + up_dy + ng) = q;
-                  *reinterpret_cast<uint4*>(urow + up_dy + up_dx + ng) = q;
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  if (ng + j < p.N) {
-                    const uint32_t w2 = pk[4 * g + (j >> 1)];
-                    const __half hv = __ushort_as_half(static_cast<unsigned short>((j & 1) ? (w2 >> 16) : (w2 & 0xffffu)));
-                    orow[ng + j] = hv;
-                    if (urow != nullptr) {
-                      urow[ng + j] = hv;
-                      urow[up_dx + ng + j] = hv;
-                      urow[up_dy + ng + j] = hv;
-                      urow[up_dy + up_dx + ng + j] = hv;
-                    }
-                  }
-                }
-              }
-            }
-          }
-        }
-      }
-      // all of this warp's TMEM reads of accumulator `as` are complete (wait::ld above): hand it back
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
-    }
+    gemm_epilogue_loop(p, sm, tmem_base, acc_cols, mt0, mt_step, m_tiles, n0, warp, lane, warp - 2);
   }
 
   // ---- teardown -----------------------------------------------------------------------------------
@@ -376,7 +402,9 @@ static int sm_count() {
   return cached;
 }
 
-template <bool kIm2col>
+enum GemmMode { kModeTma2d = 0, kModeIm2colTma = 1 };
+
+template <int kMode>
 static int32_t launch_gemm(GemmParams& p, int n_tiles, int total_kb, cudaStream_t stream) {
   const int b_bytes = p.tile_n * kBlockK * 2;
   const int m_tiles = ceil_div(p.M, kBlockM);
@@ -418,16 +446,16 @@ static int32_t launch_gemm(GemmParams& p, int n_tiles, int total_kb, cudaStream_
                  : 0;
   const size_t smem = static_cast<size_t>(p.w_resident ? panel : 0) + static_cast<size_t>(stages) * slot_bytes +
                       (2 * stages + 5) * 8 + 16 + static_cast<size_t>(p.tile_n) * 4 + 1024;
-  static bool configured[2] = {false, false};
-  if (!configured[kIm2col]) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<kIm2col>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         227 * 1024);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<kMode == kModeIm2colTma>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail(MAF_E_CUDA, "cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e));
-    configured[kIm2col] = true;
+    configured = true;
   }
   if (smem > 227 * 1024) return fail(MAF_E_ARG, "gemm: %zu B of shared memory needed", smem);
-  gemm_tc_kernel<kIm2col><<<grid, kGemmThreads, smem, stream>>>(p);
-  return check_launch(kIm2col ? "conv3x3s2 kernel launch" : "conv1x1 kernel launch");
+  gemm_tc_kernel<kMode == kModeIm2colTma><<<grid, kGemmThreads, smem, stream>>>(p);
+  return check_launch(kMode == kModeTma2d ? "conv1x1 kernel launch" : "conv3x3s2 kernel launch");
 }
 
 }  // namespace mafb200
@@ -488,7 +516,7 @@ extern "C" int32_t mafb200_conv1x1(const maf_tensor* srcs, int32_t n_src, const 
     p.out2 = static_cast<__half*>(dst_up2x->ptr);
     p.out2_ld = dst_up2x->c_stride;
   }
-  return launch_gemm<false>(p, n_tiles, total_kb, static_cast<cudaStream_t>(stream));
+  return launch_gemm<kModeTma2d>(p, n_tiles, total_kb, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int32_t mafb200_conv3x3s2(const maf_tensor* src, const void* w_packed, const float* bias, int32_t act,
@@ -524,5 +552,5 @@ extern "C" int32_t mafb200_conv3x3s2(const maf_tensor* src, const void* w_packed
   p.out_h = dst->h;
   p.out_w = dst->w;
   p.act = act;
-  return launch_gemm<true>(p, n_tiles, 9 * p.kblocks[0], static_cast<cudaStream_t>(stream));
+  return launch_gemm<kModeIm2colTma>(p, n_tiles, 9 * p.kblocks[0], static_cast<cudaStream_t>(stream));
 }

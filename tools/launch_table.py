@@ -31,7 +31,14 @@ def main():
             hdr = r
             continue
         if hdr and len(r) == len(hdr):
-            data.append(dict(zip(hdr, r)))
+            d = dict(zip(hdr, r))
+            if d.get("Metric Name", "gpu__time_duration.sum") != "gpu__time_duration.sum":
+                continue  # multi-metric capture: keep one row per launch
+            if d.get("Metric Unit") == "ns":
+                d["Metric Value"] = str(float(d["Metric Value"].replace(",", "")))
+            elif d.get("Metric Unit") == "us":
+                d["Metric Value"] = str(float(d["Metric Value"].replace(",", "")) * 1e3)
+            data.append(d)
     names = [re.sub(r"\(.*", "", d["Kernel Name"]) for d in data]
     starts = [i for i, n in enumerate(names) if "stem_conv" in n]
     start = starts[min(a.forward, len(starts) - 1)]
