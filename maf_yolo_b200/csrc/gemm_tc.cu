@@ -76,6 +76,33 @@ __device__ __forceinline__ void st_global_256(void* ptr, const uint32_t* v) {
                : "memory");
 }
 
+// bias + activation + fp16 pack of 32 accumulator columns, specialised per activation so the element loop
+// has no per-element dispatch.  SiLU: h = 0.5*(acc + bias) as ONE FFMA against the pre-halved bias, then
+// h + h*tanh(h): 3 instructions (FFMA, MUFU.TANH, FFMA) per element.
+template <int kAct>
+__device__ __forceinline__ void epi_pack32(const uint32_t (&r)[32], const float* __restrict__ bias,
+                                           const float* __restrict__ half_bias, uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float v[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const float acc = __uint_as_float(r[2 * j + e]);
+      if (kAct == ACT_SILU) {
+        const float h = fmaf(acc, 0.5f, half_bias[2 * j + e]);
+        v[e] = fmaf(h, tanh_approx(h), h);
+      } else if (kAct == ACT_RELU) {
+        v[e] = fmaxf(acc + bias[2 * j + e], 0.0f);
+      } else if (kAct == ACT_SIGMOID) {
+        v[e] = __fdividef(1.0f, 1.0f + __expf(-(acc + bias[2 * j + e])));
+      } else {
+        v[e] = acc + bias[2 * j + e];
+      }
+    }
+    pk[j] = pack_half2(v[0], v[1]);
+  }
+}
+
 struct GemmSmem {
   uint8_t* wpanel;
   uint8_t* ring;
@@ -125,6 +152,7 @@ __device__ __forceinline__ void gemm_epilogue_loop(const GemmParams& p, const Ge
                                                    uint32_t acc_cols, int mt0, int mt_step, int m_tiles, int n0,
                                                    int warp, int lane, int ew) {
   const float* s_bias = sm.bias;
+  const float* s_hbias = sm.bias + p.tile_n + 32;  // 0.5 * bias (SiLU path); +32: groups may read past tile_n
   const int quarter = warp & 3;     // TMEM lanes this warp may access: 32 * (warp id % 4)
   const int col_group = ew >> 2;    // even / odd 32-column groups
   const int row = quarter * 32 + lane;
@@ -274,7 +302,11 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
     tmem_alloc(tmem_slot, p.tmem_cols);
     tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < p.tile_n; i += blockDim.x) s_bias[i] = p.bias[n0 + i];
+  for (int i = threadIdx.x; i < p.tile_n + 32; i += blockDim.x) {
+    const float bv = i < p.tile_n ? p.bias[n0 + i] : 0.0f;
+    s_bias[i] = bv;
+    s_bias[p.tile_n + 32 + i] = 0.5f * bv;
+  }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -445,7 +477,7 @@ static int32_t launch_gemm(GemmParams& p, int n_tiles, int total_kb, cudaStream_
                  ? 1
                  : 0;
   const size_t smem = static_cast<size_t>(p.w_resident ? panel : 0) + static_cast<size_t>(stages) * slot_bytes +
-                      (2 * stages + 5) * 8 + 16 + static_cast<size_t>(p.tile_n) * 4 + 1024;
+                      (2 * stages + 5) * 8 + 16 + static_cast<size_t>(p.tile_n + 32) * 8 + 1024;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<kMode == kModeIm2colTma>,
