@@ -235,6 +235,18 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int m, int n) {
   return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
+// Packed 2 x fp32 FMA (SASS FFMA2, new on sm_100): one issue slot for two IEEE fused multiply-adds; bit-
+// identical to two fmaf().  The depth-wise kernel is issue-bound, and its (2 channel) float2 operands map
+// onto it directly.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a);
+  unsigned long long rb = *reinterpret_cast<unsigned long long*>(&b);
+  unsigned long long rc = *reinterpret_cast<unsigned long long*>(&c);
+  unsigned long long rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
+
 // ----------------------------------------------------------------------------------------------
 // Small numeric helpers
 // ----------------------------------------------------------------------------------------------

@@ -13,7 +13,8 @@
 //     a 10 x 20 output tile into shared memory; out-of-bounds zero fill IS the conv padding and the
 //     channel tail, so there is not a single bounds check or address computation per tap;
 //   * weights of the CB channels are staged once per CTA as fp32 [k*k][CB];
-//   * a thread owns 2 channels (half2 -> float2) x 5 x 5 outputs: 50 independent fp32 accumulators,
+//   * a thread owns 2 channels (half2 -> float2) x 5 x 5 outputs: 25 independent float2 accumulators
+//     updated with the packed FFMA2 (fma.rn.f32x2: two IEEE FMAs per issue slot, new on sm_100),
 //     every shared-memory operand address is (thread base + compile-time immediate);
 //   * one tile per CTA with 3-5 CTAs resident per SM measured FASTER than persistent CTAs with a
 //     two-stage TMA ring (857 vs 920 us per forward): the inner loop is co-limited by the FFMA pipe and
@@ -130,8 +131,7 @@ __global__ void __launch_bounds__(128)
         for (int r = 0; r < kDwR; ++r) {
 #pragma unroll
           for (int kx = 0; kx < K; ++kx) {
-            acc[i][r].x = fmaf(win[r + kx].x, wv[kx].x, acc[i][r].x);
-            acc[i][r].y = fmaf(win[r + kx].y, wv[kx].y, acc[i][r].y);
+            acc[i][r] = ffma2(win[r + kx], wv[kx], acc[i][r]);
           }
         }
       }
