@@ -61,9 +61,9 @@ __global__ void __launch_bounds__(128)
 
   extern __shared__ __align__(128) uint8_t smem_dw[];
   __half* s_in = reinterpret_cast<__half*>(smem_dw);                        // [TH][TW][CB]
-  float* s_w = reinterpret_cast<float*>(smem_dw + kTileBytes);              // [K*K][CB]
-  float* s_b = s_w + K * K * CB;                                            // [CB]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(s_b + CB);
+  float* s_w = reinterpret_cast<float*>(smem_dw + kTileBytes);              // [K*K][CB]   (k >= 7 only)
+  float* s_b = s_w + K * K * CB;                                            // [CB]        (k >= 7 only)
+  uint64_t* bar = (K <= 5) ? reinterpret_cast<uint64_t*>(smem_dw + kTileBytes) : reinterpret_cast<uint64_t*>(s_b + CB);
 
   const int tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
   const int c0 = blockIdx.y * CB;
@@ -76,29 +76,34 @@ __global__ void __launch_bounds__(128)
     mbar_arrive_expect_tx(bar, kTileBytes);
     tma_load_tile_4d(s_in, &tm_in, bar, c0, x0 - P, y0 - P, img);
   }
-  for (int i = threadIdx.x; i < K * K * CB; i += blockDim.x) {
-    const int t = i / CB, c = i - t * CB;
-    s_w[i] = (c0 + c < C) ? __ldg(wgt + static_cast<size_t>(t) * C + c0 + c) : 0.0f;
-  }
-  for (int i = threadIdx.x; i < CB; i += blockDim.x) s_b[i] = (c0 + i < C) ? __ldg(bias + c0 + i) : 0.0f;
-  __syncthreads();
-  mbar_wait(bar, 0);
-
+  constexpr bool kRegW = K <= 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pair = lane % PAIRS;
   const int xsel = lane / PAIRS;
   const bool ch_ok = c0 + 2 * pair < C;
-  const float2 bv = *reinterpret_cast<const float2*>(s_b + 2 * pair);
-  const float* wbase = s_w + 2 * pair;
-  // k <= 5: the thread's k*k weights (2 channels) live in registers for the whole tile, which removes the
-  // weight LDS.64 traffic that co-limits the inner loop with the FFMA pipe (for k = 5 it equals the FFMA
-  // issue time).  k = 7 / 9 would need 98 / 162 registers and keep reading weights from shared memory.
-  constexpr bool kRegW = K <= 5;
+  // k <= 5: the thread's k*k weights (2 channels) go straight from global memory (L2-resident, coalesced
+  // 8 B per lane) into registers while the TMA tile is in flight — no shared-memory staging, no weight
+  // LDS in the inner loop.  k = 7 / 9 would need 98 / 162 registers: staged in shared memory instead.
   float2 wreg[kRegW ? K * K : 1];
+  float2 bv = make_float2(0.f, 0.f);
   if (kRegW) {
 #pragma unroll
-    for (int t = 0; t < K * K; ++t) wreg[t] = *reinterpret_cast<const float2*>(wbase + t * CB);
+    for (int t = 0; t < K * K; ++t)
+      wreg[t] = ch_ok ? __ldg(reinterpret_cast<const float2*>(wgt + static_cast<size_t>(t) * C + c0 + 2 * pair))
+                      : make_float2(0.f, 0.f);
+    if (ch_ok) bv = __ldg(reinterpret_cast<const float2*>(bias + c0 + 2 * pair));
+    __syncthreads();  // mbarrier init visible to all threads before they wait on it
+  } else {
+    for (int i = threadIdx.x; i < K * K * CB; i += blockDim.x) {
+      const int t = i / CB, c = i - t * CB;
+      s_w[i] = (c0 + c < C) ? __ldg(wgt + static_cast<size_t>(t) * C + c0 + c) : 0.0f;
+    }
+    for (int i = threadIdx.x; i < CB; i += blockDim.x) s_b[i] = (c0 + i < C) ? __ldg(bias + c0 + i) : 0.0f;
+    __syncthreads();
+    bv = *reinterpret_cast<const float2*>(s_b + 2 * pair);
   }
+  mbar_wait(bar, 0);
+  const float* wbase = s_w + 2 * pair;
 
 #pragma unroll 1
   for (int u = warp; u < UNITS; u += 4) {
@@ -175,7 +180,7 @@ static int32_t launch_dw(const maf_tensor* src, const float* w, const float* bia
   if (r != CUDA_SUCCESS)
     return fail(MAF_E_CUDA, "dwconv: cuTensorMapEncodeTiled(c=%d w=%d h=%d n=%d) failed: %d", src->c, src->w, src->h,
                 src->n, (int)r);
-  const size_t smem = static_cast<size_t>(TH) * TW * CB * 2 + static_cast<size_t>(K * K + 1) * CB * 4 + 16;
+  const size_t smem = static_cast<size_t>(TH) * TW * CB * 2 + (K <= 5 ? 0 : static_cast<size_t>(K * K + 1) * CB * 4) + 16;
   static bool configured = false;
   if (!configured) {
     cudaError_t e =
@@ -211,6 +216,8 @@ extern "C" int32_t mafb200_dwconv(const maf_tensor* src, const float* weight, co
   if ((src->c & 1) || (dst->c_stride & 1) || (reinterpret_cast<uintptr_t>(dst->ptr) & 3))
     return fail(MAF_E_ALIGN, "dwconv: channels and dst stride must be even, dst 4-B aligned");
   if (!aligned_f16_view(src)) return fail(MAF_E_ALIGN, "dwconv: src must be 16-B aligned with c_stride %% 8 == 0 (TMA)");
+  if ((reinterpret_cast<uintptr_t>(weight) & 7) || (reinterpret_cast<uintptr_t>(bias) & 7))
+    return fail(MAF_E_ALIGN, "dwconv: weight / bias must be 8-B aligned");
   if (src->n > 65535) return fail(MAF_E_ARG, "dwconv: batch %d > 65535", src->n);
   if (act != MAF_ACT_NONE && act != MAF_ACT_SILU && act != MAF_ACT_RELU) return fail(MAF_E_ARG, "dwconv: bad act");
   if (k != 3 && k != 5 && k != 7 && k != 9) return fail(MAF_E_ARG, "dwconv: kernel size %d not in {3,5,7,9}", k);
