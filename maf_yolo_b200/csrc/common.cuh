@@ -57,6 +57,13 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// Programmatic dependent launch (see host.h launch_pdl).  pdl_wait blocks until every prerequisite grid
+// has completed and its writes are visible; pdl_launch_dependents lets the next kernel of the stream be
+// scheduled early (it then parks in its own pdl_wait).  Kernels that allocate TMEM trigger only AFTER
+// their allocation, so a dependent CTA can never take the columns its prerequisite still needs.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }

@@ -35,6 +35,8 @@ struct DecodeParams {
 };
 
 __global__ void __launch_bounds__(256) head_decode_kernel(const __grid_constant__ DecodeParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float s_box[kAnchorsPerCta][4];
   __shared__ __align__(16) __half s_reg[kAnchorsPerCta * 264];  // up to 4*(63+1)=256 (+pad) halves per anchor
   const int b = blockIdx.y;
@@ -168,6 +170,6 @@ extern "C" int32_t mafb200_head_decode(const maf_tensor* cls_logits, const maf_t
   if (n > 65535) return fail(MAF_E_ARG, "head_decode: batch %d > 65535", n);
   int32_t rc = require_sm100();
   if (rc) return rc;
-  head_decode_kernel<<<dim3(ctas, n), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  launch_pdl(head_decode_kernel, dim3(ctas, n), dim3(256), 0, static_cast<cudaStream_t>(stream), p);
   return check_launch("head_decode kernel launch");
 }

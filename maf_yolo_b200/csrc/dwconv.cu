@@ -73,6 +73,8 @@ __global__ void __launch_bounds__(128)
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
     fence_barrier_init();
+    pdl_launch_dependents();
+    pdl_wait();  // the input tile (and, causally through `bar`, every output store) follows the previous kernels
     mbar_arrive_expect_tx(bar, kTileBytes);
     tma_load_tile_4d(s_in, &tm_in, bar, c0, x0 - P, y0 - P, img);
   }
@@ -190,8 +192,8 @@ static int32_t launch_dw(const maf_tensor* src, const float* w, const float* bia
   }
   const int tiles_x = ceil_div(src->w, kDwTXB), tiles_y = ceil_div(src->h, kDwTYB);
   dim3 grid(tiles_x * tiles_y, ceil_div(src->c, CB), src->n);
-  dwconv_kernel<K, CB><<<grid, 128, smem, st>>>(tm, static_cast<__half*>(dst->ptr), dst->c_stride, w, bias, src->h,
-                                                src->w, src->c, act, tiles_x);
+  launch_pdl(dwconv_kernel<K, CB>, grid, dim3(128), smem, st, tm, static_cast<__half*>(dst->ptr), dst->c_stride, w, bias,
+             src->h, src->w, src->c, act, tiles_x);
   return check_launch("dwconv kernel launch");
 }
 

@@ -312,14 +312,19 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t acc_cols = p.tmem_cols >> 1;  // columns of one accumulator buffer
+  // TMEM is allocated: the next kernel of the stream may now be scheduled behind this one (PDL)
+  if (threadIdx.x == 0) pdl_launch_dependents();
 
   if (warp == 0) {
     // ---- TMA producer ---------------------------------------------------------------------------
     if (lane == 0 && mt0 < m_tiles) {
-      if (w_res) {
+      if (w_res) {  // weights are constants: fetched while the previous kernel may still be running
         mbar_arrive_expect_tx(w_bar, total_kb * b_bytes);
         for (int k = 0; k < total_kb; ++k) tma_load_2d(s_wpanel + k * b_bytes, &p.tmW, w_bar, k * kBlockK, n0);
       }
+      // every global read of activations (and, through the MMA -> epilogue chain, every store) is ordered
+      // after the prerequisite kernels by this wait
+      pdl_wait();
       int kb = 0;  // running ring position across tiles
       for (int mt = mt0; mt < m_tiles; mt += mt_step) {
         const int m0 = mt * kBlockM;
@@ -486,7 +491,7 @@ static int32_t launch_gemm(GemmParams& p, int n_tiles, int total_kb, cudaStream_
     configured = true;
   }
   if (smem > 227 * 1024) return fail(MAF_E_ARG, "gemm: %zu B of shared memory needed", smem);
-  gemm_tc_kernel<kMode == kModeIm2colTma><<<grid, kGemmThreads, smem, stream>>>(p);
+  launch_pdl(gemm_tc_kernel<kMode == kModeIm2colTma>, dim3(grid), dim3(kGemmThreads), smem, stream, p);
   return check_launch(kMode == kModeTma2d ? "conv1x1 kernel launch" : "conv3x3s2 kernel launch");
 }
 

@@ -1,6 +1,8 @@
 // Host-side plumbing: thread-local error text, launch counter, device check, driver entry points.
 #include "host.h"
 
+#include <stdlib.h>
+
 #include <atomic>
 #include <mutex>
 
@@ -21,6 +23,14 @@ const char* last_error_text() { return g_err; }
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 int64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* v = getenv("MAFB200_PDL");
+    return !(v && v[0] == '0');
+  }();
+  return on;
+}
 
 int32_t check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();

@@ -35,6 +35,28 @@ typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
 EncodeTiledFn encode_tiled_fn();
 EncodeIm2colFn encode_im2col_fn();
 
+// Programmatic dependent launch: every kernel of this library executes pdl_wait() (griddepcontrol.wait)
+// before it touches memory another kernel may have produced, so consecutive launches in a stream (and
+// the kernel->kernel edges of a captured graph) may overlap the next kernel's prologue (barrier init,
+// TMEM allocation, weight loads) with the previous kernel's tail.  MAFB200_PDL=0 turns it off.
+bool pdl_enabled();
+
+template <bool kPdl = true, typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                       Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (kPdl && pdl_enabled()) ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);  // error picked up by check_launch()
+}
+
 inline bool valid_f16_view(const maf_tensor* t) {
   return t && t->ptr && t->dtype == MAF_F16 && t->n > 0 && t->h > 0 && t->w > 0 && t->c > 0 && t->c_stride >= t->c;
 }

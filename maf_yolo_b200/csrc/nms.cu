@@ -54,6 +54,8 @@ struct NmsParams {
 
 // ---- kernel 1: threshold + compaction ----------------------------------------------------------
 __global__ void __launch_bounds__(256) nms_compact_kernel(const NmsParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int a = blockIdx.x * 8 + warp;
   const int b = blockIdx.y;
@@ -157,6 +159,8 @@ __device__ __forceinline__ bool iou_gt(float ax1, float ay1, float ax2, float ay
 
 // ---- kernel 2: per-image sort + greedy NMS ---------------------------------------------------------
 __global__ void __launch_bounds__(1024) nms_select_kernel(const NmsParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ unsigned long long s_dyn[];
   unsigned long long* s_keys = s_dyn;                                          // [kSortSmemKeys]
   float* k_box = reinterpret_cast<float*>(s_keys + kSortSmemKeys);             // kept: [max_det][5]
@@ -382,7 +386,8 @@ extern "C" int32_t mafb200_nms(const float* pred, int32_t batch, int32_t anchors
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaError_t e = cudaMemsetAsync(p.ncand, 0, static_cast<size_t>(batch) * 4, st);
   if (e != cudaSuccess) return fail(MAF_E_CUDA, "nms: cudaMemsetAsync: %s", cudaGetErrorString(e));
-  nms_compact_kernel<<<dim3(ceil_div(anchors, 8), batch), 256, 0, st>>>(p);
+  // follows a memset node, not a kernel: plain stream-ordered launch
+  launch_pdl<false>(nms_compact_kernel, dim3(ceil_div(anchors, 8), batch), dim3(256), 0, st, p);
   rc = check_launch("nms_compact kernel launch");
   if (rc) return rc;
 
@@ -395,6 +400,6 @@ extern "C" int32_t mafb200_nms(const float* pred, int32_t batch, int32_t anchors
     if (e != cudaSuccess) return fail(MAF_E_CUDA, "nms: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
   }
-  nms_select_kernel<<<batch, 1024, smem, st>>>(p);
+  launch_pdl<false>(nms_select_kernel, dim3(batch), dim3(1024), smem, st, p);
   return check_launch("nms_select kernel launch");
 }

@@ -24,6 +24,8 @@ __device__ __forceinline__ uint4 hmax8(uint4 a, uint4 b) {
 __global__ void __launch_bounds__(256)
     maxpool2x2_kernel(const __half* __restrict__ in, int in_ld, __half* __restrict__ out, int out_ld, int B, int H,
                       int W, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int cg = C >> 3;
   const int Ho = H >> 1, Wo = W >> 1;
   const long long total = static_cast<long long>(B) * Ho * Wo * cg;
@@ -51,6 +53,8 @@ __global__ void __launch_bounds__(256)
     sppf_pool_kernel(const __half* __restrict__ in, int in_ld, __half* __restrict__ y1, int ld1,
                      __half* __restrict__ y2, int ld2, __half* __restrict__ y3, int ld3, int H, int W, int C) {
   extern __shared__ uint4 s_map[];  // [4][H*W]: input, row-max r2, r4, r6
+  pdl_launch_dependents();
+  pdl_wait();
   const int cg = C >> 3;
   const int g = blockIdx.x % cg;
   const int b = blockIdx.x / cg;
@@ -103,6 +107,8 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     upsample2x_kernel(const __half* __restrict__ in, int in_ld, __half* __restrict__ out, int out_ld, int B, int H,
                       int W, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int cg = C >> 3;
   const long long total = static_cast<long long>(B) * H * W * cg;
   const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -127,6 +133,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
     nchw_to_nhwc_kernel(const T* __restrict__ in, __half* __restrict__ out, int out_ld, int C, int HW) {
   __shared__ float tile[32][33];
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.z;
   const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -147,6 +155,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
     nhwc_to_nchw_kernel(const __half* __restrict__ in, int in_ld, T* __restrict__ out, int C, int HW) {
   __shared__ float tile[32][33];
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.z;
   const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -178,7 +188,8 @@ extern "C" int32_t mafb200_maxpool2x2(const maf_tensor* src, const maf_tensor* d
   int32_t rc = require_sm100();
   if (rc) return rc;
   const long long total = static_cast<long long>(dst->n) * dst->h * dst->w * (dst->c / 8);
-  maxpool2x2_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(maxpool2x2_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0,
+             static_cast<cudaStream_t>(stream),
       static_cast<const __half*>(src->ptr), src->c_stride, static_cast<__half*>(dst->ptr), dst->c_stride, src->n,
       src->h, src->w, src->c);
   return check_launch("maxpool2x2 kernel launch");
@@ -205,7 +216,7 @@ extern "C" int32_t mafb200_sppf_pool(const maf_tensor* src, const maf_tensor* y1
     configured = true;
   }
   const unsigned blocks = static_cast<unsigned>(src->n) * (src->c / 8);
-  sppf_pool_kernel<<<blocks, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(sppf_pool_kernel, dim3(blocks), dim3(256), smem, static_cast<cudaStream_t>(stream),
       static_cast<const __half*>(src->ptr), src->c_stride, static_cast<__half*>(y1->ptr), y1->c_stride,
       static_cast<__half*>(y2->ptr), y2->c_stride, static_cast<__half*>(y3->ptr), y3->c_stride, src->h, src->w,
       src->c);
@@ -220,7 +231,8 @@ extern "C" int32_t mafb200_upsample2x(const maf_tensor* src, const maf_tensor* d
   int32_t rc = require_sm100();
   if (rc) return rc;
   const long long total = static_cast<long long>(src->n) * src->h * src->w * (src->c / 8);
-  upsample2x_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(upsample2x_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0,
+             static_cast<cudaStream_t>(stream),
       static_cast<const __half*>(src->ptr), src->c_stride, static_cast<__half*>(dst->ptr), dst->c_stride, src->n,
       src->h, src->w, src->c);
   return check_launch("upsample2x kernel launch");
@@ -234,10 +246,10 @@ extern "C" int32_t mafb200_nchw_to_nhwc_f16(const void* src, int32_t src_dtype, 
   dim3 grid(ceil_div(HW, 32), ceil_div(dst->c, 32), dst->n);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (src_dtype == MAF_F32)
-    nchw_to_nhwc_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(src), static_cast<__half*>(dst->ptr),
+    launch_pdl(nchw_to_nhwc_kernel<float>, grid, dim3(256), 0, st, static_cast<const float*>(src), static_cast<__half*>(dst->ptr),
                                                      dst->c_stride, dst->c, HW);
   else if (src_dtype == MAF_F16)
-    nchw_to_nhwc_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(src), static_cast<__half*>(dst->ptr),
+    launch_pdl(nchw_to_nhwc_kernel<__half>, grid, dim3(256), 0, st, static_cast<const __half*>(src), static_cast<__half*>(dst->ptr),
                                                       dst->c_stride, dst->c, HW);
   else
     return fail(MAF_E_ARG, "nchw_to_nhwc: unsupported dtype %d", src_dtype);
@@ -252,10 +264,10 @@ extern "C" int32_t mafb200_nhwc_f16_to_nchw(const maf_tensor* src, void* dst, in
   dim3 grid(ceil_div(HW, 32), ceil_div(src->c, 32), src->n);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dst_dtype == MAF_F32)
-    nhwc_to_nchw_kernel<float><<<grid, 256, 0, st>>>(static_cast<const __half*>(src->ptr), src->c_stride,
+    launch_pdl(nhwc_to_nchw_kernel<float>, grid, dim3(256), 0, st, static_cast<const __half*>(src->ptr), src->c_stride,
                                                      static_cast<float*>(dst), src->c, HW);
   else if (dst_dtype == MAF_F16)
-    nhwc_to_nchw_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(src->ptr), src->c_stride,
+    launch_pdl(nhwc_to_nchw_kernel<__half>, grid, dim3(256), 0, st, static_cast<const __half*>(src->ptr), src->c_stride,
                                                       static_cast<__half*>(dst), src->c, HW);
   else
     return fail(MAF_E_ARG, "nhwc_to_nchw: unsupported dtype %d", dst_dtype);

@@ -110,6 +110,8 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const T* __restrict__ x,
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
+  if (t == 0) pdl_launch_dependents();  // after the TMEM allocation (see common.cuh)
+  pdl_wait();                           // x / out may belong to kernels still running
   const uint32_t tmem_base = s_tmem;
   const uint64_t da = umma_smem_desc_noswz(smem_u32(s_a));
   const uint64_t db = umma_smem_desc_noswz(smem_u32(s_b));
@@ -261,15 +263,15 @@ extern "C" int32_t mafb200_stem_conv3x3s2(const void* x_nchw, int32_t x_dtype, i
   const int st256 = ((dst->c_stride % 16) == 0 && (reinterpret_cast<uintptr_t>(dst->ptr) & 31) == 0) ? 1 : 0;
   switch (x_dtype) {
     case MAF_F32:
-      stem_conv_kernel<float><<<blocks, 128, 0, st>>>(static_cast<const float*>(x_nchw), weight, bias, out, n, h, w,
+      launch_pdl(stem_conv_kernel<float>, dim3(blocks), dim3(128), 0, st, static_cast<const float*>(x_nchw), weight, bias, out, n, h, w,
                                                       dst->c, tile_n, tmem_cols, idesc, dst->c_stride, act, st256);
       break;
     case MAF_F16:
-      stem_conv_kernel<__half><<<blocks, 128, 0, st>>>(static_cast<const __half*>(x_nchw), weight, bias, out, n, h, w,
+      launch_pdl(stem_conv_kernel<__half>, dim3(blocks), dim3(128), 0, st, static_cast<const __half*>(x_nchw), weight, bias, out, n, h, w,
                                                        dst->c, tile_n, tmem_cols, idesc, dst->c_stride, act, st256);
       break;
     case MAF_U8:
-      stem_conv_kernel<uint8_t><<<blocks, 128, 0, st>>>(static_cast<const uint8_t*>(x_nchw), weight, bias, out, n, h,
+      launch_pdl(stem_conv_kernel<uint8_t>, dim3(blocks), dim3(128), 0, st, static_cast<const uint8_t*>(x_nchw), weight, bias, out, n, h,
                                                         w, dst->c, tile_n, tmem_cols, idesc, dst->c_stride, act, st256);
       break;
     default:
