@@ -329,7 +329,7 @@ def run_ours(a):
         "frac": round(achieved / peak, 4), "traffic": profiled_traffic(top, a.variant, B), "peak_source": peak_src,
         "bytes_per_launch": int(ft["bytes"] / ft["launches"]), "avg_launch_us": round(1e3 * ft["ms"] / ft["launches"], 2),
         "share_of_forward": round(ft["ms"] / tot_ms, 3),
-        "families": {k: {"share": round(v["ms"] / tot_ms, 3), "GB/s": round(v["bytes"] / 1e9 / (v["ms"] / 1e3), 1),
+        "families": {k: {"share": round(v["ms"] / tot_ms, 3), "us_per_forward": round(1e3 * v["ms"] * len(eng.plan.ops) / sum(f["launches"] for f in fam.values()), 1), "GB/s": round(v["bytes"] / 1e9 / (v["ms"] / 1e3), 1),
                          "TFLOP/s": round(v["flops"] / 1e12 / (v["ms"] / 1e3), 2)} for k, v in sorted(fam.items())},
     }
     plan = eng.plan

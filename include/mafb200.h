@@ -116,6 +116,16 @@ MAFB200_API int32_t mafb200_stem_conv3x3s2(const void* x_nchw, int32_t x_dtype, 
 MAFB200_API int32_t mafb200_dwconv(const maf_tensor* src, const float* weight, const float* bias, int32_t k, int32_t act,
                        const maf_tensor* dst, void* stream);
 
+/* ---- the same depth-wise conv on the tensor cores (mma.sync, Toeplitz formulation; c % 8 == 0) ---------
+ * The k*k fp32 weights of each channel are packed ON THE HOST (pure CPU, no GPU needed) into fp16 B
+ * fragments: `table` = mafb200_dw_tc_table_bytes(c, k) bytes; weight fp32 [c][k][k] (PyTorch's [C,1,k,k]).
+ * mafb200_dwconv_tc takes the table as DEVICE memory; dst must be 32-B aligned with c_stride % 16 == 0.
+ * Replaces the same reference lines as mafb200_dwconv (common.py:2948-3100, 915-923, 1328-1334). */
+MAFB200_API size_t mafb200_dw_tc_table_bytes(int32_t c, int32_t k);
+MAFB200_API int32_t mafb200_dw_tc_pack(const float* weight_host, int32_t c, int32_t k, void* table_host);
+MAFB200_API int32_t mafb200_dwconv_tc(const maf_tensor* src, const void* table, const float* bias, int32_t k,
+                          int32_t act, const maf_tensor* dst, void* stream);
+
 /* ---- pooling / resampling ------------------------------------------------------------------- */
 MAFB200_API int32_t mafb200_maxpool2x2(const maf_tensor* src, const maf_tensor* dst, void* stream);
 /* y1 = maxpool5(x), y2 = maxpool5(y1), y3 = maxpool5(y2) (stride 1, pad 2, -inf padding). */

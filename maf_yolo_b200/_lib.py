@@ -54,6 +54,10 @@ _SIGNATURES = {
                                            C.c_void_p, C.c_int32, _P(MafTensor), C.c_void_p]),
     "mafb200_dwconv": (C.c_int32, [_P(MafTensor), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, _P(MafTensor),
                                    C.c_void_p]),
+    "mafb200_dw_tc_table_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "mafb200_dw_tc_pack": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "mafb200_dwconv_tc": (C.c_int32, [_P(MafTensor), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, _P(MafTensor),
+                                      C.c_void_p]),
     "mafb200_maxpool2x2": (C.c_int32, [_P(MafTensor), _P(MafTensor), C.c_void_p]),
     "mafb200_sppf_pool": (C.c_int32, [_P(MafTensor), _P(MafTensor), _P(MafTensor), _P(MafTensor), C.c_void_p]),
     "mafb200_upsample2x": (C.c_int32, [_P(MafTensor), _P(MafTensor), C.c_void_p]),

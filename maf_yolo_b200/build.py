@@ -16,7 +16,7 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libmafb200.so"
-SOURCES = ["host.cu", "gemm_tc.cu", "stem_conv.cu", "dwconv.cu", "pool.cu", "decode.cu", "nms.cu"]
+SOURCES = ["host.cu", "gemm_tc.cu", "stem_conv.cu", "dwconv.cu", "dwconv_tc.cu", "pool.cu", "decode.cu", "nms.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

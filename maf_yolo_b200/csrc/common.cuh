@@ -254,6 +254,15 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   return *reinterpret_cast<float2*>(&rd);
 }
 
+// Packed 2 x fp32 add (SASS FADD2), bit-identical to two __fadd_rn.
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a);
+  unsigned long long rb = *reinterpret_cast<unsigned long long*>(&b);
+  unsigned long long rd;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rd);
+}
+
 // ----------------------------------------------------------------------------------------------
 // Small numeric helpers
 // ----------------------------------------------------------------------------------------------

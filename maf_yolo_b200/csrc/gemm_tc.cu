@@ -77,29 +77,31 @@ __device__ __forceinline__ void st_global_256(void* ptr, const uint32_t* v) {
 }
 
 // bias + activation + fp16 pack of 32 accumulator columns, specialised per activation so the element loop
-// has no per-element dispatch.  SiLU: h = 0.5*(acc + bias) as ONE FFMA against the pre-halved bias, then
-// h + h*tanh(h): 3 instructions (FFMA, MUFU.TANH, FFMA) per element.
+// has no per-element dispatch, on the packed fp32x2 pipe (FFMA2 / FADD2: two IEEE results per issue slot,
+// bit-identical to the scalar forms).  SiLU = h + h*tanh(h) with h = 0.5*acc + 0.5*bias: per PAIR of
+// elements FFMA2, 2 x MUFU.TANH, FFMA2, F2FP — 2.5 issue slots per element instead of 4.5.
 template <int kAct>
 __device__ __forceinline__ void epi_pack32(const uint32_t (&r)[32], const float* __restrict__ bias,
                                            const float* __restrict__ half_bias, uint32_t (&pk)[16]) {
+  const float2 half2c = make_float2(0.5f, 0.5f);
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
-    float v[2];
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const float acc = __uint_as_float(r[2 * j + e]);
-      if (kAct == ACT_SILU) {
-        const float h = fmaf(acc, 0.5f, half_bias[2 * j + e]);
-        v[e] = fmaf(h, tanh_approx(h), h);
-      } else if (kAct == ACT_RELU) {
-        v[e] = fmaxf(acc + bias[2 * j + e], 0.0f);
+    const float2 acc = make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+    float2 v;
+    if (kAct == ACT_SILU) {
+      const float2 h = ffma2(acc, half2c, *reinterpret_cast<const float2*>(half_bias + 2 * j));
+      v = ffma2(h, make_float2(tanh_approx(h.x), tanh_approx(h.y)), h);
+    } else {
+      v = fadd2(acc, *reinterpret_cast<const float2*>(bias + 2 * j));
+      if (kAct == ACT_RELU) {
+        v.x = fmaxf(v.x, 0.0f);
+        v.y = fmaxf(v.y, 0.0f);
       } else if (kAct == ACT_SIGMOID) {
-        v[e] = __fdividef(1.0f, 1.0f + __expf(-(acc + bias[2 * j + e])));
-      } else {
-        v[e] = acc + bias[2 * j + e];
+        v.x = __fdividef(1.0f, 1.0f + __expf(-v.x));
+        v.y = __fdividef(1.0f, 1.0f + __expf(-v.y));
       }
     }
-    pk[j] = pack_half2(v[0], v[1]);
+    pk[j] = pack_half2(v.x, v.y);
   }
 }
 
@@ -188,12 +190,10 @@ __device__ __forceinline__ void gemm_epilogue_loop(const GemmParams& p, const Ge
         // 32 independent bias+activation chains first (MUFU latency overlaps), then pack + store
         const int valid = min(32, p.tile_n - c);  // 32 or 16 (tile_n % 16 == 0)
         uint32_t pk[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float a = apply_act_fast(__uint_as_float(r[2 * j]) + s_bias[c + 2 * j], act);
-          const float b = apply_act_fast(__uint_as_float(r[2 * j + 1]) + s_bias[c + 2 * j + 1], act);
-          pk[j] = pack_half2(a, b);
-        }
+        if (act == ACT_SILU) epi_pack32<ACT_SILU>(r, s_bias + c, s_hbias + c, pk);
+        else if (act == ACT_NONE) epi_pack32<ACT_NONE>(r, s_bias + c, s_hbias + c, pk);
+        else if (act == ACT_RELU) epi_pack32<ACT_RELU>(r, s_bias + c, s_hbias + c, pk);
+        else epi_pack32<ACT_SIGMOID>(r, s_bias + c, s_hbias + c, pk);
         if (p.st256 && n + valid <= p.N) {
           // full 32-byte sectors: 2 (or 1) x 256-bit stores for this thread's 64 (32) contiguous bytes
           st_global_256(orow + n, pk);

@@ -15,6 +15,7 @@ stem kernel; the result is the reference's `[B, A, 5+nc]` fp32 prediction tensor
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
@@ -336,6 +337,10 @@ class Engine:
             self._weights[op.name] = (w, b)
             return lambda: ops.conv3x3s2(reads[0], w, b, op.act, writes[0])
         if op.kind == "dwconv":
+            if reads[0].c % 8 == 0 and writes[0].ld % 16 == 0 and os.environ.get("MAFB200_DW_TC", "1") != "0":
+                w, b = ops.pack_dw_tc(*folded[op.weight], device=dev)  # tensor-core (Toeplitz HMMA) kernel
+                self._weights[op.name] = (w, b)
+                return lambda: ops.dwconv_tc(reads[0], w, b, op.k, op.act, writes[0])
             w, b = ops.pack_dw(*folded[op.weight], device=dev)
             self._weights[op.name] = (w, b)
             return lambda: ops.dwconv(reads[0], w, b, op.k, op.act, writes[0])
