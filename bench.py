@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--streams", type=int, default=4, help="streams captured into the CUDA graph (branch concurrency)")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="run NMS on the forward's stream (strictly sequential steps) instead of model.detect_async")
     return ap.parse_args()
 
 
@@ -233,12 +235,28 @@ def run_ours(a):
     det_host = torch.empty_like(det, device="cpu").pin_memory()
     cnt_host = torch.empty_like(cnt, device="cpu").pin_memory()
 
-    def step(x):
+    pipelined = not a.no_pipeline
+    last_done = [None]
+
+    def gather(d, c):
+        return mdist.all_gather_detections(d, c, B * world) if world > 1 else (d, c)
+
+    def step(x, after=None):
+        """One pass of the hot path over one batch.  Pipelined (default): the public serving call
+        model.detect_async — forward + decode on this stream, this batch's NMS (+ all-gather / D2H) on a side
+        stream where it overlaps the NEXT step's forward; every step's work is still inside the timed region
+        (the closing event waits for the last NMS)."""
+        if pipelined:
+            fn = (lambda d, c: after(*gather(d, c))) if after is not None else gather
+            d, c, done, res = model.detect_async(x, **EVAL_NMS, after_nms=fn)
+            last_done[0] = done
+            return res if after is None else (d, c)
         pred = model(x)[0]
         mb.non_max_suppression_padded(pred, **EVAL_NMS, det=det, count=cnt)
-        if world > 1:
-            return mdist.all_gather_detections(det, cnt, B * world)
-        return det, cnt
+        res = gather(det, cnt)
+        if after is not None:
+            after(*res)
+        return res
 
     def barrier():
         if world > 1:
@@ -251,6 +269,8 @@ def run_ours(a):
         s.record()
         for i in range(steps):
             fn(i)
+        if last_done[0] is not None:
+            torch.cuda.current_stream().wait_event(last_done[0])  # the last step's side-stream NMS is part of the region
         e.record()
         barrier()
         ms = s.elapsed_time(e)
@@ -288,6 +308,10 @@ def run_ours(a):
     for ev in consumed:
         ev.record(main_stream)
 
+    def d2h(d, c):  # runs on the stream the NMS ran on
+        det_host.copy_(d[:B] if world == 1 else d[rank * B:(rank + 1) * B], non_blocking=True)
+        cnt_host.copy_(c[:B] if world == 1 else c[rank * B:(rank + 1) * B], non_blocking=True)
+
     def e2e_step(i):
         k = i % 2
         with torch.cuda.stream(copy_stream):
@@ -295,10 +319,8 @@ def run_ours(a):
             x_u8[k].copy_(host_u8[k], non_blocking=True)
             ready[k].record(copy_stream)
         main_stream.wait_event(ready[k])
-        d, c = step(x_u8[k])
-        consumed[k].record(main_stream)
-        det_host.copy_(d[:B] if world == 1 else d[rank * B:(rank + 1) * B], non_blocking=True)
-        cnt_host.copy_(c[:B] if world == 1 else c[rank * B:(rank + 1) * B], non_blocking=True)
+        step(x_u8[k], after=d2h)
+        consumed[k].record(main_stream)  # the forward (the only reader of x_u8[k]) is enqueued on the main stream
 
     for i in range(3):
         e2e_step(i)
@@ -353,7 +375,9 @@ def run_ours(a):
         "data": "synthetic",
         "config": {"workload": workload_name(a), "global_batch": B * world, "parallelism": f"dp{world} (image shards)",
                    "l2": "inputs (2 rotating 157 MB fp32 batches) and the 460 MB activation arena exceed the 126 MB L2",
-                   "cuda_graph": not a.no_graph, "graph_streams": a.streams},
+                   "cuda_graph": not a.no_graph, "graph_streams": a.streams,
+                   "pipeline": ("model.detect_async: NMS of step i on a side stream overlaps the forward of step i+1 "
+                                "(double-buffered predictions)") if pipelined else "sequential"},
         "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": round(ms_e2e / a.steps, 4), "input": "pinned uint8 NCHW (the dataloader's dtype)"},
         "gpu_launches": per_step_launches * a.steps, "gpu_launches_per_step": per_step_launches,

@@ -17,7 +17,8 @@ PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libmafb200.so"
 SOURCES = ["host.cu", "gemm_tc.cu", "stem_conv.cu", "dwconv.cu", "dwconv_tc.cu", "pool.cu", "decode.cu", "nms.cu"]
-NVCC_FLAGS = [
+EXTRA = os.environ.get("MAFB200_NVCC_EXTRA", "").split()
+NVCC_FLAGS = EXTRA + [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC",

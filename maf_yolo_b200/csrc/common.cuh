@@ -90,6 +90,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // try_wait suspends the thread in hardware until the phase completes or the hint (ns) elapses, so a waiting
 // warp does not burn issue slots polling (the epilogue is issue-bound; ncu showed ~70 % of the GEMM's
 // executed instructions were wait-loop overhead with the un-hinted form).
+#ifndef MAFB200_WAIT_HINT_NS
+#define MAFB200_WAIT_HINT_NS 1000000u
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -99,7 +102,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       "selp.u32 %0, 1, 0, p;\n\t"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(MAFB200_WAIT_HINT_NS)
       : "memory");
   return ok != 0;
 }

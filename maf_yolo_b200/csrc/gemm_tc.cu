@@ -34,6 +34,7 @@
 // (2) a 1-CTA/SM 216 KB shape keeping the 54-72 KB weight panels of the small-Cin layers resident: slower.
 // The im2col TMA itself costs ~0.35-0.55 us per 128-pixel box almost independently of the channel count
 // (one L2 request per pixel row), which is what bounds the 3x3 layers today.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -463,6 +464,13 @@ static int32_t launch_gemm(GemmParams& p, int n_tiles, int total_kb, cudaStream_
     stages = budget / (kABytes + b_bytes);
     if (stages > 2 * total_kb) stages = 2 * total_kb;
     if (stages > 6) stages = 6;
+  }
+  {
+    static const int cap = [] {
+      const char* v = getenv("MAFB200_GEMM_MAX_STAGES");  // experiment knob (no effect measured for 3..12)
+      return v ? atoi(v) : 0;
+    }();
+    if (cap > 0 && stages > cap) stages = cap;
   }
   if (stages < 1) stages = 1;
   // persistent grid: a multiple of n_tiles (each CTA owns one column tile)

@@ -53,74 +53,99 @@ struct NmsParams {
 };
 
 // ---- kernel 1: threshold + compaction ----------------------------------------------------------
+// A CTA stages kCompactRows consecutive prediction rows (one contiguous span of pred) in shared memory
+// with coalesced 16-byte loads — all of them in flight before the first use — then each warp filters
+// rows from there.  (One warp per row straight from global memory ran at 1.7 TB/s: three dependent,
+// unaligned 128-byte loads per row and nothing else in flight.)
+constexpr int kCompactRows = 64;
+
 __global__ void __launch_bounds__(256) nms_compact_kernel(const NmsParams p) {
   pdl_launch_dependents();
   pdl_wait();
+  extern __shared__ __align__(16) float s_rows[];  // [kCompactRows][5 + nc]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int a = blockIdx.x * 8 + warp;
   const int b = blockIdx.y;
-  if (a >= p.A) return;
+  const int a0 = blockIdx.x * kCompactRows;
+  const int rows = min(kCompactRows, p.A - a0);
   const int no = 5 + p.nc;
-  const float* row = p.pred + (static_cast<size_t>(b) * p.A + a) * no;
-  const float obj = __ldg(row + 4);
-
-  // pass 1: raw class maximum (nms.py:48)
-  float mx = -INFINITY;
-  for (int c = lane; c < p.nc; c += 32) mx = fmaxf(mx, __ldg(row + 5 + c));
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  if (!(obj > p.conf) || !(mx > p.conf)) return;
+  const float* src = p.pred + (static_cast<size_t>(b) * p.A + a0) * no;
+  const int nflt = rows * no;
+  if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    const int n4 = nflt >> 2;
+    const float4* src4 = reinterpret_cast<const float4*>(src);
+    float4* dst4 = reinterpret_cast<float4*>(s_rows);
+#pragma unroll 6
+    for (int i = threadIdx.x; i < n4; i += 256) dst4[i] = __ldg(src4 + i);
+    for (int i = (n4 << 2) + threadIdx.x; i < nflt; i += 256) s_rows[i] = __ldg(src + i);
+  } else {
+#pragma unroll 8
+    for (int i = threadIdx.x; i < nflt; i += 256) s_rows[i] = __ldg(src + i);
+  }
+  __syncthreads();
 
   unsigned long long* keys = p.keys + static_cast<size_t>(b) * p.cap_pow2;
-  if (p.multi_label) {
-    for (int c0 = 0; c0 < p.nc; c0 += 32) {
-      const int c = c0 + lane;
-      float s = 0.f;
-      bool pass = false;
-      if (c < p.nc) {
-        s = __fmul_rn(__ldg(row + 5 + c), obj);
-        pass = s > p.conf && (p.class_filter == nullptr || p.class_filter[c] != 0);
-      }
-      const unsigned m = __ballot_sync(0xffffffffu, pass);
-      if (m == 0) continue;
-      int base = 0;
-      if (lane == 0) base = atomicAdd(&p.ncand[b], __popc(m));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (pass) {
-        const long long slot = base + __popc(m & ((1u << lane) - 1));
-        if (slot < p.cap_pow2) {
-          const unsigned sb = __float_as_uint(s);
-          keys[slot] = (static_cast<unsigned long long>(~sb) << 32) |
-                       static_cast<unsigned long long>(static_cast<unsigned>(a) * p.nc + c);
+  for (int r = warp; r < rows; r += 8) {
+    const int a = a0 + r;
+    const float* row = s_rows + r * no;
+    const float obj = row[4];
+
+    // pass 1: raw class maximum (nms.py:48)
+    float mx = -INFINITY;
+    for (int c = lane; c < p.nc; c += 32) mx = fmaxf(mx, row[5 + c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (!(obj > p.conf) || !(mx > p.conf)) continue;
+
+    if (p.multi_label) {
+      for (int c0 = 0; c0 < p.nc; c0 += 32) {
+        const int c = c0 + lane;
+        float s = 0.f;
+        bool pass = false;
+        if (c < p.nc) {
+          s = __fmul_rn(row[5 + c], obj);
+          pass = s > p.conf && (p.class_filter == nullptr || p.class_filter[c] != 0);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, pass);
+        if (m == 0) continue;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&p.ncand[b], __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (pass) {
+          const long long slot = base + __popc(m & ((1u << lane) - 1));
+          if (slot < p.cap_pow2) {
+            const unsigned sb = __float_as_uint(s);
+            keys[slot] = (static_cast<unsigned long long>(~sb) << 32) |
+                         static_cast<unsigned long long>(static_cast<unsigned>(a) * p.nc + c);
+          }
         }
       }
-    }
-  } else {
-    // best class by score, first maximum on ties (torch.max semantics on CPU)
-    float best = -INFINITY;
-    int bi = 0x7fffffff;
-    for (int c = lane; c < p.nc; c += 32) {
-      const float s = __fmul_rn(__ldg(row + 5 + c), obj);
-      if (s > best) {
-        best = s;
-        bi = c;
+    } else {
+      // best class by score, first maximum on ties (torch.max semantics on CPU)
+      float best = -INFINITY;
+      int bi = 0x7fffffff;
+      for (int c = lane; c < p.nc; c += 32) {
+        const float s = __fmul_rn(row[5 + c], obj);
+        if (s > best) {
+          best = s;
+          bi = c;
+        }
       }
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ob > best || (ob == best && oi < bi)) {
-        best = ob;
-        bi = oi;
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) {
+          best = ob;
+          bi = oi;
+        }
       }
-    }
-    if (lane == 0 && best > p.conf && bi < p.nc && (p.class_filter == nullptr || p.class_filter[bi] != 0)) {
-      const long long slot = atomicAdd(&p.ncand[b], 1);
-      if (slot < p.cap_pow2) {
-        const unsigned sb = __float_as_uint(best);
-        keys[slot] = (static_cast<unsigned long long>(~sb) << 32) |
-                     static_cast<unsigned long long>(static_cast<unsigned>(a) * p.nc + bi);
+      if (lane == 0 && best > p.conf && bi < p.nc && (p.class_filter == nullptr || p.class_filter[bi] != 0)) {
+        const long long slot = atomicAdd(&p.ncand[b], 1);
+        if (slot < p.cap_pow2) {
+          const unsigned sb = __float_as_uint(best);
+          keys[slot] = (static_cast<unsigned long long>(~sb) << 32) |
+                       static_cast<unsigned long long>(static_cast<unsigned>(a) * p.nc + bi);
+        }
       }
     }
   }
@@ -146,13 +171,20 @@ __device__ __forceinline__ void bitonic_sort(unsigned long long* k, int P) {
   __syncthreads();
 }
 
-__device__ __forceinline__ bool iou_gt(float ax1, float ay1, float ax2, float ay2, float aarea, float bx1, float by1,
-                                       float bx2, float by2, float barea, double thr) {
+// Intersection area exactly as torchvision computes it (fp32, no FMA contraction).
+__device__ __forceinline__ float box_inter(float ax1, float ay1, float ax2, float ay2, float bx1, float by1, float bx2,
+                                           float by2) {
   const float xx1 = fmaxf(ax1, bx1), yy1 = fmaxf(ay1, by1);
   const float xx2 = fminf(ax2, bx2), yy2 = fminf(ay2, by2);
   const float w = fmaxf(0.0f, __fsub_rn(xx2, xx1));
   const float h = fmaxf(0.0f, __fsub_rn(yy2, yy1));
-  const float inter = __fmul_rn(w, h);
+  return __fmul_rn(w, h);
+}
+// inter / (area_a + area_b - inter) > thr with IEEE division, threshold compared in double (torchvision CPU).
+// inter == 0 gives 0 (or NaN for two empty boxes): never > thr for thr in [0, 1], so callers test
+// `inter > 0` first and only pay the division for boxes that actually overlap — with class-offset boxes
+// (nms.py:94-95) that is a few percent of all pairs.
+__device__ __forceinline__ bool iou_gt_inter(float inter, float aarea, float barea, double thr) {
   const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aarea, barea), inter));
   return static_cast<double>(ovr) > thr;
 }
@@ -234,10 +266,12 @@ __global__ void __launch_bounds__(1024) nms_select_kernel(const NmsParams p) {
       const int ci = threadIdx.x >> 2, part = threadIdx.x & 3;
       if (ci < cn) {
         const float* cb = c_box + ci * 5;
+        const float b0 = cb[0], b1 = cb[1], b2 = cb[2], b3 = cb[3], b4 = cb[4];
         bool dead = false;
         for (int k = part; k < nk0 && !dead; k += 4) {
           const float* kb = k_box + k * 5;
-          dead = iou_gt(kb[0], kb[1], kb[2], kb[3], kb[4], cb[0], cb[1], cb[2], cb[3], cb[4], p.iou);
+          const float inter = box_inter(kb[0], kb[1], kb[2], kb[3], b0, b1, b2, b3);
+          if (inter > 0.0f) dead = iou_gt_inter(inter, kb[4], b4, p.iou);
         }
         if (dead) c_alive[ci] = 0;
       }
@@ -256,11 +290,20 @@ __global__ void __launch_bounds__(1024) nms_select_kernel(const NmsParams p) {
       if (i >= cn || !c_alive[i] || j0 + 63 <= i) continue;  // c_mask was zeroed in (1)
       const float* ib = c_box + i * 5;
       const float i0 = ib[0], i1 = ib[1], i2 = ib[2], i3 = ib[3], i4 = ib[4];
-      unsigned long long bits = 0ull;
       const int jlo = max(j0, i + 1), jhi = min(j0 + 64, cn);
+      // pass 1: which boxes overlap at all (no division); pass 2: exact IoU test for those only
+      unsigned long long cand = 0ull;
       for (int j = jlo; j < jhi; ++j) {
         const float* jb = c_box + j * 5;
-        if (iou_gt(i0, i1, i2, i3, i4, jb[0], jb[1], jb[2], jb[3], jb[4], p.iou)) bits |= 1ull << (j - j0);
+        if (box_inter(i0, i1, i2, i3, jb[0], jb[1], jb[2], jb[3]) > 0.0f) cand |= 1ull << (j - j0);
+      }
+      unsigned long long bits = 0ull;
+      while (cand) {
+        const int bpos = __ffsll(static_cast<long long>(cand)) - 1;
+        cand &= cand - 1ull;
+        const float* jb = c_box + (j0 + bpos) * 5;
+        const float inter = box_inter(i0, i1, i2, i3, jb[0], jb[1], jb[2], jb[3]);
+        if (iou_gt_inter(inter, i4, jb[4], p.iou)) bits |= 1ull << bpos;
       }
       c_mask[t] = bits;
     }
@@ -387,7 +430,15 @@ extern "C" int32_t mafb200_nms(const float* pred, int32_t batch, int32_t anchors
   cudaError_t e = cudaMemsetAsync(p.ncand, 0, static_cast<size_t>(batch) * 4, st);
   if (e != cudaSuccess) return fail(MAF_E_CUDA, "nms: cudaMemsetAsync: %s", cudaGetErrorString(e));
   // follows a memset node, not a kernel: plain stream-ordered launch
-  launch_pdl<false>(nms_compact_kernel, dim3(ceil_div(anchors, 8), batch), dim3(256), 0, st, p);
+  const size_t csmem = static_cast<size_t>(kCompactRows) * (5 + nc) * sizeof(float);
+  if (csmem > 200 * 1024) return fail(MAF_E_ARG, "nms: nc=%d too large for the compaction tile", nc);
+  static size_t compact_smem_cfg = 48 * 1024;
+  if (csmem > compact_smem_cfg) {
+    e = cudaFuncSetAttribute(nms_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(csmem));
+    if (e != cudaSuccess) return fail(MAF_E_CUDA, "nms: cudaFuncSetAttribute(compact): %s", cudaGetErrorString(e));
+    compact_smem_cfg = csmem;
+  }
+  launch_pdl<false>(nms_compact_kernel, dim3(ceil_div(anchors, kCompactRows), batch), dim3(256), csmem, st, p);
   rc = check_launch("nms_compact kernel launch");
   if (rc) return rc;
 

@@ -295,13 +295,18 @@ class Engine:
         with torch.cuda.device(self.device):
             nbytes = self.plan.assign_offsets(batch, reuse=reuse_buffers)
             self.arena = torch.empty(nbytes // 2, dtype=torch.float16, device=self.device)
-            self.pred = torch.empty((batch, self.plan.anchors, 5 + graph.nc), dtype=torch.float32, device=self.device)
+            # two prediction buffers, used alternately: the NMS of call i may still read preds[i % 2] on another
+            # stream while call i+1 runs (B200DetectModel.detect_async); sequential callers never notice
+            self.preds = [torch.empty((batch, self.plan.anchors, 5 + graph.nc), dtype=torch.float32, device=self.device)
+                          for _ in range(2)]
+            self.pred = self.preds[0]
+            self._flip = 0
+            self.last_index = 0
             self._views: Dict[Tuple[int, int, int], NHWC] = {}
             self._weights: Dict[str, Tuple[torch.Tensor, torch.Tensor]] = {}
             self._x: Optional[torch.Tensor] = None
             self._calls: List[Callable[[], None]] = [self._bind(op, folded) for op in self.plan.ops]
-        self._graph: Optional[torch.cuda.CUDAGraph] = None
-        self._graph_x_ptr = None
+        self._graphs: List[Optional[torch.cuda.CUDAGraph]] = [None, None]  # one per prediction buffer
         self.launches_per_forward = len(self._calls)
         self._schedule = self._make_schedule() if self.n_streams > 1 else None
         self._side_streams = [torch.cuda.Stream(device=self.device) for _ in range(self.n_streams - 1)]
@@ -337,7 +342,7 @@ class Engine:
             self._weights[op.name] = (w, b)
             return lambda: ops.conv3x3s2(reads[0], w, b, op.act, writes[0])
         if op.kind == "dwconv":
-            if reads[0].c % 8 == 0 and writes[0].ld % 16 == 0 and os.environ.get("MAFB200_DW_TC", "1") != "0":
+            if reads[0].c % 8 == 0 and writes[0].ld % 16 == 0 and os.environ.get("MAFB200_DW_TC", "0") != "0":
                 w, b = ops.pack_dw_tc(*folded[op.weight], device=dev)  # tensor-core (Toeplitz HMMA) kernel
                 self._weights[op.name] = (w, b)
                 return lambda: ops.dwconv_tc(reads[0], w, b, op.k, op.act, writes[0])
@@ -438,6 +443,10 @@ class Engine:
 
     def run_eager(self, x: torch.Tensor) -> torch.Tensor:
         self._x = self._check_input(x)
+        k = self._flip
+        self._flip ^= 1
+        self.last_index = k
+        self.pred = self.preds[k]
         for call in self._calls:
             call()
         return self.pred
@@ -448,10 +457,14 @@ class Engine:
             return self.run_eager(x)
         x = self._check_input(x)
         self._x = x
+        k = self._flip
+        self._flip ^= 1
+        self.last_index = k
+        self.pred = self.preds[k]  # the decode launch reads self.pred when it is issued / captured
         # The stem kernel reads the caller's tensor (its address changes per call), so it is launched
         # eagerly; everything behind it only touches engine-owned memory and is replayed as one graph.
         self._calls[0]()
-        if self._graph is None:
+        if self._graphs[k] is None:
             for call in self._calls[1:]:  # warm-up outside capture (sets func attributes, loads modules)
                 call()
             torch.cuda.synchronize(self.device)
@@ -462,9 +475,9 @@ class Engine:
                 else:
                     for call in self._calls[1:]:
                         call()
-            self._graph = g
+            self._graphs[k] = g
             self._calls[0]()
-        self._graph.replay()
+        self._graphs[k].replay()
         return self.pred
 
     __call__ = forward

@@ -138,6 +138,47 @@ class B200DetectModel(torch.nn.Module):
         return [pred, feats]
 
 
+    @torch.no_grad()
+    def detect_async(self, x: torch.Tensor, conf_thres: float = 0.25, iou_thres: float = 0.45,
+                     classes: Optional[Sequence[int]] = None, agnostic: bool = False, multi_label: bool = False,
+                     max_det: int = 300, max_nms: int = _MAX_NMS, after_nms=None):
+        """Serving form of `pred = model(x)[0]; non_max_suppression(pred, ...)` (evaler.py:168,178) that keeps
+        two batches in flight: forward + decode run on the caller's stream, the NMS of THIS batch runs on a
+        side stream and overlaps the forward of the NEXT call (the 32 NMS CTAs leave most SMs idle).
+        Returns (det [B,max_det,6], count [B], done_event): wait on `done_event` (or synchronize) before reading;
+        the buffers are reused two calls later.  `after_nms(det, count)` — optional — is invoked on the NMS
+        stream right after the NMS (e.g. to enqueue a D2H copy or the detection all-gather)."""
+        if not x.is_cuda:
+            raise RuntimeError("B200DetectModel needs a CUDA input tensor: there is no CPU fallback on this path")
+        eng = self.engine_for(x)
+        with torch.cuda.device(x.device):
+            st = getattr(eng, "_async_state", None)
+            if st is None or st["max_det"] != max_det:
+                st = {"max_det": max_det, "stream": torch.cuda.Stream(device=x.device),
+                      "det": [torch.empty((eng.batch, max_det, 6), dtype=torch.float32, device=x.device) for _ in range(2)],
+                      "cnt": [torch.empty((eng.batch,), dtype=torch.int32, device=x.device) for _ in range(2)],
+                      "done": [torch.cuda.Event() for _ in range(2)], "used": [False, False]}
+                eng._async_state = st
+            main = torch.cuda.current_stream(x.device)
+            k = eng._flip  # the prediction buffer this call will write
+            if st["used"][k]:
+                main.wait_event(st["done"][k])  # its previous reader (the NMS two calls ago) must have finished
+            pred = eng.forward(x)
+            fwd_done = torch.cuda.Event()
+            fwd_done.record(main)
+            side = st["stream"]
+            side.wait_event(fwd_done)
+            with torch.cuda.stream(side):
+                det, cnt = non_max_suppression_padded(pred, conf_thres, iou_thres, classes, agnostic, multi_label,
+                                                      max_det, max_nms, det=st["det"][k], count=st["cnt"][k])
+                res = after_nms(det, cnt) if after_nms is not None else None
+                st["done"][k].record(side)
+            st["used"][k] = True
+        if after_nms is not None:
+            return det, cnt, st["done"][k], res
+        return det, cnt, st["done"][k]
+
+
 def from_state_dict(state_dict, variant_or_yaml="n", nc: int = 80, bn_eps: float = 1e-3, **kw) -> B200DetectModel:
     """Builds the drop-in from reference weights (train- or deploy-form `state_dict`)."""
     from .fold import fold_state_dict

@@ -1,0 +1,7 @@
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q --no-header -p no:cacheprovider -k "nms or model or smoke" > gpurun_out/t24.log 2>&1; echo "exit $?" >> gpurun_out/t24.log
+tail -5 gpurun_out/t24.log
+timeout 400 python bench.py --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/bench24.json 2> gpurun_out/bench24.err; echo "exit $?" >> gpurun_out/bench24.err
+python - <<PY
+import json; d=json.load(open("gpurun_out/bench24.json")); print(d["value"], d["ms_per_step"], d["breakdown_ms"], "e2e", d["e2e"]["value"])
+PY
