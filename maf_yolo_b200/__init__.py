@@ -7,7 +7,7 @@ Public API (mirrors the reference's names):
     convert_blocks(model)             per-block drop-ins inside the reference's own Model.forward loop (blocks.py)
 """
 from .blocks import B200Block, B200Detect, convert_blocks  # noqa: F401
-from .nn import B200DetectModel, convert, from_state_dict, non_max_suppression, non_max_suppression_padded  # noqa: F401
+from .nn import B200DetectModel, DetectTicket, convert, from_state_dict, non_max_suppression, non_max_suppression_padded  # noqa: F401
 
-__all__ = ["B200DetectModel", "convert", "from_state_dict", "non_max_suppression", "non_max_suppression_padded",
+__all__ = ["B200DetectModel", "DetectTicket", "convert", "from_state_dict", "non_max_suppression", "non_max_suppression_padded",
            "B200Block", "B200Detect", "convert_blocks"]

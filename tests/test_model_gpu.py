@@ -156,28 +156,31 @@ def test_end_to_end_detections(cuda_device):
         assert 0 < d.shape[0] <= 300 and (np.diff(d[:, 4]) <= 0).all() and (d[:, 2] > d[:, 0]).all()
 
 
-def test_detect_async_equals_sequential(cuda_device):
+@pytest.mark.parametrize("in_flight", [1, 2, 3])
+def test_detect_async_equals_sequential(cuda_device, in_flight):
     """model.detect_async (NMS on a side stream, double-buffered predictions, two batches in flight) returns
     bit-identical detections to `pred = model(x)[0]; non_max_suppression_padded(pred)` for every batch of a
     stream of different inputs — including while the next forward is already running."""
     import maf_yolo_b200 as mb
 
     g, sd, spec, x = _setup("n", 2)
-    model = mb.from_state_dict(sd, "n")
+    model = mb.from_state_dict(sd, "n", in_flight=in_flight)
     xs = [x.to(cuda_device), x.flip(3).contiguous().to(cuda_device), (x * 0.5).to(cuda_device), x.flip(2).contiguous().to(cuda_device)]
+    xs = xs + [t.flip(0).contiguous() for t in xs]
     want = []
     for xi in xs:
         d, c = mb.non_max_suppression_padded(model(xi)[0], 0.03, 0.65, multi_label=True)
         torch.cuda.synchronize()
         want.append((d.clone(), c.clone()))
     got = []
-    for xi in xs:  # no synchronisation between calls: call i+1's forward overlaps call i's NMS
-        d, c, done = model.detect_async(xi, 0.03, 0.65, multi_label=True)
-        got.append((d, c, done))
-        if len(got) >= 2:  # results must be consumed before their buffers are reused two calls later
+    for xi in xs:  # no synchronisation between calls: up to in_flight forwards + their NMS overlap
+        t = model.detect_async(xi, 0.03, 0.65, multi_label=True)
+        got.append((t.det, t.count, t.done))
+        if len(got) >= 2:  # results must be consumed before their buffers are reused 2 * in_flight calls later
             d0, c0, e0 = got[-2]
-            e0.synchronize()
-            got[-2] = (d0.clone(), c0.clone(), e0)
+            if not isinstance(e0, bool):
+                e0.synchronize()
+                got[-2] = (d0.clone(), c0.clone(), True)
     got[-1][2].synchronize()
     for i, ((wd, wc), (gd, gc, _)) in enumerate(zip(want, got)):
         assert torch.equal(wc, gc), f"batch {i}: counts differ"
