@@ -14,6 +14,8 @@
  *                            branch + generate_anchors + dist2bbox         yolov6/assigners/anchor_generator.py:11-25,
  *                                                                          yolov6/utils/general.py:29-40
  *   mafb200_nms              non_max_suppression + torchvision.ops.nms     yolov6/utils/nms.py:31-105
+ *   mafb200_scale_detections Evaler.scale_coords / box_convert /           yolov6/core/evaler.py:382-434,
+ *                            Inferer.rescale                               yolov6/core/inferer.py:181-195
  *
  * Conventions
  *   - plain pointers and sizes only; no torch / C++ types cross this boundary.
@@ -158,6 +160,18 @@ MAFB200_API int32_t mafb200_nms(const float* pred, int32_t batch, int32_t anchor
                     double iou_thres, int32_t multi_label, int32_t agnostic, const uint8_t* class_filter,
                     int32_t max_det, int32_t max_nms, float* det, int32_t* count, void* workspace,
                     size_t workspace_bytes, void* stream);
+
+/* ---- post-NMS rescaling (the step right after the hot path) --------------------------------------
+ * For every valid row of det [B, max_det, 6] (row i < count[b]): (x - pad_x) / gain_x, (y - pad_y) / gain_y,
+ * clamped to [0, w0] x [0, h0] — Evaler.scale_coords (yolov6/core/evaler.py:391-418) and Inferer.rescale
+ * (yolov6/core/inferer.py:181-195).  params fp32 [B][6] = gain_x, gain_y, pad_x, pad_y, w0, h0 (device).
+ * mode 0: out = (x1,y1,x2,y2,score,cls); mode 1: out = (x_tl,y_tl,w,h,score,cls) as box_convert + the
+ * top-left shift of evaler.py:382-390,428-429.  out_cat (optional) = category_ids[int(cls)] (evaler.py:433;
+ * category_ids: device int32 [nc] or NULL = the class index), -1 for padding rows; padding rows of out are 0.
+ * recip_mul = 0 reproduces torch-CPU division bit for bit, 1 torch-CUDA's x * (1 / gain).  out may alias det. */
+MAFB200_API int32_t mafb200_scale_detections(const float* det, const int32_t* count, int32_t batch, int32_t max_det,
+                                 const float* params, const int32_t* category_ids, int32_t nc, int32_t mode,
+                                 int32_t recip_mul, float* out, int32_t* out_cat, void* stream);
 
 /* number of kernel launches issued by this library in the calling process (bench.py gpu_launches) */
 MAFB200_API int64_t mafb200_launch_count(void);
