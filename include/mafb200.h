@@ -13,6 +13,8 @@
  *   mafb200_head_decode      Head_DepthUni sigmoid + Detect_yaml eval      common.py:1332, yolov6/models/yolo.py:355-396,
  *                            branch + generate_anchors + dist2bbox         yolov6/assigners/anchor_generator.py:11-25,
  *                                                                          yolov6/utils/general.py:29-40
+ *   mafb200_letterbox_u8     letterbox + Inferer.precess_image             yolov6/data/data_augment.py:53-83,
+ *                                                                          yolov6/core/inferer.py:168-178
  *   mafb200_nms              non_max_suppression + torchvision.ops.nms     yolov6/utils/nms.py:31-105
  *   mafb200_scale_detections Evaler.scale_coords / box_convert /           yolov6/core/evaler.py:382-434,
  *                            Inferer.rescale                               yolov6/core/inferer.py:181-195
@@ -160,6 +162,17 @@ MAFB200_API int32_t mafb200_nms(const float* pred, int32_t batch, int32_t anchor
                     double iou_thres, int32_t multi_label, int32_t agnostic, const uint8_t* class_filter,
                     int32_t max_det, int32_t max_nms, float* det, int32_t* count, void* workspace,
                     size_t workspace_bytes, void* stream);
+
+/* ---- image pre-processing (the step right before the hot path) ------------------------------------
+ * letterbox (yolov6/data/data_augment.py:53-83: cv2.resize INTER_LINEAR to new_w x new_h — reproduced bit for
+ * bit — then a constant border of `fill`) + HWC -> CHW and BGR -> RGB (Inferer.precess_image,
+ * yolov6/core/inferer.py:168-178) of ONE uint8 image, written into the uint8 [3, dst_h, dst_w] slot the stem
+ * kernel reads (mafb200_stem_conv3x3s2 with MAF_U8 folds the /255).  Geometry comes from the host exactly as
+ * letterbox() computes it: resized size (new_h, new_w; equal to the source size = no resize) and the
+ * top / left border.  src: device memory, HWC, src_pitch_bytes per row. */
+MAFB200_API int32_t mafb200_letterbox_u8(const void* src_hwc, int32_t src_h, int32_t src_w, int32_t src_pitch_bytes,
+                             void* dst_chw, int32_t dst_h, int32_t dst_w, int32_t new_h, int32_t new_w,
+                             int32_t top, int32_t left, int32_t fill, int32_t swap_rb, void* stream);
 
 /* ---- post-NMS rescaling (the step right after the hot path) --------------------------------------
  * For every valid row of det [B, max_det, 6] (row i < count[b]): (x - pad_x) / gain_x, (y - pad_y) / gain_y,
