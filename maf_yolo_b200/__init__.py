@@ -4,10 +4,13 @@ Public API (mirrors the reference's names):
     convert(model)                    reference `Model`  -> B200DetectModel        (nn.py)
     from_state_dict(sd, variant)      reference weights  -> B200DetectModel
     non_max_suppression(...)          == yolov6/utils/nms.py:31
+    from_checkpoint(path)             reference `.pt` (pickled model) -> B200DetectModel, no reference code needed (checkpoint.py)
+    preprocess.* / postprocess.*      letterbox / precess_image and scale_coords / convert_to_coco_format on the device
     convert_blocks(model)             per-block drop-ins inside the reference's own Model.forward loop (blocks.py)
 """
+from .checkpoint import from_checkpoint, load_checkpoint  # noqa: F401
 from .blocks import B200Block, B200Detect, convert_blocks  # noqa: F401
 from .nn import B200DetectModel, DetectTicket, convert, from_state_dict, non_max_suppression, non_max_suppression_padded  # noqa: F401
 
 __all__ = ["B200DetectModel", "DetectTicket", "convert", "from_state_dict", "non_max_suppression", "non_max_suppression_padded",
-           "B200Block", "B200Detect", "convert_blocks"]
+           "B200Block", "B200Detect", "convert_blocks", "from_checkpoint", "load_checkpoint"]

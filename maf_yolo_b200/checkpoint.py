@@ -1,0 +1,132 @@
+"""Checkpoint ingestion: the reference's pickled `.pt` files without the reference's classes.
+
+`yolov6/utils/checkpoint.py:83-93` (`load_checkpoint`) does `torch.load(weights)` and takes `ckpt['ema']` or
+`ckpt['model']` — a pickled *nn.Module object*, so unpickling normally needs yolov6.models.yolo.Model,
+yolov6.layers.common.* ... importable under exactly those paths.  Here a restricted unpickler resolves only
+torch / numpy / builtins classes; every other class (the reference's modules, its Config objects, ...) becomes
+an inert stub that just holds its pickled `__dict__`.  The module tree is then walked (`_modules`,
+`_parameters`, `_buffers`) into an ordinary `state_dict`, and `model.yaml` (yolo.py:145), `names` and `nc` are
+read off the stub — everything `from_state_dict` / `convert` need.  No code from the checkpoint is executed.
+
+    model = maf_yolo_b200.from_checkpoint("MAFYOLOn.pt")          # -> B200DetectModel
+    sd, meta = maf_yolo_b200.checkpoint.load_checkpoint("x.pt")   # state_dict (fp32) + {"yaml", "names", "nc", "which"}
+"""
+from __future__ import annotations
+
+import pickle
+import types
+from collections import OrderedDict
+from typing import Dict, Tuple
+
+import torch
+
+_SAFE_PREFIXES = ("torch", "collections", "numpy", "builtins", "__builtin__", "_codecs", "copyreg", "pathlib", "argparse")
+_stub_cache: Dict[Tuple[str, str], type] = {}
+
+
+class _Stub:
+    """Stands in for any class of the checkpoint that is not torch/numpy/builtin: keeps the pickled state only."""
+
+    def __init__(self, *args, **kwargs):
+        self._stub_args = (args, kwargs)
+
+    def __setstate__(self, state):
+        if isinstance(state, dict):
+            self.__dict__.update(state)
+        elif isinstance(state, tuple) and len(state) == 2 and isinstance(state[0], (dict, type(None))):
+            for part in state:
+                if isinstance(part, dict):
+                    self.__dict__.update(part)
+        else:
+            self.__dict__["_stub_state"] = state
+
+    def __call__(self, *args, **kwargs):  # e.g. a pickled functools.partial-like reduce on a stubbed callable
+        return _Stub(*args, **kwargs)
+
+
+def _stub_class(module: str, name: str) -> type:
+    key = (module, name)
+    cls = _stub_cache.get(key)
+    if cls is None:
+        cls = type(name, (_Stub,), {"__module__": module})
+        _stub_cache[key] = cls
+    return cls
+
+
+class _Unpickler(pickle.Unpickler):
+    def find_class(self, module, name):
+        if module.split(".")[0] in _SAFE_PREFIXES or module in _SAFE_PREFIXES:
+            return super().find_class(module, name)
+        return _stub_class(module, name)
+
+
+# the object torch.load(pickle_module=...) expects: a module-like namespace with Unpickler / load
+_pickle_module = types.ModuleType("maf_yolo_b200._restricted_pickle")
+_pickle_module.Unpickler = _Unpickler
+_pickle_module.load = lambda f, **kw: _Unpickler(f, **kw).load()
+_pickle_module.__dict__.update({k: getattr(pickle, k) for k in ("HIGHEST_PROTOCOL", "DEFAULT_PROTOCOL", "PickleError",
+                                                                 "UnpicklingError", "dump", "dumps", "Pickler")})
+
+
+def _is_module_like(obj) -> bool:
+    d = getattr(obj, "__dict__", None)
+    return isinstance(d, dict) and "_modules" in d and "_parameters" in d
+
+
+def module_state_dict(mod, prefix: str = "", out=None) -> "OrderedDict[str, torch.Tensor]":
+    """state_dict() of a (stubbed or real) module tree, same keys and order as nn.Module.state_dict."""
+    out = OrderedDict() if out is None else out
+    d = mod.__dict__
+    for k, p in (d.get("_parameters") or {}).items():
+        if p is not None:
+            out[prefix + k] = p.detach() if isinstance(p, torch.Tensor) else p
+    skip = d.get("_non_persistent_buffers_set") or set()
+    for k, b in (d.get("_buffers") or {}).items():
+        if b is not None and k not in skip:
+            out[prefix + k] = b
+    for k, m in (d.get("_modules") or {}).items():
+        if m is not None:
+            module_state_dict(m, prefix + k + ".", out)
+    return out
+
+
+def load_checkpoint(weights, map_location="cpu"):
+    """Same selection rule as the reference (`ckpt['ema'] if ckpt.get('ema') else ckpt['model']`, then `.float()`).
+    Also accepts a bare pickled module, or a plain (train- or deploy-form) state_dict file.
+    Returns (state_dict, meta) with meta = {"yaml": model.yaml rows | None, "names", "nc", "which"}."""
+    ckpt = torch.load(weights, map_location=map_location, pickle_module=_pickle_module, weights_only=False)
+    which, model = "state_dict", None
+    if isinstance(ckpt, dict) and ("model" in ckpt or "ema" in ckpt):
+        which = "ema" if ckpt.get("ema") is not None and ckpt.get("ema") is not False else "model"
+        model = ckpt[which]
+    elif _is_module_like(ckpt):
+        which, model = "module", ckpt
+    if model is not None and _is_module_like(model):
+        sd = module_state_dict(model)
+        meta = {"yaml": getattr(model, "yaml", None), "names": getattr(model, "names", None), "which": which}
+        det = (model.__dict__.get("_modules") or {}).get("detect")
+        meta["nc"] = getattr(det, "nc", None) if det is not None else None
+    else:
+        sd = model if model is not None else ckpt
+        if isinstance(sd, dict) and "state_dict" in sd:
+            sd = sd["state_dict"]
+        if not (isinstance(sd, dict) and sd and all(isinstance(v, torch.Tensor) for v in sd.values())):
+            raise TypeError(f"{weights}: neither a pickled model checkpoint nor a state_dict")
+        meta = {"yaml": None, "names": None, "nc": None, "which": which}
+    sd = OrderedDict((k, v.float() if v.is_floating_point() else v) for k, v in sd.items())
+    return sd, meta
+
+
+def from_checkpoint(weights, variant_or_yaml=None, nc=None, bn_eps: float = 1e-3, **kw):
+    """Reference `.pt` -> B200DetectModel.  The topology comes from the checkpoint's own `model.yaml` unless
+    `variant_or_yaml` ('n' | 's' | 'm' | yaml path / rows) is given (needed for bare state_dict files)."""
+    from .nn import from_state_dict
+
+    sd, meta = load_checkpoint(weights)
+    topo = variant_or_yaml if variant_or_yaml is not None else meta["yaml"]
+    if topo is None:
+        raise ValueError("the file holds a bare state_dict: pass variant_or_yaml ('n' | 's' | 'm' | yaml)")
+    ncls = nc if nc is not None else (meta["nc"] or 80)
+    if meta.get("names") is not None and "names" not in kw:
+        kw["names"] = meta["names"]
+    return from_state_dict(sd, topo, ncls, bn_eps, **kw)

@@ -1,0 +1,96 @@
+"""Checkpoint ingestion (maf_yolo_b200/checkpoint.py): pickled-model `.pt` files load into a plain state_dict
+without the classes they were pickled from (yolov6/utils/checkpoint.py:83-93 needs them importable)."""
+import os
+import sys
+import types
+
+import pytest
+import torch
+import torch.nn as nn
+
+from maf_yolo_b200 import checkpoint as ck
+from oracle import ref_loader
+
+
+def _fake_reference_package():
+    """A throw-away package with the reference's module paths, used only to CREATE a checkpoint."""
+    pkg = types.ModuleType("fakeyolo"); sub = types.ModuleType("fakeyolo.models")
+    class Block(nn.Module):
+        def __init__(self, c):
+            super().__init__()
+            self.conv = nn.Conv2d(c, c, 3, bias=False)
+            self.bn = nn.BatchNorm2d(c)
+            self.register_buffer("scratch", torch.ones(2), persistent=False)
+    class Model(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.backbone = nn.Sequential(Block(4), Block(4))
+            self.detect = Block(4)
+            self.detect.nc = 7
+            self.yaml = {"backbone": [[-1, 1, "Block", [4]]], "nc": 7}
+            self.names = ["a", "b"]
+    Block.__module__ = Model.__module__ = "fakeyolo.models"
+    Block.__qualname__, Model.__qualname__ = "Block", "Model"
+    sub.Block, sub.Model = Block, Model
+    sys.modules["fakeyolo"], sys.modules["fakeyolo.models"] = pkg, sub
+    return Model
+
+
+def test_loads_pickled_model_without_its_classes(tmp_path):
+    Model = _fake_reference_package()
+    m = Model().half()
+    want = {k: v.float() for k, v in m.state_dict().items()}
+    path = tmp_path / "ckpt.pt"
+    torch.save({"model": m, "ema": None, "epoch": 3, "optimizer": None}, path)
+    for name in ("fakeyolo", "fakeyolo.models"):
+        del sys.modules[name]  # the classes are gone, as on a machine without the reference repository
+    with pytest.raises(Exception):
+        torch.load(path, weights_only=False)
+    sd, meta = ck.load_checkpoint(path)
+    assert list(sd) == list(want) and all(torch.equal(sd[k], want[k]) for k in want)
+    assert all(v.dtype == torch.float32 for v in sd.values() if v.is_floating_point())
+    assert "backbone.0.scratch" not in sd  # non-persistent buffers stay out, as in nn.Module.state_dict()
+    assert meta["which"] == "model" and meta["yaml"]["nc"] == 7 and meta["names"] == ["a", "b"] and meta["nc"] == 7
+
+
+def test_prefers_ema_and_accepts_state_dict_files(tmp_path):
+    Model = _fake_reference_package()
+    a, b = Model(), Model()
+    torch.save({"model": a, "ema": b}, tmp_path / "e.pt")
+    torch.save(a.state_dict(), tmp_path / "sd.pt")
+    for name in ("fakeyolo", "fakeyolo.models"):
+        del sys.modules[name]
+    sd, meta = ck.load_checkpoint(tmp_path / "e.pt")
+    assert meta["which"] == "ema" and torch.equal(sd["backbone.0.conv.weight"], b.backbone[0].conv.weight.detach())
+    sd2, meta2 = ck.load_checkpoint(tmp_path / "sd.pt")
+    assert meta2["which"] == "state_dict" and meta2["yaml"] is None
+    assert torch.equal(sd2["detect.bn.running_var"], a.detect.bn.running_var)
+    with pytest.raises(ValueError):
+        ck.from_checkpoint(tmp_path / "sd.pt")  # a bare state_dict needs the variant
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not mounted")
+def test_real_reference_checkpoint_round_trip(tmp_path):
+    """A checkpoint written the way the reference's trainer writes it (yolov6/core/engine.py:195-202: the pickled
+    Model object) folds to the same deploy weights as the live model."""
+    from maf_yolo_b200 import fold, topology
+    from oracle import model as om
+
+    ns = ref_loader.load()
+    torch.manual_seed(0)
+    model = om.build_reference_model(ns, "n") if hasattr(om, "build_reference_model") else None
+    if model is None:
+        class NS(dict):
+            __getattr__ = dict.__getitem__
+        cfg = NS(model=NS(build_type="yaml", yaml_file=os.path.join(ref_loader.REF_ROOT, "configs/yaml/MAF-YOLO-n.yaml"),
+                          head=NS(num_layers=3, anchors=1, strides=[8, 16, 32], use_dfl=True, reg_max=16)))
+        model = ns.Model(cfg, channels=3, num_classes=80, anchors=1).eval()
+    path = tmp_path / "ref.pt"
+    torch.save({"model": model.half(), "ema": None, "epoch": 0}, path)
+    sd, meta = ck.load_checkpoint(path)
+    want = model.float().state_dict()
+    assert list(sd) == list(want) and all(torch.equal(sd[k], want[k]) for k in want)
+    assert meta["nc"] == 80 and meta["yaml"] is not None
+    g = topology.build_graph(meta["yaml"], 80)
+    a, b = fold.fold_state_dict(g, sd), fold.fold_state_dict(g, want)
+    assert a.keys() == b.keys() and all(torch.equal(a[k][0], b[k][0]) and torch.equal(a[k][1], b[k][1]) for k in a)
