@@ -21,6 +21,7 @@
 //     shared-memory bandwidth (fp32 weights: 8 B per lane per tap), so resident warps matter most;
 //   * CB = 64 channels per CTA when C % 64 == 0, else 32 (lanes then split into two 5-column strips
 //     whose smem rows fall in disjoint banks because the strip width 5 is odd).
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -44,11 +45,11 @@ __device__ __forceinline__ void tma_load_tile_4d(void* smem_dst, const CUtensorM
       : "memory");
 }
 
-template <int K, int CB>
+template <int K, int CB, bool kTma>
 __global__ void __launch_bounds__(128)
-    dwconv_kernel(const __grid_constant__ CUtensorMap tm_in, __half* __restrict__ out, int out_ld,
-                  const float* __restrict__ wgt, const float* __restrict__ bias, int H, int W, int C, int act,
-                  int tiles_x) {
+    dwconv_kernel(const __grid_constant__ CUtensorMap tm_in, const __half* __restrict__ in, int in_ld,
+                  __half* __restrict__ out, int out_ld, const float* __restrict__ wgt,
+                  const float* __restrict__ bias, int H, int W, int C, int act, int tiles_x) {
   constexpr int P = K / 2;
   constexpr int TW = kDwTXB + K - 1;        // halo tile width (pixels)
   constexpr int TH = kDwTYB + K - 1;
@@ -70,13 +71,48 @@ __global__ void __launch_bounds__(128)
   const int img = blockIdx.z;
   const int x0 = tile_x * kDwTXB, y0 = tile_y * kDwTYB;
 
-  if (threadIdx.x == 0) {
-    mbar_init(bar, 1);
-    fence_barrier_init();
-    pdl_launch_dependents();
-    pdl_wait();  // the input tile (and, causally through `bar`, every output store) follows the previous kernels
-    mbar_arrive_expect_tx(bar, kTileBytes);
-    tma_load_tile_4d(s_in, &tm_in, bar, c0, x0 - P, y0 - P, img);
+  if (kTma) {
+    if (threadIdx.x == 0) {
+      mbar_init(bar, 1);
+      fence_barrier_init();
+      pdl_launch_dependents();
+      pdl_wait();  // the input tile (and, causally through `bar`, every output store) follows the previous kernels
+      mbar_arrive_expect_tx(bar, kTileBytes);
+      tma_load_tile_4d(s_in, &tm_in, bar, c0, x0 - P, y0 - P, img);
+    }
+  } else {
+    // Halo tile by 16-byte cp.async (zero fill = padding / channel tail).  The TMA box of this tile is one
+    // 64-128-byte ROW per halo pixel and the TMA unit sustains only ~0.25 rows/ns per SM
+    // (tools/ubench/tma_rate.cu), i.e. 1.3 us per 14x24 tile — as long as the tile's FFMA work itself.
+    // Each thread owns fixed (halo x, 8-channel chunk) columns and walks down the rows: addresses advance
+    // by constants, ~3 instructions per 16 bytes.
+    if (threadIdx.x == 0) pdl_launch_dependents();
+    pdl_wait();
+    constexpr int CH = CB / 8;          // 16-byte chunks per pixel
+    constexpr int COMBOS = TW * CH;     // chunks per halo row
+    const uint32_t s_in_a = smem_u32(s_in);
+#pragma unroll
+    for (int cc = 0; cc < (COMBOS + 127) / 128; ++cc) {
+      const int combo = threadIdx.x + cc * 128;
+      if (combo < COMBOS) {
+        const int hx = combo / CH, j = combo - hx * CH;
+        const int gx = x0 - P + hx;
+        const bool ok_x = gx >= 0 && gx < W && c0 + 8 * j < C;
+        const __half* src = in + ((static_cast<size_t>(img) * H + (y0 - P)) * W + gx) * in_ld + c0 + 8 * j;
+        const size_t row_step = static_cast<size_t>(W) * in_ld;
+        const uint32_t dst = s_in_a + (hx * CB + 8 * j) * 2;
+#pragma unroll
+        for (int hy = 0; hy < TH; ++hy) {
+          const int gy = y0 - P + hy;
+          const bool ok = ok_x && gy >= 0 && gy < H;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + hy * (TW * CB * 2)),
+                       "l"(ok ? src : in), "r"(ok ? 16 : 0)
+                       : "memory");
+          src += row_step;
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
   constexpr bool kRegW = K <= 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -104,7 +140,12 @@ __global__ void __launch_bounds__(128)
     __syncthreads();
     bv = *reinterpret_cast<const float2*>(s_b + 2 * pair);
   }
-  mbar_wait(bar, 0);
+  if (kTma) {
+    mbar_wait(bar, 0);
+  } else {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+  }
   const float* wbase = s_w + 2 * pair;
 
 #pragma unroll 1
@@ -163,7 +204,15 @@ __global__ void __launch_bounds__(128)
   }
 }
 
-template <int K, int CB>
+static bool dw_use_tma() {
+  static const bool on = [] {
+    const char* v = getenv("MAFB200_DW_TMA");  // default on: the cp.async path measured 5 % slower (722 vs 688 us / forward)
+    return !(v && v[0] == '0');
+  }();
+  return on;
+}
+
+template <int K, int CB, bool kTma>
 static int32_t launch_dw(const maf_tensor* src, const float* w, const float* bias, int act, const maf_tensor* dst,
                          cudaStream_t st) {
   constexpr int TW = kDwTXB + K - 1, TH = kDwTYB + K - 1;
@@ -186,14 +235,14 @@ static int32_t launch_dw(const maf_tensor* src, const float* w, const float* bia
   static bool configured = false;
   if (!configured) {
     cudaError_t e =
-        cudaFuncSetAttribute(dwconv_kernel<K, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaFuncSetAttribute(dwconv_kernel<K, CB, kTma>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     if (e != cudaSuccess) return fail(MAF_E_CUDA, "dwconv: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
   }
   const int tiles_x = ceil_div(src->w, kDwTXB), tiles_y = ceil_div(src->h, kDwTYB);
   dim3 grid(tiles_x * tiles_y, ceil_div(src->c, CB), src->n);
-  launch_pdl(dwconv_kernel<K, CB>, grid, dim3(128), smem, st, tm, static_cast<__half*>(dst->ptr), dst->c_stride, w, bias,
-             src->h, src->w, src->c, act, tiles_x);
+  launch_pdl(dwconv_kernel<K, CB, kTma>, grid, dim3(128), smem, st, tm, static_cast<const __half*>(src->ptr),
+             src->c_stride, static_cast<__half*>(dst->ptr), dst->c_stride, w, bias, src->h, src->w, src->c, act, tiles_x);
   return check_launch("dwconv kernel launch");
 }
 
@@ -202,8 +251,12 @@ static int32_t dispatch_dw(const maf_tensor* src, const float* w, const float* b
                            cudaStream_t st) {
   // 64-channel CTAs when they tile C exactly and the halo tile stays small enough for >= 3 CTAs/SM,
   // else 32-channel CTAs (<= 25 % idle lanes in the worst case, C = 72).
-  if (src->c % 64 == 0 && K <= 5) return launch_dw<K, 64>(src, w, bias, act, dst, st);
-  return launch_dw<K, 32>(src, w, bias, act, dst, st);
+  if (dw_use_tma()) {
+    if (src->c % 64 == 0 && K <= 5) return launch_dw<K, 64, true>(src, w, bias, act, dst, st);
+    return launch_dw<K, 32, true>(src, w, bias, act, dst, st);
+  }
+  if (src->c % 64 == 0 && K <= 5) return launch_dw<K, 64, false>(src, w, bias, act, dst, st);
+  return launch_dw<K, 32, false>(src, w, bias, act, dst, st);
 }
 
 }  // namespace mafb200

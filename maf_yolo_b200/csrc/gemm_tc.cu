@@ -451,7 +451,11 @@ static int32_t launch_gemm(GemmParams& p, int n_tiles, int total_kb, cudaStream_
   // layers was measured slower: those layers are bound by the im2col TMA's per-pixel-row request rate —
   // ~0.35 us per 128-row im2col box regardless of Cin — not by weight re-streaming or ring depth.)
   const int panel = total_kb * b_bytes;
-  const int ctas_per_sm = 2;
+  static const int ctas_per_sm = [] {
+    const char* v = getenv("MAFB200_GEMM_CTAS_PER_SM");  // experiment knob: 1 leaves room for a co-resident kernel
+    const int n = v ? atoi(v) : 2;
+    return n >= 1 && n <= 2 ? n : 2;
+  }();
   const int budget = 104 * 1024;
   int stages;
   p.w_resident = (panel + 3 * kABytes <= budget) ? 1 : 0;

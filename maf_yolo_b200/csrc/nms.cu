@@ -216,29 +216,87 @@ __global__ void __launch_bounds__(1024) nms_select_kernel(const NmsParams p) {
   }
 
   // ---- sort -----------------------------------------------------------------------------------
+  // n <= 8192: bitonic sort in shared memory.  Larger: greedy NMS only ever needs the best-scoring prefix of
+  // the list (it stops at max_det survivors), so first radix-SELECT the best <= 8192 keys (two 11-bit
+  // histogram levels over the score bits; bins in key order, so the selected set is exactly a prefix of the
+  // sorted list), sort and process those in shared memory, and fall back to the full global-memory sort only
+  // if they run out before max_det boxes are kept.  Results are identical either way.
   unsigned long long* gkeys = p.keys + static_cast<size_t>(b) * p.cap_pow2;
+  const int n_eff = static_cast<int>(n < p.max_nms ? n : p.max_nms);
+  const float* pred_b = p.pred + static_cast<size_t>(b) * p.A * no;
+  __shared__ int s_sel[4];  // [0] level-1 boundary bin, [1] level-2 boundary bin, [2] selected count, [3] fill cursor
+
+  for (int attempt = (n > kSortSmemKeys ? 0 : 1); attempt < 2; ++attempt) {
   unsigned long long* keys;
-  int P = 1;
-  while (P < n) P <<= 1;
-  if (P <= kSortSmemKeys) {
+  int n_run = n_eff;
+  if (n <= kSortSmemKeys) {
+    int P = 1;
+    while (P < n) P <<= 1;
     for (int i = threadIdx.x; i < P; i += blockDim.x) s_keys[i] = i < n ? gkeys[i] : ~0ull;
     keys = s_keys;
+    bitonic_sort(keys, P);
+  } else if (attempt == 0) {
+    int* hist = reinterpret_cast<int*>(c_mask);  // 2048 bins (the chunk mask is not in use yet)
+    const int budget = kSortSmemKeys;
+    int prefix = 0;
+    for (int level = 0; level < 2; ++level) {
+      for (int i = threadIdx.x; i < 2048; i += blockDim.x) hist[i] = 0;
+      __syncthreads();
+      const int b1 = level == 1 ? s_sel[0] : 0;
+      for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned hi = static_cast<unsigned>(gkeys[i] >> 32);
+        if (level == 0) atomicAdd(&hist[hi >> 21], 1);
+        else if (static_cast<int>(hi >> 21) == b1) atomicAdd(&hist[(hi >> 10) & 2047], 1);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {  // first bin whose inclusion would exceed the budget (few bins are non-empty)
+        int acc = prefix, bin = 0;
+        for (; bin < 2048; ++bin) {
+          if (acc + hist[bin] > budget) break;
+          acc += hist[bin];
+        }
+        s_sel[level] = bin;
+        s_sel[2] = acc;
+      }
+      __syncthreads();
+      prefix = s_sel[2];
+      if (s_sel[level] >= 2048) break;  // everything fits (cannot happen for n > budget at level 0)
+    }
+    const int m = s_sel[2];
+    if (m < min(n_eff, 2 * p.max_det)) continue;  // too few selectable (massive score ties): full sort
+    const int b1 = s_sel[0], b2 = s_sel[1];
+    if (threadIdx.x == 0) s_sel[3] = 0;
+    __syncthreads();
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+      const unsigned long long key = gkeys[i];
+      const unsigned hi = static_cast<unsigned>(key >> 32);
+      const int k1 = static_cast<int>(hi >> 21), k2 = static_cast<int>((hi >> 10) & 2047);
+      if (k1 < b1 || (k1 == b1 && k2 < b2)) s_keys[atomicAdd(&s_sel[3], 1)] = key;
+    }
+    int P = 1;
+    while (P < m) P <<= 1;
+    __syncthreads();
+    for (int i = m + threadIdx.x; i < P; i += blockDim.x) s_keys[i] = ~0ull;
+    keys = s_keys;
+    bitonic_sort(keys, P);
+    n_run = m < n_eff ? m : n_eff;
   } else {
+    int P = 1;
+    while (P < n) P <<= 1;
     for (long long i = n + threadIdx.x; i < P; i += blockDim.x) gkeys[i] = ~0ull;
     keys = gkeys;
+    bitonic_sort(keys, P);
   }
-  bitonic_sort(keys, P);
-  const int n_eff = static_cast<int>(n < p.max_nms ? n : p.max_nms);
 
+  __syncthreads();
   if (threadIdx.x == 0) {
     s_nk = 0;
     s_done = 0;
   }
   __syncthreads();
 
-  const float* pred_b = p.pred + static_cast<size_t>(b) * p.A * no;
-  for (int base = 0; base < n_eff; base += kChunk) {
-    const int cn = min(kChunk, n_eff - base);
+  for (int base = 0; base < n_run; base += kChunk) {
+    const int cn = min(kChunk, n_run - base);
     const int nk0 = s_nk;
     // (1) materialise the chunk's class-offset boxes
     if (threadIdx.x < cn) {
@@ -366,6 +424,10 @@ __global__ void __launch_bounds__(1024) nms_select_kernel(const NmsParams p) {
     __syncthreads();
     if (s_done) break;
   }
+  // a prefix run that kept max_det boxes, or that covered every candidate, is final
+  if (n_run == n_eff || s_nk >= p.max_det) break;
+  __syncthreads();
+  }  // attempt
   if (threadIdx.x == 0) p.count[b] = s_nk;
 }
 

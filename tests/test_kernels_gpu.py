@@ -309,6 +309,43 @@ def test_nms_bitexact(cuda_device, kw):
         assert np.array_equal(gt.cpu().numpy(), rf), f"image {i}: NMS output differs from the oracle"
 
 
+def test_nms_many_candidates_prefix_select(cuda_device):
+    """> 8192 candidates per image: the radix pre-selection of the best <= 8192 keys must give the same result as
+    sorting everything — when the prefix suffices (max_det reached), when it does not (the best 8192 candidates
+    collapse to a handful of survivors, so the kernel falls back to the full sort), with > max_nms candidates,
+    and with massive exact score ties (selection impossible -> full sort)."""
+    from maf_yolo_b200 import nn as mnn
+    from oracle import nms as onms
+
+    g = torch.Generator().manual_seed(21)
+    A, nc = 8400, 80
+    # (a) 40k candidates, random boxes: the prefix reaches max_det
+    pa = _synthetic_pred(1, A, nc, seed=3)
+    pa[..., 5:] = (pa[..., 5:] * 40).clamp(max=0.999)
+    # (b) the 9000 best-scoring candidates are the same box (one survivor), the rest are spread out
+    pb = _synthetic_pred(1, A, nc, seed=4, dup=False)
+    pb[..., 5:] = pb[..., 5:] * 0.0
+    pb[0, :, 5] = 0.05 + 0.1 * torch.rand(A, generator=g)             # everybody: class 0, low scores
+    pb[0, :6000, :4] = torch.tensor([320.0, 320.0, 100.0, 100.0])     # 6000 anchors share one box ...
+    pb[0, :6000, 5] = 0.5 + 0.4 * torch.rand(6000, generator=g)       # ... with the best class-0 scores
+    pb[0, :6000, 6] = 0.5 + 0.4 * torch.rand(6000, generator=g)       # ... and class-1 scores: 12000 top keys, 2 survivors
+    # (c) every candidate has exactly the same score
+    pc = _synthetic_pred(1, A, nc, seed=5, dup=False)
+    pc[..., 5:] = 0.0
+    pc[0, :, 5:8] = 0.25
+    for name, pred, kws in (("prefix", pa, [dict(conf_thres=0.03, iou_thres=0.65, multi_label=True, max_det=300),
+                                            dict(conf_thres=0.03, iou_thres=0.65, multi_label=True, max_det=300, max_nms=20000),
+                                            dict(conf_thres=0.001, iou_thres=0.3, multi_label=True, max_det=2000)]),
+                            ("fallback", pb, [dict(conf_thres=0.03, iou_thres=0.5, multi_label=True, max_det=300)]),
+                            ("ties", pc, [dict(conf_thres=0.03, iou_thres=0.5, multi_label=True, max_det=300)])):
+        for kw in kws:
+            n_cand = int(((pred[..., 5:] * pred[..., 4:5]) > kw["conf_thres"]).sum())
+            assert n_cand > 8192, (name, n_cand)
+            ref = onms.non_max_suppression(pred.numpy(), **kw)
+            got = mnn.non_max_suppression(pred.to(cuda_device), **kw)
+            assert np.array_equal(got[0].cpu().numpy(), ref[0]), f"{name} {kw}: differs from the oracle ({n_cand} candidates)"
+
+
 def test_nms_obj_and_small(cuda_device):
     """objectness != 1, a batch where one image is empty, nc == 1 (multi_label is forced off)."""
     from maf_yolo_b200 import nn as mnn
