@@ -267,12 +267,16 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_ms = [0.0]
+
     def timed(fn, steps):
         barrier()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
+        t_host = time.perf_counter()
         for i in range(steps):
             fn(i)
+        host_ms[0] = 1e3 * (time.perf_counter() - t_host) / steps  # python enqueue time per step (no sync inside)
         for ev in pending:  # the side-stream work of the last steps is part of the timed region
             torch.cuda.current_stream().wait_event(ev)
         e.record()
@@ -296,6 +300,7 @@ def run_ours(a):
     per_step_launches = eng.launches_per_forward + 2  # + the two NMS kernels
     counted = _lib.launch_count() - launches0  # eager launches only; graph replays are not API calls
     value = B * world * a.steps / (ms / 1e3)
+    host_enqueue_ms = host_ms[0]
 
     # ---- stage breakdown (outside the headline region; same device-event timing) -------------------------
     ms_fwd = timed(lambda i: model(x_f32[i % 2]), a.steps)
@@ -351,6 +356,7 @@ def run_ours(a):
         e2e_step(i)
     ms_e2e = timed(e2e_step, a.steps)
     e2e_value = B * world * a.steps / (ms_e2e / 1e3)
+    host_enqueue_e2e_ms = host_ms[0]
     h2d = host_u8[0].numel()
     d2h_bytes = det_host[0].numel() * 4 + cnt_host[0].numel() * 4
 
@@ -410,6 +416,7 @@ def run_ours(a):
         "eager_api_launches_in_timed_region": int(counted),
         "breakdown_ms": {"forward_decode": round(ms_fwd / a.steps, 4), "nms": round(ms_nms / a.steps, 4)},
         "latency_ms_per_batch": latency,
+        "host_enqueue_ms_per_step": {"value_loop": round(host_enqueue_ms, 4), "e2e_loop": round(host_enqueue_e2e_ms, 4)},
         "clocks": clocks, "roofline": roofline, "whole_step": whole, "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
