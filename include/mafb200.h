@@ -108,6 +108,13 @@ MAFB200_API int32_t mafb200_conv1x1(const maf_tensor* srcs, int32_t n_src, const
 MAFB200_API int32_t mafb200_conv3x3s2(const maf_tensor* src, const void* w_packed, const float* bias, int32_t act,
                           const maf_tensor* dst, void* stream);
 
+/* The same conv for a NARROW input (src->c_stride == 32 fp16: one 128-byte row per pixel PAIR, c <= 32): the map is
+ * read as pixel pairs, so a tile needs 6 im2col boxes instead of 9 (the TMA cost is per box row, not per byte).
+ * src padding channels [c, c_stride) must hold finite values.  w_packed: fp16 [n_tiles*tile_n][6*64], block
+ * o = ky*2 + po; po = 0: kx = 0 at channel offset c_stride; po = 1: kx = 1 at offset 0, kx = 2 at offset c_stride. */
+MAFB200_API int32_t mafb200_conv3x3s2_pair(const maf_tensor* src, const void* w_packed, const float* bias, int32_t act,
+                               const maf_tensor* dst, void* stream);
+
 /* First layer: reads the reference's input tensor directly — NCHW, `x_dtype` in {MAF_F32, MAF_F16
  * (values in [0,1], evaler.py:161-163), MAF_U8 (raw pixels; the /255 is folded in)} — 3 input
  * channels, 3x3 stride 2 pad 1.  w: fp32 [cout][3][3][3] (co, ky, kx, ci); bias fp32 [cout]. */

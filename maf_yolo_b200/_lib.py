@@ -50,6 +50,7 @@ _SIGNATURES = {
     "mafb200_conv1x1": (C.c_int32, [_P(MafTensor), C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, _P(MafTensor),
                                     _P(MafTensor), C.c_void_p]),
     "mafb200_conv3x3s2": (C.c_int32, [_P(MafTensor), C.c_void_p, C.c_void_p, C.c_int32, _P(MafTensor), C.c_void_p]),
+    "mafb200_conv3x3s2_pair": (C.c_int32, [_P(MafTensor), C.c_void_p, C.c_void_p, C.c_int32, _P(MafTensor), C.c_void_p]),
     "mafb200_stem_conv3x3s2": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                            C.c_void_p, C.c_int32, _P(MafTensor), C.c_void_p]),
     "mafb200_dwconv": (C.c_int32, [_P(MafTensor), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, _P(MafTensor),

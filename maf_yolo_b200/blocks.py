@@ -41,7 +41,7 @@ class _BlockEngine(Engine):
         self.use_cuda_graph, self.n_streams = False, 1
         with torch.cuda.device(self.device):
             nbytes = self.plan.assign_offsets(batch, reuse=False)
-            self.arena = torch.empty(max(nbytes // 2, 8), dtype=torch.float16, device=self.device)
+            self.arena = torch.zeros(max(nbytes // 2, 8), dtype=torch.float16, device=self.device)
             self.pred = None
             self._views, self._weights, self._x = {}, {}, None
             self._calls = [self._bind(op, folded) for op in self.plan.ops]

@@ -67,6 +67,7 @@ struct GemmParams {
   int32_t n_tiles;
   int32_t m_stride;    // row-tile step of a CTA = gridDim.x / n_tiles
   int32_t st256;       // 1: every 16-column group of every output row starts 32-B aligned -> 256-bit stores
+  int32_t pair;        // 3x3 s2 over PIXEL PAIRS (Cin <= 32): 6 taps (ky, pair offset) instead of 9 (ky, kx)
   uint32_t idesc;
 };
 
@@ -338,7 +339,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
           q0 = rem - p0 * p.out_w;
         }
         int wk = 0;  // column in the packed weights
-        const int n_outer = kIm2col ? 9 : p.nsrc;
+        const int n_outer = kIm2col ? (p.pair ? 6 : 9) : p.nsrc;
         for (int o = 0; o < n_outer; ++o) {
           const int nblk = kIm2col ? p.kblocks[0] : p.kblocks[o];
           for (int j = 0; j < nblk; ++j, ++kb, wk += kBlockK) {
@@ -348,9 +349,17 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
             uint8_t* sa = s_ring + slot * slot_bytes;
             mbar_arrive_expect_tx(&full_bar[slot], slot_bytes);
             if (kIm2col) {
-              const int ky = o / 3, kx = o - ky * 3;
-              tma_load_im2col_4d(sa, &p.tmA[0], &full_bar[slot], j * kBlockK, 2 * q0 - 1, 2 * p0 - 1, img,
-                                 static_cast<uint16_t>(kx), static_cast<uint16_t>(ky));
+              if (p.pair) {
+                // the tensor is viewed as [N][H][W/2][2*ld]: input columns 2x-1, 2x, 2x+1 of output x are the
+                // second pixel of pair x-1 and both pixels of pair x -> base pair x-1, offsets {0, 1}, x stride 1
+                const int ky = o >> 1, po = o & 1;
+                tma_load_im2col_4d(sa, &p.tmA[0], &full_bar[slot], 0, q0 - 1, 2 * p0 - 1, img,
+                                   static_cast<uint16_t>(po), static_cast<uint16_t>(ky));
+              } else {
+                const int ky = o / 3, kx = o - ky * 3;
+                tma_load_im2col_4d(sa, &p.tmA[0], &full_bar[slot], j * kBlockK, 2 * q0 - 1, 2 * p0 - 1, img,
+                                   static_cast<uint16_t>(kx), static_cast<uint16_t>(ky));
+              }
             } else {
               tma_load_2d(sa, &p.tmA[o], &full_bar[slot], j * kBlockK, m0);
             }
@@ -418,6 +427,29 @@ static int32_t encode_a_map_im2col(CUtensorMap* tm, const maf_tensor* t) {
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(MAF_E_CUDA, "cuTensorMapEncodeIm2col(c=%d w=%d h=%d n=%d) failed: %d", t->c, t->w, t->h, t->n, (int)r);
+  return MAF_OK;
+}
+
+// Pixel-pair view for the 3x3 s2 conv of a narrow map (2 * c_stride <= 64): dims {2*ld, W/2, H, N}, x traversal
+// stride 1 over pairs (kernel extent 2: pair offsets {0,1}, one pair of left padding), y as before.  The im2col TMA
+// costs ~0.4 us per 128-pixel box whatever the channel count, so 6 dense boxes per tile replace 9 sparse ones.
+static int32_t encode_a_map_im2col_pair(CUtensorMap* tm, const maf_tensor* t) {
+  EncodeIm2colFn enc = encode_im2col_fn();
+  if (!enc) return fail(MAF_E_ARCH, "cuTensorMapEncodeIm2col entry point not available");
+  const cuuint64_t pair_ch = static_cast<cuuint64_t>(2) * t->c_stride;
+  cuuint64_t dims[4] = {pair_ch, static_cast<cuuint64_t>(t->w / 2), static_cast<cuuint64_t>(t->h),
+                        static_cast<cuuint64_t>(t->n)};
+  const cuuint64_t px = static_cast<cuuint64_t>(t->c_stride) * 2;
+  cuuint64_t strides[3] = {2 * px, px * t->w, px * t->w * t->h};
+  int lower[2] = {-1, -1};
+  int upper[2] = {-1, -1};  // W: pad_right 0 - (2 - 1); H: pad 1 - (3 - 1)
+  cuuint32_t estr[4] = {1, 1, 2, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, t->ptr, dims, strides, lower, upper,
+                   static_cast<cuuint32_t>(pair_ch), kBlockM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(MAF_E_CUDA, "cuTensorMapEncodeIm2col(pair view, ld=%d w=%d h=%d n=%d) failed: %d", t->c_stride, t->w,
+                t->h, t->n, (int)r);
   return MAF_OK;
 }
 
@@ -602,4 +634,45 @@ extern "C" int32_t mafb200_conv3x3s2(const maf_tensor* src, const void* w_packed
   p.out_w = dst->w;
   p.act = act;
   return launch_gemm<kModeIm2colTma>(p, n_tiles, 9 * p.kblocks[0], static_cast<cudaStream_t>(stream));
+}
+
+// 3x3 s2 pad 1 over pixel pairs: requires src->c_stride == 32 (so a pair is one 128-byte swizzle row), even w,
+// and FINITE values in the padding channels [c, c_stride) of src (they meet zero weights).  Packed weights: fp16
+// [rows][6 * 64], block o = (ky, po): po = 0 -> kx = 0 at channel offset c_stride (second pixel of the left pair);
+// po = 1 -> kx = 1 at offset 0 and kx = 2 at offset c_stride.
+extern "C" int32_t mafb200_conv3x3s2_pair(const maf_tensor* src, const void* w_packed, const float* bias, int32_t act,
+                                          const maf_tensor* dst, void* stream) {
+  if (!valid_f16_view(src) || !valid_f16_view(dst)) return fail(MAF_E_ARG, "conv3x3s2_pair: bad src/dst tensor");
+  if (!aligned_f16_view(src) || !aligned_f16_view(dst)) return fail(MAF_E_ALIGN, "conv3x3s2_pair: alignment");
+  if (!w_packed || !bias) return fail(MAF_E_ARG, "conv3x3s2_pair: null weights/bias");
+  if ((reinterpret_cast<uintptr_t>(w_packed) & 15) != 0) return fail(MAF_E_ALIGN, "conv3x3s2_pair: w_packed alignment");
+  if (2 * src->c_stride != kBlockK)
+    return fail(MAF_E_ARG, "conv3x3s2_pair: needs c_stride == 32 (a pixel pair = one 128-byte row), got %d", src->c_stride);
+  if ((src->h & 1) || (src->w & 1) || dst->h != src->h / 2 || dst->w != src->w / 2 || dst->n != src->n)
+    return fail(MAF_E_ARG, "conv3x3s2_pair: need even h,w and dst = [n,h/2,w/2,cout]");
+  if (act < MAF_ACT_NONE || act > MAF_ACT_SIGMOID) return fail(MAF_E_ARG, "conv3x3s2_pair: bad act %d", act);
+  int32_t rc = require_sm100();
+  if (rc) return rc;
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  rc = encode_a_map_im2col_pair(&p.tmA[0], src);
+  if (rc) return rc;
+  int n_tiles = 0, tile_n = 0;
+  mafb200_gemm_tiling(dst->c, &n_tiles, &tile_n);
+  rc = encode_w_map(&p.tmW, w_packed, 6 * kBlockK, n_tiles * tile_n, tile_n);
+  if (rc) return rc;
+  p.kblocks[0] = 1;
+  p.nsrc = 1;
+  p.pair = 1;
+  p.bias = bias;
+  p.out = static_cast<__half*>(dst->ptr);
+  p.out_ld = dst->c_stride;
+  p.M = dst->n * dst->h * dst->w;
+  p.N = dst->c;
+  p.tile_n = tile_n;
+  p.out_h = dst->h;
+  p.out_w = dst->w;
+  p.act = act;
+  return launch_gemm<kModeIm2colTma>(p, n_tiles, 6, static_cast<cudaStream_t>(stream));
 }

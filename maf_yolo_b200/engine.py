@@ -294,7 +294,7 @@ class Engine:
             reuse_buffers = self.n_streams == 1
         with torch.cuda.device(self.device):
             nbytes = self.plan.assign_offsets(batch, reuse=reuse_buffers)
-            self.arena = torch.empty(nbytes // 2, dtype=torch.float16, device=self.device)
+            self.arena = torch.zeros(nbytes // 2, dtype=torch.float16, device=self.device)  # padding channels finite
             # two prediction buffers, used alternately: the NMS of call i may still read preds[i % 2] on another
             # stream while call i+1 runs (B200DetectModel.detect_async); sequential callers never notice
             self.preds = [torch.empty((batch, self.plan.anchors, 5 + graph.nc), dtype=torch.float32, device=self.device)
@@ -338,6 +338,14 @@ class Engine:
             up = writes[1] if len(writes) > 1 else None
             return lambda: ops.conv1x1(reads, w, b, op.act, writes[0], up)
         if op.kind == "conv3x3s2":
+            src = reads[0]
+            if (2 * src.ld == 64 and src.c_off == 0 and src.w % 2 == 0 and
+                    os.environ.get("MAFB200_CONV3_PAIR", "1") != "0"):
+                # narrow map (N / S layer 1): pixel-pair im2col, 6 boxes per tile instead of 9.  Its zero weights meet
+                # the padding channels of the source buffer, which therefore must be finite: the arena is zero-filled.
+                w, b = ops.pack_conv3x3_pair(*folded[op.weight], ld=src.ld, device=dev)
+                self._weights[op.name] = (w, b)
+                return lambda: ops.conv3x3s2_pair(src, w, b, op.act, writes[0])
             w, b = ops.pack_conv3x3(*folded[op.weight], device=dev)
             self._weights[op.name] = (w, b)
             return lambda: ops.conv3x3s2(reads[0], w, b, op.act, writes[0])

@@ -109,6 +109,23 @@ def pack_conv3x3(weight: torch.Tensor, bias: torch.Tensor, device="cuda"):
     return wp.reshape(rows, 9 * cpad).contiguous().to(device), bp.to(device)
 
 
+def pack_conv3x3_pair(weight: torch.Tensor, bias: torch.Tensor, ld: int, device="cuda"):
+    """weight [Cout, Cin, 3, 3] for mafb200_conv3x3s2_pair on a source with channel stride `ld` (2*ld <= 64):
+    fp16 [rows, 6*64], block o = ky*2 + po over the pixel-pair view (see include/mafb200.h)."""
+    cout, cin, kh, kw = weight.shape
+    assert kh == 3 and kw == 3 and 2 * ld == 64 and cin <= ld
+    n_tiles, tile_n = _lib.gemm_tiling(cout)
+    rows = n_tiles * tile_n
+    wp = torch.zeros((rows, 3, 2, 64), dtype=torch.float16)
+    w16 = weight.to(torch.float16)
+    wp[:cout, :, 0, ld:ld + cin] = w16[:, :, :, 0].permute(0, 2, 1)   # po = 0: second pixel of the left pair <- kx = 0
+    wp[:cout, :, 1, 0:cin] = w16[:, :, :, 1].permute(0, 2, 1)         # po = 1: first pixel  <- kx = 1
+    wp[:cout, :, 1, ld:ld + cin] = w16[:, :, :, 2].permute(0, 2, 1)   #         second pixel <- kx = 2
+    bp = torch.zeros(rows, dtype=torch.float32)
+    bp[:cout] = bias.to(torch.float32)
+    return wp.reshape(rows, 6 * 64).contiguous().to(device), bp.to(device)
+
+
 def pack_stem(weight: torch.Tensor, bias: torch.Tensor, device="cuda"):
     """weight [Cout, 3, 3, 3] (co, ci, ky, kx) -> fp32 [co][ky][kx][ci]."""
     return (weight.permute(0, 2, 3, 1).contiguous().to(torch.float32).to(device),
@@ -149,6 +166,10 @@ def conv1x1(srcs: Sequence[NHWC], w_packed: torch.Tensor, bias: torch.Tensor, ac
 
 def conv3x3s2(src: NHWC, w_packed: torch.Tensor, bias: torch.Tensor, act, dst: NHWC) -> None:
     check(lib().mafb200_conv3x3s2(src.ref(), w_packed.data_ptr(), bias.data_ptr(), _act(act), dst.ref(), _stream()))
+
+
+def conv3x3s2_pair(src: NHWC, w_packed: torch.Tensor, bias: torch.Tensor, act, dst: NHWC) -> None:
+    check(lib().mafb200_conv3x3s2_pair(src.ref(), w_packed.data_ptr(), bias.data_ptr(), _act(act), dst.ref(), _stream()))
 
 
 def stem_conv3x3s2(x_nchw: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, act, dst: NHWC) -> None:

@@ -132,6 +132,28 @@ def test_conv3x3s2(cuda_device, cin, cout, h, w, n, act):
     _close(dst.to_nchw(), ref, f"conv3x3s2 {cin}->{cout} @{h}x{w}")
 
 
+@pytest.mark.parametrize("cin,cout,h,w,n,act", [(24, 48, 40, 64, 2, "relu"), (32, 64, 24, 20, 1, "silu"),
+                                                (24, 48, 320, 320, 1, "relu"), (8, 16, 6, 10, 3, "none")])
+def test_conv3x3s2_pair(cuda_device, cin, cout, h, w, n, act):
+    """Pixel-pair im2col form of the 3x3 s2 conv (narrow inputs, channel stride 32): same result as the 9-tap form;
+    the padding channels of the source hold finite junk that must not leak (they meet zero weights)."""
+    from maf_yolo_b200 import ops
+
+    g = torch.Generator().manual_seed(91 + cin + cout)
+    x = torch.randn(n, cin, h, w, generator=g).half().float()
+    wgt = (torch.randn(cout, cin, 3, 3, generator=g) / (3 * cin ** 0.5)).half().float()
+    bias = torch.randn(cout, generator=g)
+    ref = _act_ref(F.conv2d(x, wgt, bias, stride=2, padding=1), act)
+    src = ops.NHWC.from_nchw(x.to(cuda_device), ld=32)
+    if cin < 32:
+        src.buf[..., cin:] = 123.0  # junk in the padding channels
+    wp, bp = ops.pack_conv3x3_pair(wgt, bias, 32, cuda_device)
+    dst = ops.NHWC.empty(n, h // 2, w // 2, cout, cuda_device)
+    ops.conv3x3s2_pair(src, wp, bp, act, dst)
+    torch.cuda.synchronize()
+    _close(dst.to_nchw(), ref, f"conv3x3s2_pair {cin}->{cout} @{h}x{w}")
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.uint8])
 @pytest.mark.parametrize("cout", [24, 32, 48])
 def test_stem_conv(cuda_device, dtype, cout):
