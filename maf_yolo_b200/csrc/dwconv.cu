@@ -251,8 +251,12 @@ static int32_t dispatch_dw(const maf_tensor* src, const float* w, const float* b
                            cudaStream_t st) {
   // 64-channel CTAs when they tile C exactly and the halo tile stays small enough for >= 3 CTAs/SM,
   // else 32-channel CTAs (<= 25 % idle lanes in the worst case, C = 72).
+  static const int cb64_max_k = [] {
+    const char* v = getenv("MAFB200_DW_CB64_MAXK");  // experiment knob
+    return v ? atoi(v) : 5;
+  }();
   if (dw_use_tma()) {
-    if (src->c % 64 == 0 && K <= 5) return launch_dw<K, 64, true>(src, w, bias, act, dst, st);
+    if (src->c % 64 == 0 && K <= cb64_max_k) return launch_dw<K, 64, true>(src, w, bias, act, dst, st);
     return launch_dw<K, 32, true>(src, w, bias, act, dst, st);
   }
   if (src->c % 64 == 0 && K <= 5) return launch_dw<K, 64, false>(src, w, bias, act, dst, st);
