@@ -188,6 +188,32 @@ def test_detect_async_equals_sequential(cuda_device, in_flight):
     assert int(want[0][1].sum()) > 0
 
 
+def test_full_size_properties(cuda_device):
+    """BASELINE.json configs[1] at full size (MAF-YOLO-N, 32 x 3 x 640 x 640), where the oracle is too slow to run:
+    size-independent properties — images are independent (permuting the batch permutes predictions and detections
+    bit for bit; image i of a batch of 32 equals the same image in a batch of 2), replays are deterministic, and
+    the pipelined serving call equals the sequential reference-shaped calls."""
+    import maf_yolo_b200 as mb
+    from tests._synthetic import synthetic_image
+
+    g, sd, spec, _ = _setup("n", 1)
+    model = mb.from_state_dict(sd, "n", in_flight=2)
+    x = synthetic_image(32, seed=5).to(cuda_device)
+    perm = torch.randperm(32, generator=torch.Generator().manual_seed(1)).to(cuda_device)
+    p1 = model(x)[0].clone()
+    p2 = model(x[perm].contiguous())[0].clone()
+    assert torch.equal(p1[perm], p2), "predictions must not depend on the position in the batch"
+    assert torch.equal(model(x)[0], p1), "replay must be deterministic"
+    small = model(x[:2].contiguous())[0]
+    assert torch.equal(small, p1[:2]), "an image's prediction must not depend on the batch size"
+    d1, c1 = mb.non_max_suppression_padded(p1, 0.03, 0.65, multi_label=True)
+    d1, c1 = d1.clone(), c1.clone()
+    t = model.detect_async(x[perm].contiguous(), 0.03, 0.65, multi_label=True)
+    t.done.synchronize()
+    assert torch.equal(t.count, c1[perm]) and torch.equal(t.det, d1[perm])
+    assert int(c1.min()) > 0 and p1.shape == (32, 8400, 85) and bool((p1[..., 4] == 1).all())
+
+
 def test_api_contract(cuda_device):
     import maf_yolo_b200 as mb
 
