@@ -302,6 +302,12 @@ class Engine:
             self.pred = self.preds[0]
             self._flip = 0
             self.last_index = 0
+            # event of the last side-stream reader (detect_async's NMS) of each prediction buffer: the next
+            # forward that overwrites the buffer waits for it, whichever API the caller mixes
+            self.reader_done: List[Optional[torch.cuda.Event]] = [None, None]
+            # completion of the last forward that detect_async issued on ITS stream: a later forward of this
+            # engine from another stream must not touch the arena before it
+            self.last_async_forward: Optional[torch.cuda.Event] = None
             self._views: Dict[Tuple[int, int, int], NHWC] = {}
             self._weights: Dict[str, Tuple[torch.Tensor, torch.Tensor]] = {}
             self._x: Optional[torch.Tensor] = None
@@ -455,6 +461,12 @@ class Engine:
         self._flip ^= 1
         self.last_index = k
         self.pred = self.preds[k]
+        if self.reader_done[k] is not None:
+            torch.cuda.current_stream(self.device).wait_event(self.reader_done[k])
+            self.reader_done[k] = None
+        if self.last_async_forward is not None:
+            torch.cuda.current_stream(self.device).wait_event(self.last_async_forward)
+            self.last_async_forward = None
         for call in self._calls:
             call()
         return self.pred
@@ -469,6 +481,12 @@ class Engine:
         self._flip ^= 1
         self.last_index = k
         self.pred = self.preds[k]  # the decode launch reads self.pred when it is issued / captured
+        if self.reader_done[k] is not None:
+            torch.cuda.current_stream(self.device).wait_event(self.reader_done[k])
+            self.reader_done[k] = None
+        if self.last_async_forward is not None:
+            torch.cuda.current_stream(self.device).wait_event(self.last_async_forward)
+            self.last_async_forward = None
         # The stem kernel reads the caller's tensor (its address changes per call), so it is launched
         # eagerly; everything behind it only touches engine-owned memory and is replayed as one graph.
         self._calls[0]()

@@ -172,7 +172,7 @@ class B200DetectModel(torch.nn.Module):
                       "fwd": torch.cuda.Stream(device=dev) if self.in_flight > 1 else None,
                       "det": [torch.empty((b, max_det, 6), dtype=torch.float32, device=dev) for _ in range(2)],
                       "cnt": [torch.empty((b,), dtype=torch.int32, device=dev) for _ in range(2)],
-                      "done": [torch.cuda.Event() for _ in range(2)], "used": [False, False],
+                      "done": [torch.cuda.Event() for _ in range(2)],
                       "ws": torch.empty((ops.nms_workspace_bytes(b, a, nc) + 7) // 8, dtype=torch.int64, device=dev)}
                 eng._async_state = st
             caller = torch.cuda.current_stream(dev)
@@ -183,12 +183,11 @@ class B200DetectModel(torch.nn.Module):
                 fwd_stream.wait_event(ready)  # x was produced on the caller's stream
                 x.record_stream(fwd_stream)
             with torch.cuda.stream(fwd_stream):
-                k = eng._flip  # the prediction buffer this call will write
-                if st["used"][k]:
-                    fwd_stream.wait_event(st["done"][k])  # its previous reader (an earlier NMS) must have finished
+                k = eng._flip  # the prediction buffer this call will write (forward waits for its last reader)
                 pred = eng.forward(x)
                 fwd_done = torch.cuda.Event()
                 fwd_done.record(fwd_stream)
+                eng.last_async_forward = fwd_done
             side = st["stream"]
             side.wait_event(fwd_done)
             with torch.cuda.stream(side):
@@ -197,7 +196,7 @@ class B200DetectModel(torch.nn.Module):
                                                       workspace=st["ws"])
                 extra = after_nms(det, cnt) if after_nms is not None else None
                 st["done"][k].record(side)
-            st["used"][k] = True
+            eng.reader_done[k] = st["done"][k]
         return DetectTicket(det, cnt, st["done"][k], fwd_done, extra)
 
 

@@ -186,6 +186,13 @@ def test_detect_async_equals_sequential(cuda_device, in_flight):
         assert torch.equal(wc, gc), f"batch {i}: counts differ"
         assert torch.equal(wd, gd), f"batch {i}: detections differ"
     assert int(want[0][1].sum()) > 0
+    # mixing the two APIs on one model is safe: a sequential forward waits for the side-stream reader of the
+    # prediction buffer it is about to overwrite
+    t = model.detect_async(xs[0], 0.03, 0.65, multi_label=True)
+    for xi in xs[1:4]:
+        model(xi)
+    t.done.synchronize()
+    assert torch.equal(t.count, want[0][1]) and torch.equal(t.det, want[0][0])
 
 
 def test_full_size_properties(cuda_device):
