@@ -68,6 +68,8 @@ class _Op:
     weight: Optional[str] = None
     act: str = "none"
     k: int = 0
+    wslice: Optional[Tuple[int, int]] = None  # channel range of the folded weight this op uses (split depth-wise convs)
+    impl: str = ""                            # "" = default kernel, "tc" = tensor-core depth-wise kernel
     flops_per_image: int = 0
     bytes_per_image: int = 0   # algorithmic: activations read once + written once (fp16), weights excluded
 
@@ -113,6 +115,24 @@ class Plan:
             op.flops_per_image = 2 * kw["k"] * kw["k"] * writes[0].c * px_out
         self.ops.append(op)
         return op
+
+    def _emit_dw(self, name: str, src: _View, dst: _View, weight: str, act: str, k: int):
+        """One depth-wise conv, or — experiment knob MAFB200_DW_SPLIT=<fraction>, default off — two launches over
+        disjoint channel ranges: the first on the FFMA kernel (FMA pipe 60 % busy, LSU 18 %), the rest on the
+        tensor-core kernel (LSU 85 %, FMA 8 %; profiles/r01_ncu_full_summaries.md), on different streams of the
+        captured graph so that the complementary pipes overlap.  Measured: 17.15k images/s at 0.34 / 0.5 / 0.67
+        against 17.96k unsplit — the two grids mostly run one after the other and 16 launches are added."""
+        c = src.c
+        frac = float(os.environ.get("MAFB200_DW_SPLIT", "0"))
+        c_tc = int(c * frac) // 32 * 32 if frac > 0 else 0
+        if c_tc <= 0 or c - c_tc < 32 or (c - c_tc) % 16 != 0 or dst.buf.ld % 16 != 0 or (dst.c_off + c - c_tc) % 16 != 0:
+            self._emit("dwconv", name, [src], [dst], weight=weight, act=act, k=k)
+            return
+        c_a = c - c_tc
+        self._emit("dwconv", name + ".ffma", [src.slice(0, c_a)], [dst.slice(0, c_a)], weight=weight, act=act, k=k,
+                   wslice=(0, c_a))
+        self._emit("dwconv", name + ".tc", [src.slice(c_a, c_tc)], [dst.slice(c_a, c_tc)], weight=weight, act=act, k=k,
+                   wslice=(c_a, c), impl="tc")
 
     # ---- the schedule ----------------------------------------------------------------------------
     def _plan(self):
@@ -171,7 +191,7 @@ class Plan:
                     self._emit("conv1x1", f"L{i}.m{j}.conv1", [cat.slice((1 + j) * c_, c_)], [t1],
                                weight=f"{i}.m.{j}.conv1", act="silu")
                     t2 = self._buf(h, w, mid, f"L{i}.m{j}.dw")
-                    self._emit("dwconv", f"L{i}.m{j}.dw{l.k}", [t1], [t2], weight=f"{i}.m.{j}.dw", act="silu", k=l.k)
+                    self._emit_dw(f"L{i}.m{j}.dw{l.k}", t1, t2, f"{i}.m.{j}.dw", "silu", l.k)
                     self._emit("conv1x1", f"L{i}.m{j}.one_conv", [t2], [cat.slice((2 + j) * c_, c_)],
                                weight=f"{i}.m.{j}.one_conv", act="silu")
                 dst = self._buf(h, w, l.c_out, f"L{i}")
@@ -223,7 +243,7 @@ class Plan:
                 res = {}
                 for br, cout in (("cls", g.nc), ("reg", 4 * (l.reg_max + 1))):
                     t = self._buf(h, w, c, f"L{i}.{br}_dw")
-                    self._emit("dwconv", f"L{i}.{br}_dw{l.k}", [stem], [t], weight=f"{i}.{br}_dw", act="none", k=l.k)
+                    self._emit_dw(f"L{i}.{br}_dw{l.k}", stem, t, f"{i}.{br}_dw", "none", l.k)
                     f2 = self._buf(h, w, c, f"L{i}.{br}_s")
                     self._emit("conv1x1", f"L{i}.{br}_s", [t], [f2], weight=f"{i}.{br}_s", act="silu")
                     o = self._buf(h, w, cout, f"L{i}.{br}_pred")
@@ -356,11 +376,15 @@ class Engine:
             self._weights[op.name] = (w, b)
             return lambda: ops.conv3x3s2(reads[0], w, b, op.act, writes[0])
         if op.kind == "dwconv":
-            if reads[0].c % 8 == 0 and writes[0].ld % 16 == 0 and os.environ.get("MAFB200_DW_TC", "0") != "0":
-                w, b = ops.pack_dw_tc(*folded[op.weight], device=dev)  # tensor-core (Toeplitz HMMA) kernel
+            wt, bs = folded[op.weight]
+            if op.wslice is not None:
+                wt, bs = wt[op.wslice[0]:op.wslice[1]], bs[op.wslice[0]:op.wslice[1]]
+            use_tc = op.impl == "tc" or os.environ.get("MAFB200_DW_TC", "0") != "0"
+            if use_tc and reads[0].c % 8 == 0 and writes[0].ld % 16 == 0 and writes[0].c_off % 16 == 0:
+                w, b = ops.pack_dw_tc(wt, bs, device=dev)  # tensor-core (Toeplitz HMMA) kernel
                 self._weights[op.name] = (w, b)
                 return lambda: ops.dwconv_tc(reads[0], w, b, op.k, op.act, writes[0])
-            w, b = ops.pack_dw(*folded[op.weight], device=dev)
+            w, b = ops.pack_dw(wt, bs, device=dev)
             self._weights[op.name] = (w, b)
             return lambda: ops.dwconv(reads[0], w, b, op.k, op.act, writes[0])
         if op.kind == "maxpool2x2":
@@ -383,17 +407,20 @@ class Engine:
         producer is still the stream's tail, otherwise takes the least-recently-used stream."""
         ops_ = self.plan.ops
 
-        def ranges(views):
-            return [(v.buf.offset, v.buf.offset + v.buf.nbytes(self.batch)) for v in views]
+        def ranges(views):  # (byte range of the buffer, buffer identity, channel range of the view)
+            return [(v.buf.offset, v.buf.offset + v.buf.nbytes(self.batch), id(v.buf), v.c_off, v.c_off + v.c) for v in views]
 
         rd = [ranges(o.reads) for o in ops_]
         wr = [ranges(o.writes) for o in ops_]
         for j, o in enumerate(ops_):
             if o.kind == "decode":
-                wr[j] = wr[j] + [(-2, -1)]  # the pred tensor (outside the arena)
+                wr[j] = wr[j] + [(-2, -1, -1, 0, 1)]  # the pred tensor (outside the arena)
 
         def hit(a, b):
-            return any(x0 < y1 and y0 < x1 for x0, x1 in a for y0, y1 in b)
+            # byte ranges overlap, and — inside ONE buffer — so do the channel slices (disjoint channel slices of a
+            # buffer never conflict: the two halves of a split depth-wise conv, the producers of a concat buffer)
+            return any(x0 < y1 and y0 < x1 and (xb != yb or (xc0 < yc1 and yc0 < xc1))
+                       for x0, x1, xb, xc0, xc1 in a for y0, y1, yb, yc0, yc1 in b)
 
         deps = []
         for j in range(len(ops_)):

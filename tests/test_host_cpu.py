@@ -154,6 +154,8 @@ def test_plan_liveness_and_arena(variant):
     for op in plan.ops:
         if op.weight:
             w, bias = folded[op.weight]
+            if op.wslice is not None:  # a split depth-wise conv uses a channel range of the folded weight
+                w, bias = w[op.wslice[0]:op.wslice[1]], bias[op.wslice[0]:op.wslice[1]]
             assert w.shape[0] == op.writes[0].c == bias.shape[0], op.name
             if op.kind == "conv1x1":
                 assert w.shape[1] == sum(v.c for v in op.reads), op.name
