@@ -170,6 +170,21 @@ MAFB200_API int32_t mafb200_nms(const float* pred, int32_t batch, int32_t anchor
                     int32_t max_det, int32_t max_nms, float* det, int32_t* count, void* workspace,
                     size_t workspace_bytes, void* stream);
 
+/* ---- serving path: decode fused with the NMS threshold / compaction pass -------------------------------
+ * mafb200_head_decode_detect = mafb200_head_decode + the first half of mafb200_nms (yolov6/utils/nms.py:48-84) in
+ * one kernel: boxes fp32 [n, A, 4] (cx, cy, w, h) and, in `workspace` (size / layout of mafb200_nms), the unordered
+ * candidate keys + per-image counts.  pred may be NULL — the [n, A, 5+nc] tensor (91 MB at bs32) is then never
+ * written nor read back.  mafb200_nms_select = the second half of mafb200_nms (sort + greedy NMS, nms.py:90-100) on
+ * those candidates; box_stride = 4 for `boxes`, 5+nc when boxes points at a pred tensor.  Together they give the
+ * same det / count as mafb200_head_decode followed by mafb200_nms, bit for bit. */
+MAFB200_API int32_t mafb200_head_decode_detect(const maf_tensor* cls_logits, const maf_tensor* reg, const float* strides,
+                                   int32_t n_levels, int32_t reg_max, int32_t cls_is_prob, float* pred, float* boxes,
+                                   double conf_thres, int32_t multi_label, const uint8_t* class_filter,
+                                   void* workspace, size_t workspace_bytes, void* stream);
+MAFB200_API int32_t mafb200_nms_select(const float* boxes, int32_t box_stride, int32_t batch, int32_t anchors, int32_t nc,
+                           double iou_thres, int32_t agnostic, int32_t max_det, int32_t max_nms, float* det,
+                           int32_t* count, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- image pre-processing (the step right before the hot path) ------------------------------------
  * letterbox (yolov6/data/data_augment.py:53-83: cv2.resize INTER_LINEAR to new_w x new_h — reproduced bit for
  * bit — then a constant border of `fill`) + HWC -> CHW and BGR -> RGB (Inferer.precess_image,

@@ -74,6 +74,11 @@ _SIGNATURES = {
                                          C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "mafb200_scale_detections": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                              C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mafb200_head_decode_detect": (C.c_int32, [_P(MafTensor), _P(MafTensor), _P(C.c_float), C.c_int32, C.c_int32, C.c_int32,
+                                               C.c_void_p, C.c_void_p, C.c_double, C.c_int32, C.c_void_p, C.c_void_p,
+                                               C.c_size_t, C.c_void_p]),
+    "mafb200_nms_select": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32,
+                                       C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "mafb200_launch_count": (C.c_int64, []),
 }
 

@@ -16,6 +16,7 @@
 
 #include "common.cuh"
 #include "host.h"
+#include "nms_filter.cuh"
 
 namespace mafb200 {
 
@@ -31,13 +32,24 @@ struct DecodeParams {
   int32_t cta_off[kMaxLevels + 1]; // first CTA (per image) of the level
   float stride[kMaxLevels];
   int32_t n_levels, nc, bins, total_anchors, cls_is_prob;
-  float* pred;
+  float* pred;   // [B, A, 5+nc] or nullptr (detect mode: never materialised)
+  // detect mode (mafb200_head_decode_detect): the threshold / compaction pass of the NMS fused in
+  float* boxes;  // [B, A, 4] (cx, cy, w, h) or nullptr
+  int32_t emit, multi_label;
+  float conf;
+  const uint8_t* class_filter;
+  int32_t* ncand;
+  unsigned long long* keys;
+  long long cap_pow2;
 };
+
+constexpr int kRowBuf = 160;  // floats per warp: one output row (5 + nc <= 160 in detect mode)
 
 __global__ void __launch_bounds__(256) head_decode_kernel(const __grid_constant__ DecodeParams p) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float s_box[kAnchorsPerCta][4];
+  __shared__ float s_row[8][kRowBuf];  // detect mode: the row a warp just decoded, read back by the candidate filter
   __shared__ __align__(16) __half s_reg[kAnchorsPerCta * 264];  // up to 4*(63+1)=256 (+pad) halves per anchor
   const int b = blockIdx.y;
   int lvl = 0;
@@ -108,10 +120,12 @@ __global__ void __launch_bounds__(256) head_decode_kernel(const __grid_constant_
   // ---- phase 2: one warp per output row (anchor), lanes stride the 5+nc columns: contiguous fp32
   //      stores, contiguous fp16 class-logit loads, no integer division ---------------------------------
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* dst0 = p.pred + (static_cast<size_t>(b) * p.total_anchors + p.anchor_off[lvl] + a0) * no;
+  const size_t row0 = static_cast<size_t>(b) * p.total_anchors + p.anchor_off[lvl] + a0;
+  float* dst0 = p.pred != nullptr ? p.pred + row0 * no : nullptr;
   const __half* cls0 = p.cls[lvl] + (static_cast<size_t>(b) * L + a0) * p.cls_ld[lvl];
+  unsigned long long* keys_b = p.emit ? p.keys + static_cast<size_t>(b) * p.cap_pow2 : nullptr;
   for (int al = warp; al < na; al += 8) {
-    float* dst = dst0 + static_cast<size_t>(al) * no;
+    float* dst = dst0 != nullptr ? dst0 + static_cast<size_t>(al) * no : nullptr;
     const __half* cls = cls0 + static_cast<size_t>(al) * p.cls_ld[lvl];
     for (int j = lane; j < no; j += 32) {
       float v;
@@ -123,8 +137,18 @@ __global__ void __launch_bounds__(256) head_decode_kernel(const __grid_constant_
         const float z = __half2float(__ldg(cls + (j - 5)));
         v = p.cls_is_prob ? z : __fdividef(1.0f, 1.0f + __expf(-z));
       }
-      dst[j] = v;
+      if (dst != nullptr) dst[j] = v;
+      if (p.emit) s_row[warp][j] = v;
     }
+    if (p.emit) {
+      // the same fp32 values the reference-shaped path would read back from `pred`, so the candidate set is identical
+      __syncwarp();
+      nms_filter_row(s_row[warp], p.anchor_off[lvl] + a0 + al, p.nc, p.conf, p.multi_label, p.class_filter, &p.ncand[b],
+                     keys_b, p.cap_pow2, lane);
+      __syncwarp();
+    }
+    if (p.boxes != nullptr && lane == 0)
+      *reinterpret_cast<float4*>(p.boxes + (row0 + al) * 4) = make_float4(s_box[al][0], s_box[al][1], s_box[al][2], s_box[al][3]);
   }
 }
 
@@ -132,14 +156,65 @@ __global__ void __launch_bounds__(256) head_decode_kernel(const __grid_constant_
 
 using namespace mafb200;
 
+static int32_t decode_common(const maf_tensor* cls_logits, const maf_tensor* reg, const float* strides, int32_t n_levels,
+                             int32_t reg_max, int32_t cls_is_prob, DecodeParams& p, void* stream);
+
 extern "C" int32_t mafb200_head_decode(const maf_tensor* cls_logits, const maf_tensor* reg, const float* strides,
                                        int32_t n_levels, int32_t reg_max, int32_t cls_is_prob, float* pred,
                                        void* stream) {
-  if (!cls_logits || !reg || !strides || !pred) return fail(MAF_E_ARG, "head_decode: null pointer");
-  if (n_levels < 1 || n_levels > kMaxLevels) return fail(MAF_E_ARG, "head_decode: n_levels=%d (1..%d)", n_levels, kMaxLevels);
-  if (reg_max < 1 || reg_max > 63) return fail(MAF_E_ARG, "head_decode: reg_max=%d (1..63)", reg_max);
+  if (!pred) return fail(MAF_E_ARG, "head_decode: null pointer");
   DecodeParams p;
   memset(&p, 0, sizeof(p));
+  p.pred = pred;
+  return decode_common(cls_logits, reg, strides, n_levels, reg_max, cls_is_prob, p, stream);
+}
+
+// Decode + the threshold / compaction pass of non_max_suppression (yolov6/utils/nms.py:48-84) in one kernel: writes
+// the (cx, cy, w, h) boxes [B, A, 4] and the unordered candidate keys + per-image counts into `workspace` (layout of
+// mafb200_nms), for mafb200_nms_select.  `pred` may be NULL: the [B, A, 5+nc] tensor is then never written.
+extern "C" int32_t mafb200_head_decode_detect(const maf_tensor* cls_logits, const maf_tensor* reg, const float* strides,
+                                              int32_t n_levels, int32_t reg_max, int32_t cls_is_prob, float* pred,
+                                              float* boxes, double conf_thres, int32_t multi_label,
+                                              const uint8_t* class_filter, void* workspace, size_t workspace_bytes,
+                                              void* stream) {
+  if (!boxes || !workspace || !cls_logits) return fail(MAF_E_ARG, "head_decode_detect: null pointer");
+  if (!(conf_thres >= 0.0 && conf_thres <= 1.0))
+    return fail(MAF_E_ARG, "head_decode_detect: conf_thres must be in [0,1], got %g", conf_thres);
+  if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(MAF_E_ALIGN, "head_decode_detect: workspace must be 256-B aligned");
+  if (reinterpret_cast<uintptr_t>(boxes) & 15) return fail(MAF_E_ALIGN, "head_decode_detect: boxes must be 16-B aligned");
+  if (n_levels < 1 || n_levels > kMaxLevels) return fail(MAF_E_ARG, "head_decode_detect: n_levels=%d", n_levels);
+  const int nc = cls_logits[0].c, n = cls_logits[0].n;
+  if (5 + nc > kRowBuf) return fail(MAF_E_ARG, "head_decode_detect: nc=%d > %d", nc, kRowBuf - 5);
+  long long anchors = 0;
+  for (int l = 0; l < n_levels; ++l) anchors += static_cast<long long>(cls_logits[l].h) * cls_logits[l].w;
+  if (anchors * nc > 0x7fffffffll) return fail(MAF_E_ARG, "head_decode_detect: anchors*nc overflows int32");
+  if (workspace_bytes < mafb200_nms_workspace_bytes(n, static_cast<int32_t>(anchors), nc))
+    return fail(MAF_E_WORKSPACE, "head_decode_detect: workspace %zu < required %zu", workspace_bytes,
+                mafb200_nms_workspace_bytes(n, static_cast<int32_t>(anchors), nc));
+  DecodeParams p;
+  memset(&p, 0, sizeof(p));
+  p.pred = pred;
+  p.boxes = boxes;
+  p.emit = 1;
+  p.multi_label = (multi_label != 0 && nc > 1) ? 1 : 0;  // nms.py:57
+  p.conf = static_cast<float>(conf_thres);
+  p.class_filter = class_filter;
+  const size_t hdr = ((static_cast<size_t>(n) * 4 + 255) / 256) * 256;
+  p.ncand = static_cast<int32_t*>(workspace);
+  p.keys = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(workspace) + hdr);
+  long long cap = 1;
+  while (cap < anchors * nc) cap <<= 1;
+  p.cap_pow2 = cap;
+  cudaError_t e = cudaMemsetAsync(p.ncand, 0, static_cast<size_t>(n) * 4, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(MAF_E_CUDA, "head_decode_detect: cudaMemsetAsync: %s", cudaGetErrorString(e));
+  return decode_common(cls_logits, reg, strides, n_levels, reg_max, cls_is_prob, p, stream);
+}
+
+static int32_t decode_common(const maf_tensor* cls_logits, const maf_tensor* reg, const float* strides, int32_t n_levels,
+                             int32_t reg_max, int32_t cls_is_prob, DecodeParams& p, void* stream) {
+  if (!cls_logits || !reg || !strides) return fail(MAF_E_ARG, "head_decode: null pointer");
+  if (n_levels < 1 || n_levels > kMaxLevels) return fail(MAF_E_ARG, "head_decode: n_levels=%d (1..%d)", n_levels, kMaxLevels);
+  if (reg_max < 1 || reg_max > 63) return fail(MAF_E_ARG, "head_decode: reg_max=%d (1..63)", reg_max);
   const int nc = cls_logits[0].c, n = cls_logits[0].n;
   int anchors = 0, ctas = 0;
   for (int l = 0; l < n_levels; ++l) {
@@ -166,10 +241,12 @@ extern "C" int32_t mafb200_head_decode(const maf_tensor* cls_logits, const maf_t
   p.bins = reg_max + 1;
   p.total_anchors = anchors;
   p.cls_is_prob = cls_is_prob != 0;
-  p.pred = pred;
   if (n > 65535) return fail(MAF_E_ARG, "head_decode: batch %d > 65535", n);
   int32_t rc = require_sm100();
   if (rc) return rc;
-  launch_pdl(head_decode_kernel, dim3(ctas, n), dim3(256), 0, static_cast<cudaStream_t>(stream), p);
+  if (p.emit)  // follows a memset node, not a kernel: plain stream-ordered launch
+    launch_pdl<false>(head_decode_kernel, dim3(ctas, n), dim3(256), 0, static_cast<cudaStream_t>(stream), p);
+  else
+    launch_pdl(head_decode_kernel, dim3(ctas, n), dim3(256), 0, static_cast<cudaStream_t>(stream), p);
   return check_launch("head_decode kernel launch");
 }

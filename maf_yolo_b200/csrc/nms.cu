@@ -29,6 +29,7 @@
 
 #include "common.cuh"
 #include "host.h"
+#include "nms_filter.cuh"
 
 namespace mafb200 {
 
@@ -39,6 +40,8 @@ constexpr float kMaxWh = 4096.0f;    // nms.py:54
 
 struct NmsParams {
   const float* pred;
+  const float* box;     // (cx, cy, w, h) of anchor a of image b at box[(b * A + a) * box_stride]: pred itself
+  int32_t box_stride;   // (stride 5 + nc) or the compact [B, A, 4] array of the fused decode (stride 4)
   int32_t B, A, nc;
   float conf;
   double iou;
@@ -84,71 +87,8 @@ __global__ void __launch_bounds__(256) nms_compact_kernel(const NmsParams p) {
   __syncthreads();
 
   unsigned long long* keys = p.keys + static_cast<size_t>(b) * p.cap_pow2;
-  for (int r = warp; r < rows; r += 8) {
-    const int a = a0 + r;
-    const float* row = s_rows + r * no;
-    const float obj = row[4];
-
-    // pass 1: raw class maximum (nms.py:48)
-    float mx = -INFINITY;
-    for (int c = lane; c < p.nc; c += 32) mx = fmaxf(mx, row[5 + c]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if (!(obj > p.conf) || !(mx > p.conf)) continue;
-
-    if (p.multi_label) {
-      for (int c0 = 0; c0 < p.nc; c0 += 32) {
-        const int c = c0 + lane;
-        float s = 0.f;
-        bool pass = false;
-        if (c < p.nc) {
-          s = __fmul_rn(row[5 + c], obj);
-          pass = s > p.conf && (p.class_filter == nullptr || p.class_filter[c] != 0);
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, pass);
-        if (m == 0) continue;
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&p.ncand[b], __popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (pass) {
-          const long long slot = base + __popc(m & ((1u << lane) - 1));
-          if (slot < p.cap_pow2) {
-            const unsigned sb = __float_as_uint(s);
-            keys[slot] = (static_cast<unsigned long long>(~sb) << 32) |
-                         static_cast<unsigned long long>(static_cast<unsigned>(a) * p.nc + c);
-          }
-        }
-      }
-    } else {
-      // best class by score, first maximum on ties (torch.max semantics on CPU)
-      float best = -INFINITY;
-      int bi = 0x7fffffff;
-      for (int c = lane; c < p.nc; c += 32) {
-        const float s = __fmul_rn(row[5 + c], obj);
-        if (s > best) {
-          best = s;
-          bi = c;
-        }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ob > best || (ob == best && oi < bi)) {
-          best = ob;
-          bi = oi;
-        }
-      }
-      if (lane == 0 && best > p.conf && bi < p.nc && (p.class_filter == nullptr || p.class_filter[bi] != 0)) {
-        const long long slot = atomicAdd(&p.ncand[b], 1);
-        if (slot < p.cap_pow2) {
-          const unsigned sb = __float_as_uint(best);
-          keys[slot] = (static_cast<unsigned long long>(~sb) << 32) |
-                       static_cast<unsigned long long>(static_cast<unsigned>(a) * p.nc + bi);
-        }
-      }
-    }
-  }
+  for (int r = warp; r < rows; r += 8)
+    nms_filter_row(s_rows + r * no, a0 + r, p.nc, p.conf, p.multi_label, p.class_filter, &p.ncand[b], keys, p.cap_pow2, lane);
 }
 
 // ---- bitonic sort helpers ------------------------------------------------------------------------
@@ -223,7 +163,7 @@ __global__ void __launch_bounds__(1024) nms_select_kernel(const NmsParams p) {
   // if they run out before max_det boxes are kept.  Results are identical either way.
   unsigned long long* gkeys = p.keys + static_cast<size_t>(b) * p.cap_pow2;
   const int n_eff = static_cast<int>(n < p.max_nms ? n : p.max_nms);
-  const float* pred_b = p.pred + static_cast<size_t>(b) * p.A * no;
+  const float* pred_b = p.box + static_cast<size_t>(b) * p.A * p.box_stride;
   __shared__ int s_sel[4];  // [0] level-1 boundary bin, [1] level-2 boundary bin, [2] selected count, [3] fill cursor
 
   for (int attempt = (n > kSortSmemKeys ? 0 : 1); attempt < 2; ++attempt) {
@@ -302,7 +242,7 @@ __global__ void __launch_bounds__(1024) nms_select_kernel(const NmsParams p) {
     if (threadIdx.x < cn) {
       const unsigned idx = static_cast<unsigned>(keys[base + threadIdx.x] & 0xffffffffull);
       const int a = idx / p.nc, c = idx - a * p.nc;
-      const float* row = pred_b + static_cast<size_t>(a) * no;
+      const float* row = pred_b + static_cast<size_t>(a) * p.box_stride;
       const float cx = row[0], cy = row[1], w = row[2], h = row[3];
       const float off = p.agnostic ? 0.0f : __fmul_rn(static_cast<float>(c), kMaxWh);
       const float x1 = __fadd_rn(__fsub_rn(cx, __fdiv_rn(w, 2.0f)), off);
@@ -410,7 +350,7 @@ __global__ void __launch_bounds__(1024) nms_select_kernel(const NmsParams p) {
         const unsigned long long key = keys[base + i];
         const unsigned idx = static_cast<unsigned>(key & 0xffffffffull);
         const int a = idx / p.nc, c = idx - a * p.nc;
-        const float* row = pred_b + static_cast<size_t>(a) * no;
+        const float* row = pred_b + static_cast<size_t>(a) * p.box_stride;
         const float cx = row[0], cy = row[1], w = row[2], h = row[3];
         float* o = det + static_cast<size_t>(nk0 + t) * 6;
         o[0] = __fsub_rn(cx, __fdiv_rn(w, 2.0f));
@@ -435,6 +375,19 @@ static long long pow2_ceil(long long v) {
   long long p = 1;
   while (p < v) p <<= 1;
   return p;
+}
+
+static int32_t launch_select(const NmsParams& p, cudaStream_t st) {
+  const size_t smem = static_cast<size_t>(kSortSmemKeys) * 8 + static_cast<size_t>(round_up(p.max_det, 2)) * 5 * 4 +
+                      kChunk * 5 * 4 + kChunk * 4 * 8 + kChunk * 4 * 2 + (kChunk / 32) * 4;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(nms_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (e != cudaSuccess) return fail(MAF_E_CUDA, "nms: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  launch_pdl<false>(nms_select_kernel, dim3(p.B), dim3(1024), smem, st, p);
+  return check_launch("nms_select kernel launch");
 }
 
 }  // namespace mafb200
@@ -471,6 +424,8 @@ extern "C" int32_t mafb200_nms(const float* pred, int32_t batch, int32_t anchors
   NmsParams p;
   memset(&p, 0, sizeof(p));
   p.pred = pred;
+  p.box = pred;
+  p.box_stride = 5 + nc;
   p.B = batch;
   p.A = anchors;
   p.nc = nc;
@@ -504,15 +459,45 @@ extern "C" int32_t mafb200_nms(const float* pred, int32_t batch, int32_t anchors
   rc = check_launch("nms_compact kernel launch");
   if (rc) return rc;
 
-  const size_t smem = static_cast<size_t>(kSortSmemKeys) * 8 + static_cast<size_t>(round_up(max_det, 2)) * 5 * 4 +
-                      kChunk * 5 * 4 +
-                      kChunk * 4 * 8 + kChunk * 4 * 2 + (kChunk / 32) * 4;
-  static bool configured = false;
-  if (!configured) {
-    e = cudaFuncSetAttribute(nms_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    if (e != cudaSuccess) return fail(MAF_E_CUDA, "nms: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    configured = true;
-  }
-  launch_pdl<false>(nms_select_kernel, dim3(batch), dim3(1024), smem, st, p);
-  return check_launch("nms_select kernel launch");
+  return launch_select(p, st);
+}
+
+// Second half of mafb200_nms alone: sort + greedy NMS over candidates that are ALREADY in `workspace` (written by
+// mafb200_head_decode_detect, which fuses the decode with the threshold / compaction pass so that the
+// [B, A, 5+nc] prediction tensor is never materialised on the serving path).  `boxes`: fp32 (cx, cy, w, h) of
+// anchor a of image b at boxes[(b * anchors + a) * box_stride].
+extern "C" int32_t mafb200_nms_select(const float* boxes, int32_t box_stride, int32_t batch, int32_t anchors, int32_t nc,
+                                      double iou_thres, int32_t agnostic, int32_t max_det, int32_t max_nms, float* det,
+                                      int32_t* count, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!boxes || !det || !count || !workspace) return fail(MAF_E_ARG, "nms_select: null pointer");
+  if (batch <= 0 || anchors <= 0 || nc <= 0 || box_stride < 4)
+    return fail(MAF_E_ARG, "nms_select: bad shape B=%d A=%d nc=%d stride=%d", batch, anchors, nc, box_stride);
+  if (!(iou_thres >= 0.0 && iou_thres <= 1.0)) return fail(MAF_E_ARG, "nms_select: iou_thres must be in [0,1], got %g", iou_thres);
+  if (max_det <= 0 || max_det > kMaxDetCap) return fail(MAF_E_ARG, "nms_select: max_det=%d (1..%d)", max_det, kMaxDetCap);
+  if (max_nms <= 0) return fail(MAF_E_ARG, "nms_select: max_nms=%d", max_nms);
+  if (batch > 65535) return fail(MAF_E_ARG, "nms_select: batch %d > 65535", batch);
+  if (workspace_bytes < mafb200_nms_workspace_bytes(batch, anchors, nc))
+    return fail(MAF_E_WORKSPACE, "nms_select: workspace %zu < required %zu", workspace_bytes,
+                mafb200_nms_workspace_bytes(batch, anchors, nc));
+  if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(MAF_E_ALIGN, "nms_select: workspace must be 256-B aligned");
+  int32_t rc = require_sm100();
+  if (rc) return rc;
+  NmsParams p;
+  memset(&p, 0, sizeof(p));
+  p.box = boxes;
+  p.box_stride = box_stride;
+  p.B = batch;
+  p.A = anchors;
+  p.nc = nc;
+  p.iou = iou_thres;
+  p.agnostic = agnostic != 0;
+  p.max_det = max_det;
+  p.max_nms = max_nms;
+  p.det = det;
+  p.count = count;
+  const size_t hdr = ((static_cast<size_t>(batch) * 4 + 255) / 256) * 256;
+  p.ncand = static_cast<int32_t*>(workspace);
+  p.keys = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(workspace) + hdr);
+  p.cap_pow2 = pow2_ceil(static_cast<long long>(anchors) * nc);
+  return launch_select(p, static_cast<cudaStream_t>(stream));
 }

@@ -332,7 +332,14 @@ class Engine:
             self._weights: Dict[str, Tuple[torch.Tensor, torch.Tensor]] = {}
             self._x: Optional[torch.Tensor] = None
             self._calls: List[Callable[[], None]] = [self._bind(op, folded) for op in self.plan.ops]
-        self._graphs: List[Optional[torch.cuda.CUDAGraph]] = [None, None]  # one per prediction buffer
+        # captured graphs, keyed by (prediction-buffer index, detect configuration or None)
+        self._graphs: Dict[Tuple[int, object], torch.cuda.CUDAGraph] = {}
+        # detect mode (B200DetectModel.detect_async): the decode kernel also does the NMS threshold / compaction pass
+        # and the prediction tensor is not materialised; buffers are allocated on first use
+        self._detect: Optional[Tuple[float, bool, Optional[Tuple[int, ...]]]] = None
+        self._detect_filters: Dict[Tuple[int, ...], torch.Tensor] = {}
+        self.boxes: Optional[List[torch.Tensor]] = None
+        self.nms_ws: Optional[List[torch.Tensor]] = None
         self.launches_per_forward = len(self._calls)
         self._schedule = self._make_schedule() if self.n_streams > 1 else None
         self._side_streams = [torch.cuda.Stream(device=self.device) for _ in range(self.n_streams - 1)]
@@ -397,7 +404,17 @@ class Engine:
             nl = len(reads) // 2
             strides = [float(s) for s in self.graph.strides]
             reg_max = self.graph.layers[self.graph.head_layers[0]].reg_max
-            return lambda: ops.head_decode(reads[:nl], reads[nl:], strides, reg_max, self.pred)
+
+            def decode():
+                if self._detect is None:
+                    ops.head_decode(reads[:nl], reads[nl:], strides, reg_max, self.pred)
+                else:
+                    conf, multi_label, classes = self._detect
+                    k = self.last_index
+                    ops.head_decode_detect(reads[:nl], reads[nl:], strides, reg_max, self.boxes[k], conf, multi_label,
+                                           self._detect_filters[classes] if classes is not None else None, self.nms_ws[k])
+
+            return decode
         raise NotImplementedError(op.kind)
 
     # ---- multi-stream schedule ------------------------------------------------------------------------
@@ -498,10 +515,32 @@ class Engine:
             call()
         return self.pred
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
-        """x: NCHW fp32/fp16 in [0,1] or uint8 -> pred [B, A, 5+nc] fp32 (engine-owned buffer)."""
+    def _set_detect(self, detect) -> None:
+        """detect = None (write the prediction tensor) or (conf_thres, multi_label, classes-tuple-or-None)."""
+        self._detect = detect
+        if detect is None:
+            return
+        if self.boxes is None:
+            with torch.cuda.device(self.device):
+                a, nc = self.plan.anchors, self.graph.nc
+                self.boxes = [torch.empty((self.batch, a, 4), dtype=torch.float32, device=self.device) for _ in range(2)]
+                nbytes = ops.nms_workspace_bytes(self.batch, a, nc)
+                self.nms_ws = [torch.empty((nbytes + 7) // 8, dtype=torch.int64, device=self.device) for _ in range(2)]
+        classes = detect[2]
+        if classes is not None and classes not in self._detect_filters:
+            filt = torch.zeros(self.graph.nc, dtype=torch.uint8)
+            for c in classes:
+                if 0 <= int(c) < self.graph.nc:
+                    filt[int(c)] = 1
+            self._detect_filters[classes] = filt.to(self.device)
+
+    def forward(self, x: torch.Tensor, detect=None) -> torch.Tensor:
+        """x: NCHW fp32/fp16 in [0,1] or uint8 -> pred [B, A, 5+nc] fp32 (engine-owned buffer); with `detect`
+        (see _set_detect) -> boxes [B, A, 4], the NMS candidates being left in self.nms_ws[self.last_index]."""
+        self._set_detect(detect)
         if not self.use_cuda_graph:
-            return self.run_eager(x)
+            self.run_eager(x)
+            return self.pred if detect is None else self.boxes[self.last_index]
         x = self._check_input(x)
         self._x = x
         k = self._flip
@@ -517,7 +556,8 @@ class Engine:
         # The stem kernel reads the caller's tensor (its address changes per call), so it is launched
         # eagerly; everything behind it only touches engine-owned memory and is replayed as one graph.
         self._calls[0]()
-        if self._graphs[k] is None:
+        gkey = (k, detect)
+        if gkey not in self._graphs:
             for call in self._calls[1:]:  # warm-up outside capture (sets func attributes, loads modules)
                 call()
             torch.cuda.synchronize(self.device)
@@ -528,10 +568,10 @@ class Engine:
                 else:
                     for call in self._calls[1:]:
                         call()
-            self._graphs[k] = g
+            self._graphs[gkey] = g
             self._calls[0]()
-        self._graphs[k].replay()
-        return self.pred
+        self._graphs[gkey].replay()
+        return self.pred if detect is None else self.boxes[k]
 
     __call__ = forward
 

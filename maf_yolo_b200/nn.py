@@ -8,6 +8,7 @@ Everything computes through libmafb200.so; PyTorch only owns memory and streams.
 """
 from __future__ import annotations
 
+import os
 from typing import List, NamedTuple, Optional, Sequence
 
 import torch
@@ -102,6 +103,8 @@ class B200DetectModel(torch.nn.Module):
         self.use_cuda_graph = use_cuda_graph
         self.return_featmaps = return_featmaps
         self.n_streams = n_streams
+        # detect_async: decode fused with the NMS threshold / compaction pass (MAFB200_FUSED_DETECT=0 turns it off)
+        self.fused_detect = os.environ.get("MAFB200_FUSED_DETECT", "1") != "0"
         self.in_flight = max(1, int(in_flight))  # detect_async: engine replicas (arena + graph + streams) used round-robin
         self._rr = 0
         self._engines = {}
@@ -173,7 +176,8 @@ class B200DetectModel(torch.nn.Module):
                       "det": [torch.empty((b, max_det, 6), dtype=torch.float32, device=dev) for _ in range(2)],
                       "cnt": [torch.empty((b,), dtype=torch.int32, device=dev) for _ in range(2)],
                       "done": [torch.cuda.Event() for _ in range(2)],
-                      "ws": torch.empty((ops.nms_workspace_bytes(b, a, nc) + 7) // 8, dtype=torch.int64, device=dev)}
+                      "ws": None if self.fused_detect else
+                      torch.empty((ops.nms_workspace_bytes(b, a, nc) + 7) // 8, dtype=torch.int64, device=dev)}
                 eng._async_state = st
             caller = torch.cuda.current_stream(dev)
             fwd_stream = st["fwd"] if st["fwd"] is not None else caller
@@ -184,16 +188,28 @@ class B200DetectModel(torch.nn.Module):
                 x.record_stream(fwd_stream)
             with torch.cuda.stream(fwd_stream):
                 k = eng._flip  # the prediction buffer this call will write (forward waits for its last reader)
-                pred = eng.forward(x)
+                fused = self.fused_detect and max_nms > 0
+                if fused:
+                    # decode + NMS threshold/compaction in one kernel; the [B, A, 5+nc] tensor is never written
+                    boxes = eng.forward(x, detect=(float(conf_thres), bool(multi_label),
+                                                   tuple(int(c) for c in classes) if classes is not None else None))
+                else:
+                    pred = eng.forward(x)
                 fwd_done = torch.cuda.Event()
                 fwd_done.record(fwd_stream)
                 eng.last_async_forward = fwd_done
             side = st["stream"]
             side.wait_event(fwd_done)
             with torch.cuda.stream(side):
-                det, cnt = non_max_suppression_padded(pred, conf_thres, iou_thres, classes, agnostic, multi_label,
-                                                      max_det, max_nms, det=st["det"][k], count=st["cnt"][k],
-                                                      workspace=st["ws"])
+                if fused:
+                    assert 0 <= conf_thres <= 1, f'conf_thresh must be in 0.0 to 1.0, however {conf_thres} is provided.'
+                    assert 0 <= iou_thres <= 1, f'iou_thres must be in 0.0 to 1.0, however {iou_thres} is provided.'
+                    det, cnt = st["det"][k], st["cnt"][k]
+                    ops.nms_select(boxes, self.nc, iou_thres, agnostic, max_det, max_nms, det, cnt, eng.nms_ws[k])
+                else:
+                    det, cnt = non_max_suppression_padded(pred, conf_thres, iou_thres, classes, agnostic, multi_label,
+                                                          max_det, max_nms, det=st["det"][k], count=st["cnt"][k],
+                                                          workspace=st["ws"])
                 extra = after_nms(det, cnt) if after_nms is not None else None
                 st["done"][k].record(side)
             eng.reader_done[k] = st["done"][k]

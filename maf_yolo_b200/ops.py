@@ -219,6 +219,31 @@ def head_decode(cls_logits: Sequence[NHWC], reg: Sequence[NHWC], strides: Sequen
     check(lib().mafb200_head_decode(ca, ra, st, nl, reg_max, int(cls_is_prob), pred.data_ptr(), _stream()))
 
 
+def head_decode_detect(cls_logits: Sequence[NHWC], reg: Sequence[NHWC], strides: Sequence[float], reg_max: int,
+                       boxes: torch.Tensor, conf_thres: float, multi_label: bool, class_filter: Optional[torch.Tensor],
+                       workspace: torch.Tensor, pred: Optional[torch.Tensor] = None, cls_is_prob: bool = False) -> None:
+    """Decode fused with the NMS threshold / compaction pass: boxes [B,A,4] + candidates in `workspace`."""
+    nl = len(cls_logits)
+    assert boxes.dtype == torch.float32 and boxes.is_contiguous() and boxes.is_cuda and boxes.shape[-1] == 4
+    ca = (MafTensor * nl)(*[t.maf() for t in cls_logits])
+    ra = (MafTensor * nl)(*[t.maf() for t in reg])
+    st = (C.c_float * nl)(*[float(s) for s in strides])
+    check(lib().mafb200_head_decode_detect(ca, ra, st, nl, reg_max, int(cls_is_prob),
+                                           pred.data_ptr() if pred is not None else None, boxes.data_ptr(),
+                                           float(conf_thres), int(bool(multi_label)),
+                                           class_filter.data_ptr() if class_filter is not None else None,
+                                           workspace.data_ptr(), workspace.numel() * workspace.element_size(), _stream()))
+
+
+def nms_select(boxes: torch.Tensor, nc: int, iou_thres: float, agnostic: bool, max_det: int, max_nms: int,
+               det: torch.Tensor, count: torch.Tensor, workspace: torch.Tensor) -> None:
+    """Sort + greedy NMS over the candidates head_decode_detect left in `workspace`; boxes [B,A,4] or a pred tensor."""
+    b, a, stride = boxes.shape
+    check(lib().mafb200_nms_select(boxes.data_ptr(), stride, b, a, nc, float(iou_thres), int(bool(agnostic)), max_det,
+                                   max_nms, det.data_ptr(), count.data_ptr(), workspace.data_ptr(),
+                                   workspace.numel() * workspace.element_size(), _stream()))
+
+
 def nms_workspace_bytes(batch: int, anchors: int, nc: int) -> int:
     return int(lib().mafb200_nms_workspace_bytes(batch, anchors, nc))
 

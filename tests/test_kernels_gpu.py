@@ -368,6 +368,47 @@ def test_nms_many_candidates_prefix_select(cuda_device):
             assert np.array_equal(got[0].cpu().numpy(), ref[0]), f"{name} {kw}: differs from the oracle ({n_cand} candidates)"
 
 
+@pytest.mark.parametrize("kw", [dict(conf_thres=0.03, iou_thres=0.65, multi_label=True, max_det=300),
+                                dict(conf_thres=0.3, iou_thres=0.45, multi_label=False, max_det=1000),
+                                dict(conf_thres=0.03, iou_thres=0.65, multi_label=True, agnostic=True, classes=[1, 5, 7])])
+def test_decode_detect_equals_decode_then_nms(cuda_device, kw):
+    """mafb200_head_decode_detect + mafb200_nms_select (prediction tensor never written) give the same detections,
+    bit for bit, as mafb200_head_decode followed by mafb200_nms — and as the oracle NMS on the decoded tensor."""
+    from maf_yolo_b200 import nn as mnn, ops
+    from oracle import nms as onms
+
+    g = torch.Generator().manual_seed(23)
+    n, nc = 3, 80
+    sizes, strides = [(16, 24), (8, 12), (5, 6)], [8.0, 16.0, 32.0]
+    cls = [(torch.randn(n, nc, h, w, generator=g) * 2.5 - 4).half().float() for h, w in sizes]
+    reg = [(torch.randn(n, 68, h, w, generator=g) * 2).half().float() for h, w in sizes]
+    cls_t = [ops.NHWC.from_nchw(t.to(cuda_device)) for t in cls]
+    reg_t = [ops.NHWC.from_nchw(t.to(cuda_device)) for t in reg]
+    a = sum(h * w for h, w in sizes)
+    pred = torch.empty((n, a, 5 + nc), device=cuda_device)
+    ops.head_decode(cls_t, reg_t, strides, 16, pred)
+    kw2 = dict(kw)
+    want_det, want_cnt = mnn.non_max_suppression_padded(pred, **kw2)
+    ref = onms.non_max_suppression(pred.cpu().numpy(), **kw)
+    boxes = torch.empty((n, a, 4), device=cuda_device)
+    ws = torch.empty((ops.nms_workspace_bytes(n, a, nc) + 7) // 8, dtype=torch.int64, device=cuda_device)
+    filt = None
+    if kw.get("classes") is not None:
+        filt = torch.zeros(nc, dtype=torch.uint8)
+        filt[kw["classes"]] = 1
+        filt = filt.to(cuda_device)
+    ops.head_decode_detect(cls_t, reg_t, strides, 16, boxes, kw["conf_thres"], kw["multi_label"], filt, ws)
+    det = torch.full((n, kw.get("max_det", 300), 6), -1.0, device=cuda_device)
+    cnt = torch.full((n,), -1, dtype=torch.int32, device=cuda_device)
+    ops.nms_select(boxes, nc, kw["iou_thres"], kw.get("agnostic", False), kw.get("max_det", 300), 30000, det, cnt, ws)
+    torch.cuda.synchronize()
+    assert torch.equal(boxes, pred[..., :4])
+    assert torch.equal(cnt, want_cnt) and torch.equal(det, want_det)
+    for i, r in enumerate(ref):
+        assert np.array_equal(det[i, :int(cnt[i])].cpu().numpy(), r)
+    assert int(cnt.sum()) > 0
+
+
 def test_nms_obj_and_small(cuda_device):
     """objectness != 1, a batch where one image is empty, nc == 1 (multi_label is forced off)."""
     from maf_yolo_b200 import nn as mnn
