@@ -37,6 +37,7 @@ struct DecodeParams {
   float* boxes;  // [B, A, 4] (cx, cy, w, h) or nullptr
   int32_t emit, multi_label;
   float conf;
+  float skip_below;  // detect mode without pred: a row whose largest raw class value is below this cannot pass `> conf`
   const uint8_t* class_filter;
   int32_t* ncand;
   unsigned long long* keys;
@@ -124,9 +125,21 @@ __global__ void __launch_bounds__(256) head_decode_kernel(const __grid_constant_
   float* dst0 = p.pred != nullptr ? p.pred + row0 * no : nullptr;
   const __half* cls0 = p.cls[lvl] + (static_cast<size_t>(b) * L + a0) * p.cls_ld[lvl];
   unsigned long long* keys_b = p.emit ? p.keys + static_cast<size_t>(b) * p.cap_pow2 : nullptr;
+  const bool can_skip = p.emit && dst0 == nullptr;
   for (int al = warp; al < na; al += 8) {
     float* dst = dst0 != nullptr ? dst0 + static_cast<size_t>(al) * no : nullptr;
     const __half* cls = cls0 + static_cast<size_t>(al) * p.cls_ld[lvl];
+    if (p.boxes != nullptr && lane == 0)
+      *reinterpret_cast<float4*>(p.boxes + (row0 + al) * 4) = make_float4(s_box[al][0], s_box[al][1], s_box[al][2], s_box[al][3]);
+    if (can_skip) {
+      // ~99 % of the rows hold no candidate: decide that on the raw logits (sigmoid is monotonic; `skip_below` sits a
+      // safety margin under logit(conf)) and spare them the sigmoids and the filter
+      float mz = -INFINITY;
+      for (int c = lane; c < p.nc; c += 32) mz = fmaxf(mz, __half2float(__ldg(cls + c)));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mz = fmaxf(mz, __shfl_xor_sync(0xffffffffu, mz, o));
+      if (mz < p.skip_below) continue;
+    }
     for (int j = lane; j < no; j += 32) {
       float v;
       if (j < 4) {
@@ -147,8 +160,6 @@ __global__ void __launch_bounds__(256) head_decode_kernel(const __grid_constant_
                      keys_b, p.cap_pow2, lane);
       __syncwarp();
     }
-    if (p.boxes != nullptr && lane == 0)
-      *reinterpret_cast<float4*>(p.boxes + (row0 + al) * 4) = make_float4(s_box[al][0], s_box[al][1], s_box[al][2], s_box[al][3]);
   }
 }
 
@@ -198,6 +209,11 @@ extern "C" int32_t mafb200_head_decode_detect(const maf_tensor* cls_logits, cons
   p.emit = 1;
   p.multi_label = (multi_label != 0 && nc > 1) ? 1 : 0;  // nms.py:57
   p.conf = static_cast<float>(conf_thres);
+  // raw-value bound under which sigmoid(z) (or z itself when the input already holds probabilities) cannot exceed conf
+  if (cls_is_prob) p.skip_below = static_cast<float>(conf_thres) - 1e-3f;
+  else if (conf_thres <= 0.0) p.skip_below = -INFINITY;
+  else if (conf_thres >= 1.0) p.skip_below = 30.0f;
+  else p.skip_below = static_cast<float>(log(conf_thres / (1.0 - conf_thres)) - 0.05);
   p.class_filter = class_filter;
   const size_t hdr = ((static_cast<size_t>(n) * 4 + 255) / 256) * 256;
   p.ncand = static_cast<int32_t*>(workspace);
