@@ -137,6 +137,15 @@ MAFB200_API int32_t mafb200_dw_tc_pack(const float* weight_host, int32_t c, int3
 MAFB200_API int32_t mafb200_dwconv_tc(const maf_tensor* src, const void* table, const float* bias, int32_t k,
                           int32_t act, const maf_tensor* dst, void* stream);
 
+/* ---- depth-wise k x k fused with the 1x1 conv that consumes it (k in 3,5; cout <= 128) -------------------
+ * dst = act2(W2 * act1(DW_k(src) + dw_bias) + pw_bias): DepthBottleneckUni's conv2 -> SiLU -> one_conv
+ * (common.py:915-926) and Head_DepthUni's cls_conv -> cls_conv_s / reg_conv -> reg_conv_s (common.py:1328-1336);
+ * the depth-wise output never goes to HBM.  dw_weight / dw_bias as for mafb200_dwconv; pw_packed / pw_bias as for
+ * mafb200_conv1x1 with one source of src->c channels.  act1 in {none, silu, relu}. */
+MAFB200_API int32_t mafb200_dwconv_conv1x1(const maf_tensor* src, const float* dw_weight, const float* dw_bias, int32_t k,
+                               int32_t act1, const void* pw_packed, const float* pw_bias, int32_t act2,
+                               const maf_tensor* dst, void* stream);
+
 /* ---- pooling / resampling ------------------------------------------------------------------- */
 MAFB200_API int32_t mafb200_maxpool2x2(const maf_tensor* src, const maf_tensor* dst, void* stream);
 /* y1 = maxpool5(x), y2 = maxpool5(y1), y3 = maxpool5(y2) (stride 1, pad 2, -inf padding). */

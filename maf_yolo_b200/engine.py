@@ -68,6 +68,8 @@ class _Op:
     weight: Optional[str] = None
     act: str = "none"
     k: int = 0
+    weight2: Optional[str] = None             # fused depth-wise + 1x1 ("dwpw"): the 1x1's folded weight
+    act2: str = "none"
     wslice: Optional[Tuple[int, int]] = None  # channel range of the folded weight this op uses (split depth-wise convs)
     impl: str = ""                            # "" = default kernel, "tc" = tensor-core depth-wise kernel
     flops_per_image: int = 0
@@ -113,6 +115,8 @@ class Plan:
             op.flops_per_image = 2 * 9 * reads[0].c * writes[0].c * px_out
         elif kind == "dwconv":
             op.flops_per_image = 2 * kw["k"] * kw["k"] * writes[0].c * px_out
+        elif kind == "dwpw":
+            op.flops_per_image = 2 * kw["k"] * kw["k"] * reads[0].c * px_out + 2 * reads[0].c * writes[0].c * px_out
         self.ops.append(op)
         return op
 
@@ -133,6 +137,17 @@ class Plan:
                    wslice=(0, c_a))
         self._emit("dwconv", name + ".tc", [src.slice(c_a, c_tc)], [dst.slice(c_a, c_tc)], weight=weight, act=act, k=k,
                    wslice=(c_a, c), impl="tc")
+
+    @staticmethod
+    def _dwpw_ok(c: int, cout: int, k: int) -> bool:
+        """Can `depth-wise k x k -> 1x1` run as ONE kernel (mafb200_dwconv_conv1x1)?  k <= 5, one column tile, and the
+        A tile + W2 panel + halo tile must fit 113 KB so that two CTAs stay resident per SM."""
+        if os.environ.get("MAFB200_DWPW", "1") == "0" or k > 5 or c % 8 or cout % 8 or cout > 128:
+            return False
+        tile_n = (cout + 15) // 16 * 16
+        kblocks = (c + 63) // 64
+        halo = (10 + k - 1) * (20 + k - 1) * 64 * 2
+        return 1024 + 32768 + kblocks * tile_n * 128 + (halo + 127) // 128 * 128 + 64 + tile_n * 4 <= 113 * 1024
 
     # ---- the schedule ----------------------------------------------------------------------------
     def _plan(self):
@@ -190,6 +205,10 @@ class Plan:
                     t1 = self._buf(h, w, mid, f"L{i}.m{j}.expand")
                     self._emit("conv1x1", f"L{i}.m{j}.conv1", [cat.slice((1 + j) * c_, c_)], [t1],
                                weight=f"{i}.m.{j}.conv1", act="silu")
+                    if self._dwpw_ok(mid, c_, l.k):  # depth-wise + one_conv in one kernel: no 3c_-wide round trip
+                        self._emit("dwpw", f"L{i}.m{j}.dw{l.k}+one_conv", [t1], [cat.slice((2 + j) * c_, c_)],
+                                   weight=f"{i}.m.{j}.dw", act="silu", k=l.k, weight2=f"{i}.m.{j}.one_conv", act2="silu")
+                        continue
                     t2 = self._buf(h, w, mid, f"L{i}.m{j}.dw")
                     self._emit_dw(f"L{i}.m{j}.dw{l.k}", t1, t2, f"{i}.m.{j}.dw", "silu", l.k)
                     self._emit("conv1x1", f"L{i}.m{j}.one_conv", [t2], [cat.slice((2 + j) * c_, c_)],
@@ -242,10 +261,14 @@ class Plan:
                 self._emit("conv1x1", f"L{i}.stem", srcs_of(l), [stem], weight=i + ".stem", act="silu")
                 res = {}
                 for br, cout in (("cls", g.nc), ("reg", 4 * (l.reg_max + 1))):
-                    t = self._buf(h, w, c, f"L{i}.{br}_dw")
-                    self._emit_dw(f"L{i}.{br}_dw{l.k}", stem, t, f"{i}.{br}_dw", "none", l.k)
                     f2 = self._buf(h, w, c, f"L{i}.{br}_s")
-                    self._emit("conv1x1", f"L{i}.{br}_s", [t], [f2], weight=f"{i}.{br}_s", act="silu")
+                    if self._dwpw_ok(c, c, l.k):
+                        self._emit("dwpw", f"L{i}.{br}_dw{l.k}+{br}_s", [stem], [f2], weight=f"{i}.{br}_dw", act="none",
+                                   k=l.k, weight2=f"{i}.{br}_s", act2="silu")
+                    else:
+                        t = self._buf(h, w, c, f"L{i}.{br}_dw")
+                        self._emit_dw(f"L{i}.{br}_dw{l.k}", stem, t, f"{i}.{br}_dw", "none", l.k)
+                        self._emit("conv1x1", f"L{i}.{br}_s", [t], [f2], weight=f"{i}.{br}_s", act="silu")
                     o = self._buf(h, w, cout, f"L{i}.{br}_pred")
                     self._emit("conv1x1", f"L{i}.{br}_pred", [f2], [o], weight=f"{i}.{br}_pred",
                                act="sigmoid" if (br == "cls" and self.head_sigmoid) else "none")
@@ -382,6 +405,12 @@ class Engine:
             w, b = ops.pack_conv3x3(*folded[op.weight], device=dev)
             self._weights[op.name] = (w, b)
             return lambda: ops.conv3x3s2(reads[0], w, b, op.act, writes[0])
+        if op.kind == "dwpw":
+            dw_w, dw_b = ops.pack_dw(*folded[op.weight], device=dev)
+            wt2, bs2 = folded[op.weight2]
+            pw_w, pw_b = ops.pack_conv1x1(wt2.reshape(wt2.shape[0], -1), bs2, [reads[0].c], device=dev)
+            self._weights[op.name] = (dw_w, dw_b, pw_w, pw_b)
+            return lambda: ops.dwconv_conv1x1(reads[0], dw_w, dw_b, op.k, op.act, pw_w, pw_b, op.act2, writes[0])
         if op.kind == "dwconv":
             wt, bs = folded[op.weight]
             if op.wslice is not None:

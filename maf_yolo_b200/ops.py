@@ -187,6 +187,13 @@ def dwconv_tc(src: NHWC, table: torch.Tensor, bias: torch.Tensor, k: int, act, d
     check(lib().mafb200_dwconv_tc(src.ref(), table.data_ptr(), bias.data_ptr(), k, _act(act), dst.ref(), _stream()))
 
 
+def dwconv_conv1x1(src: NHWC, dw_w: torch.Tensor, dw_b: torch.Tensor, k: int, act1, pw_w: torch.Tensor,
+                   pw_b: torch.Tensor, act2, dst: NHWC) -> None:
+    """Depth-wise k x k (+bias, act1) fused with the 1x1 conv (+bias, act2) that consumes it."""
+    check(lib().mafb200_dwconv_conv1x1(src.ref(), dw_w.data_ptr(), dw_b.data_ptr(), k, _act(act1), pw_w.data_ptr(),
+                                       pw_b.data_ptr(), _act(act2), dst.ref(), _stream()))
+
+
 def maxpool2x2(src: NHWC, dst: NHWC) -> None:
     check(lib().mafb200_maxpool2x2(src.ref(), dst.ref(), _stream()))
 

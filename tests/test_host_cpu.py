@@ -154,6 +154,11 @@ def test_plan_liveness_and_arena(variant):
     for op in plan.ops:
         if op.weight:
             w, bias = folded[op.weight]
+            if op.kind == "dwpw":  # fused depth-wise + 1x1: depth-wise weight over the INPUT channels, 1x1 to the output
+                w2, b2 = folded[op.weight2]
+                assert w.shape[0] == op.reads[0].c == bias.shape[0] and w2.shape[0] == op.writes[0].c == b2.shape[0], op.name
+                assert w2.reshape(w2.shape[0], -1).shape[1] == op.reads[0].c, op.name
+                continue
             if op.wslice is not None:  # a split depth-wise conv uses a channel range of the folded weight
                 w, bias = w[op.wslice[0]:op.wslice[1]], bias[op.wslice[0]:op.wslice[1]]
             assert w.shape[0] == op.writes[0].c == bias.shape[0], op.name

@@ -226,6 +226,31 @@ def test_dwconv_tc(cuda_device, c, k, h, w, n, act):
         assert (dst.buf[..., c:] == 7.0).all(), "dwconv_tc wrote outside its channels"
 
 
+@pytest.mark.parametrize("c,cout,k,h,w,n,act1,act2", [(192, 64, 5, 40, 40, 2, "silu", "silu"), (128, 128, 5, 24, 30, 1, "none", "silu"),
+                                                      (72, 24, 3, 40, 40, 1, "silu", "silu"), (64, 32, 3, 7, 9, 2, "relu", "none"),
+                                                      (144, 48, 5, 20, 20, 2, "silu", "silu"), (192, 64, 5, 80, 80, 1, "silu", "silu")])
+def test_dwconv_conv1x1_fused(cuda_device, c, cout, k, h, w, n, act1, act2):
+    """Fused depth-wise -> 1x1 kernel against the two reference ops in fp32 (the intermediate is rounded to fp16 once,
+    exactly as the two separate kernels do)."""
+    from maf_yolo_b200 import ops
+
+    g = torch.Generator().manual_seed(57 + c + k)
+    x = torch.randn(n, c, h, w, generator=g).half().float()
+    dw_w = torch.randn(c, 1, k, k, generator=g) / k
+    dw_b = torch.randn(c, generator=g) * 0.5
+    pw_w = (torch.randn(cout, c, generator=g) / c ** 0.5).half().float()
+    pw_b = torch.randn(cout, generator=g)
+    mid = _act_ref(F.conv2d(x, dw_w, dw_b, padding=k // 2, groups=c), act1).half().float()
+    ref = _act_ref(F.conv2d(mid, pw_w[:, :, None, None], pw_b), act2)
+    src = ops.NHWC.from_nchw(x.to(cuda_device))
+    dwp, dbp = ops.pack_dw(dw_w, dw_b, cuda_device)
+    pwp, pbp = ops.pack_conv1x1(pw_w, pw_b, [c], cuda_device)
+    dst = ops.NHWC.empty(n, h, w, cout, cuda_device, ld=(cout + 15) // 16 * 16)
+    ops.dwconv_conv1x1(src, dwp, dbp, k, act1, pwp, pbp, act2, dst)
+    torch.cuda.synchronize()
+    _close(dst.to_nchw(), ref, f"dwconv_conv1x1 c={c}->{cout} k={k}", rtol=3e-3, atol=3e-3)
+
+
 def test_pool_upsample_layout(cuda_device):
     from maf_yolo_b200 import ops
 
