@@ -13,10 +13,11 @@
 //   TMA halo tile (14 x 24 x 64 ch, OOB zero fill = padding)  ->  25 x 25 packed FFMA2 per thread  ->  bias + act1  ->
 //   fp16 pairs written by hand into the SWIZZLE_128B K-major A tile (row = pixel 0..199 of the tile, 16-byte chunk
 //   index ^ (row & 7): a warp writes the 128 bytes of ONE row per instruction, conflict free)  ->  fence.proxy.async  ->
-//   one thread issues 2 M tiles x 4 tcgen05.mma (128 x N x 16) against the resident W2 panel, accumulating over the
-//   channel blocks in TMEM.
+//   one thread issues 2 M tiles x 4 tcgen05.mma (128 x N x 16) against that block's slice of W2 (it arrives with the
+//   halo tile, two slots), accumulating over the channel blocks in TMEM.
 // Epilogue: 8 warps drain the two 128-row accumulators (row = pixel), bias + act2, 256-bit stores.
 // Rows 200..255 of the A tile are never written (their accumulator rows are never read).
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -64,14 +65,13 @@ __global__ void __launch_bounds__(kFwThreads, 2) dwpw_kernel(const __grid_consta
   extern __shared__ uint8_t smem_fw_raw[];
   uint8_t* smem = smem_fw_raw + ((1024u - (smem_u32(smem_fw_raw) & 1023u)) & 1023u);
   uint8_t* s_a = smem;                                    // [256 rows][128 B], SWIZZLE_128B K-major
-  uint8_t* s_w = s_a + kABytes;                           // W2 panel: [k blocks][tile_n rows][128 B]
+  uint8_t* s_w = s_a + kABytes;                           // W2: two slots of one k block [tile_n rows][128 B]
   const int kblocks = (p.C + kFwCB - 1) / kFwCB;
   const int b_bytes = p.tile_n * 128;
-  __half* s_in = reinterpret_cast<__half*>(s_w + kblocks * b_bytes);  // halo tile [TH][TW][64]
+  __half* s_in = reinterpret_cast<__half*>(s_w + 2 * b_bytes);  // halo tile [TH][TW][64]
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_in) + ((kHaloBytes + 127) / 128) * 128);
-  uint64_t* bar_in = bars;       // halo tile landed (one phase per channel block)
-  uint64_t* bar_w = bars + 1;    // W2 panel landed (once)
-  uint64_t* bar_mma = bars + 2;  // the MMAs that read the A tile of block cb have completed (one phase per block)
+  uint64_t* bar_in = bars;       // halo tile + W2 block of a channel block landed (one phase per block)
+  uint64_t* bar_mma = bars + 2;  // the MMAs that read the A tile / W2 slot of block cb have completed (one phase per block)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
   float* s_pwb = reinterpret_cast<float*>(tmem_slot + 2);  // [tile_n]
 
@@ -84,7 +84,6 @@ __global__ void __launch_bounds__(kFwThreads, 2) dwpw_kernel(const __grid_consta
     tma_prefetch_desc(&p.tm_in);
     tma_prefetch_desc(&p.tm_w);
     mbar_init(bar_in, 1);
-    mbar_init(bar_w, 1);
     mbar_init(bar_mma, 1);
     fence_barrier_init();
   }
@@ -100,11 +99,9 @@ __global__ void __launch_bounds__(kFwThreads, 2) dwpw_kernel(const __grid_consta
 
   if (threadIdx.x == 0) {
     pdl_launch_dependents();
-    // weights are constants: fetched while the previous kernel may still be running
-    mbar_arrive_expect_tx(bar_w, kblocks * b_bytes);
-    for (int k = 0; k < kblocks; ++k) tma_load_2d(s_w + k * b_bytes, &p.tm_w, bar_w, k * kFwCB, 0);
+    mbar_arrive_expect_tx(bar_in, kHaloBytes + b_bytes);
+    tma_load_2d(s_w, &p.tm_w, bar_in, 0, 0);  // weights are constants: may start before the previous kernel ends
     pdl_wait();  // the input tile (and, causally, every output store) follows the previous kernels
-    mbar_arrive_expect_tx(bar_in, kHaloBytes);
     tma_load_tile_4d_fw(s_in, &p.tm_in, bar_in, 0, x0 - P, y0 - P, img);
   }
 
@@ -148,12 +145,14 @@ __global__ void __launch_bounds__(kFwThreads, 2) dwpw_kernel(const __grid_consta
       }
     }
     __syncthreads();  // every warp is done reading the halo tile of this block
-    if (threadIdx.x == 0 && cb + 1 < kblocks) {
-      mbar_arrive_expect_tx(bar_in, kHaloBytes);
-      tma_load_tile_4d_fw(s_in, &p.tm_in, bar_in, c0 + kFwCB, x0 - P, y0 - P, img);  // overlaps the A-tile writes + MMA
-    }
-    // the MMAs of the previous block must have finished reading the A tile before it is overwritten
+    // the MMAs of the previous block must have finished reading the A tile (about to be overwritten) and their W2
+    // slot (the one the next block's weights go to)
     if (cb > 0) mbar_wait(bar_mma, (cb - 1) & 1);
+    if (threadIdx.x == 0 && cb + 1 < kblocks) {  // next block's halo tile + W2 block: overlaps the A-tile writes + MMA
+      mbar_arrive_expect_tx(bar_in, kHaloBytes + b_bytes);
+      tma_load_2d(s_w + ((cb + 1) & 1) * b_bytes, &p.tm_w, bar_in, c0 + kFwCB, 0);
+      tma_load_tile_4d_fw(s_in, &p.tm_in, bar_in, c0 + kFwCB, x0 - P, y0 - P, img);
+    }
 
     // bias is already in the accumulator; act1, fp16, SW128 K-major A tile: row = pixel, 4 bytes per lane
 #pragma unroll
@@ -170,11 +169,7 @@ __global__ void __launch_bounds__(kFwThreads, 2) dwpw_kernel(const __grid_consta
     __syncthreads();
     tc_fence_after_sync();
     if (threadIdx.x == 0) {
-      if (cb == 0) {
-        mbar_wait(bar_w, 0);
-        tc_fence_after_sync();
-      }
-      const uint64_t db = umma_smem_desc_sw128(smem_u32(s_w + cb * b_bytes));
+      const uint64_t db = umma_smem_desc_sw128(smem_u32(s_w + (cb & 1) * b_bytes));  // landed with this block's halo tile
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
         const uint64_t da = umma_smem_desc_sw128(smem_u32(s_a + mt * 16384));
@@ -227,8 +222,7 @@ __global__ void __launch_bounds__(kFwThreads, 2) dwpw_kernel(const __grid_consta
 template <int K>
 static int32_t launch_dwpw(DwPwParams& p, int n, int tiles, cudaStream_t st) {
   constexpr int TW = kFwTX + K - 1, TH = kFwTY + K - 1;
-  const int kblocks = (p.C + kFwCB - 1) / kFwCB;
-  const size_t smem = 1024 + static_cast<size_t>(kFwRows) * 128 + static_cast<size_t>(kblocks) * p.tile_n * 128 +
+  const size_t smem = 1024 + static_cast<size_t>(kFwRows) * 128 + static_cast<size_t>(2) * p.tile_n * 128 +
                       ((static_cast<size_t>(TH) * TW * kFwCB * 2 + 127) / 128) * 128 + 64 + static_cast<size_t>(p.tile_n) * 4;
   if (smem > 113 * 1024) return fail(MAF_E_ARG, "dwpw: %zu B of shared memory needed (C=%d N=%d)", smem, p.C, p.N);
   static bool configured = false;

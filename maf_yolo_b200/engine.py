@@ -145,9 +145,8 @@ class Plan:
         if os.environ.get("MAFB200_DWPW", "1") == "0" or k > 5 or c % 8 or cout % 8 or cout > 128:
             return False
         tile_n = (cout + 15) // 16 * 16
-        kblocks = (c + 63) // 64
         halo = (10 + k - 1) * (20 + k - 1) * 64 * 2
-        return 1024 + 32768 + kblocks * tile_n * 128 + (halo + 127) // 128 * 128 + 64 + tile_n * 4 <= 113 * 1024
+        return 1024 + 32768 + 2 * tile_n * 128 + (halo + 127) // 128 * 128 + 64 + tile_n * 4 <= 113 * 1024
 
     # ---- the schedule ----------------------------------------------------------------------------
     def _plan(self):
