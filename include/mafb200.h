@@ -181,7 +181,7 @@ MAFB200_API int32_t mafb200_nms(const float* pred, int32_t batch, int32_t anchor
 
 /* ---- serving path: decode fused with the NMS threshold / compaction pass -------------------------------
  * mafb200_head_decode_detect = mafb200_head_decode + the first half of mafb200_nms (yolov6/utils/nms.py:48-84) in
- * one kernel: boxes fp32 [n, A, 4] (cx, cy, w, h) and, in `workspace` (size / layout of mafb200_nms), the unordered
+ * one kernel: boxes fp32 [n, A, 4] (cx, cy, w, h; written for candidate rows only when pred is NULL) and, in `workspace` (size / layout of mafb200_nms), the unordered
  * candidate keys + per-image counts.  pred may be NULL — the [n, A, 5+nc] tensor (91 MB at bs32) is then never
  * written nor read back.  mafb200_nms_select = the second half of mafb200_nms (sort + greedy NMS, nms.py:90-100) on
  * those candidates; box_stride = 4 for `boxes`, 5+nc when boxes points at a pred tensor.  Together they give the

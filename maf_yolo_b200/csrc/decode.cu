@@ -62,6 +62,34 @@ __global__ void __launch_bounds__(256) head_decode_kernel(const __grid_constant_
   const int reg_ld = p.reg_ld[lvl];
   const int nreg = 4 * p.bins;
 
+  const __half* cls0 = p.cls[lvl] + (static_cast<size_t>(b) * L + a0) * p.cls_ld[lvl];
+  const bool can_skip = p.emit && p.pred == nullptr;
+  // detect mode: ~99 % of the rows hold no candidate.  Decide that for all 64 rows of the CTA at once on the raw
+  // logits (sigmoid is monotonic; `skip_below` sits a safety margin under logit(conf)): 4 lanes per row, every load of
+  // the CTA in flight together, instead of one dependent row at a time per warp.
+  __shared__ uint8_t s_skip[kAnchorsPerCta];
+  const bool fast_skip = can_skip && (p.nc & 15) == 0 && (p.cls_ld[lvl] & 3) == 0 &&
+                         (reinterpret_cast<uintptr_t>(cls0) & 7) == 0;
+  if (fast_skip) {
+    const int r = threadIdx.x >> 2, q = threadIdx.x & 3;
+    float mz = -INFINITY;
+    if (r < na) {
+      const int per = p.nc >> 2;  // halves per lane, a multiple of 4
+      const uint2* src = reinterpret_cast<const uint2*>(cls0 + static_cast<size_t>(r) * p.cls_ld[lvl] + q * per);
+      for (int i = 0; i < (per >> 2); ++i) {
+        const uint2 u = __ldg(src + i);
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+        const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+        mz = fmaxf(mz, fmaxf(fmaxf(a.x, a.y), fmaxf(c.x, c.y)));
+      }
+    }
+    mz = fmaxf(mz, __shfl_xor_sync(0xffffffffu, mz, 1));
+    mz = fmaxf(mz, __shfl_xor_sync(0xffffffffu, mz, 2));
+    if (q == 0 && r < na) s_skip[r] = mz < p.skip_below ? 1 : 0;
+    // a CTA without a single candidate row (about half of them at conf 0.03) is done: its boxes are never read
+    if (__syncthreads_or(q == 0 && r < na && s_skip[r] == 0) == 0) return;
+  }
+
   // ---- phase 0: stage the reg rows of the CTA's anchors (rows are contiguous: coalesced 16-B loads) ----
   const __half* reg_src = p.reg[lvl] + (static_cast<size_t>(b) * L + a0) * reg_ld;
   const bool fast = (reg_ld & 7) == 0 && (reinterpret_cast<uintptr_t>(reg_src) & 15) == 0 && reg_ld <= 264;
@@ -123,41 +151,14 @@ __global__ void __launch_bounds__(256) head_decode_kernel(const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t row0 = static_cast<size_t>(b) * p.total_anchors + p.anchor_off[lvl] + a0;
   float* dst0 = p.pred != nullptr ? p.pred + row0 * no : nullptr;
-  const __half* cls0 = p.cls[lvl] + (static_cast<size_t>(b) * L + a0) * p.cls_ld[lvl];
   unsigned long long* keys_b = p.emit ? p.keys + static_cast<size_t>(b) * p.cap_pow2 : nullptr;
-  const bool can_skip = p.emit && dst0 == nullptr;
-  // detect mode: ~99 % of the rows hold no candidate.  Decide that for all 64 rows of the CTA at once on the raw
-  // logits (sigmoid is monotonic; `skip_below` sits a safety margin under logit(conf)): 4 lanes per row, every load of
-  // the CTA in flight together, instead of one dependent row at a time per warp.
-  __shared__ uint8_t s_skip[kAnchorsPerCta];
-  const bool fast_skip = can_skip && (p.nc & 15) == 0 && (p.cls_ld[lvl] & 3) == 0 &&
-                         (reinterpret_cast<uintptr_t>(cls0) & 7) == 0;
-  if (fast_skip) {
-    const int r = threadIdx.x >> 2, q = threadIdx.x & 3;
-    float mz = -INFINITY;
-    if (r < na) {
-      const int per = p.nc >> 2;  // halves per lane, a multiple of 4
-      const uint2* src = reinterpret_cast<const uint2*>(cls0 + static_cast<size_t>(r) * p.cls_ld[lvl] + q * per);
-      for (int i = 0; i < (per >> 2); ++i) {
-        const uint2 u = __ldg(src + i);
-        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
-        const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
-        mz = fmaxf(mz, fmaxf(fmaxf(a.x, a.y), fmaxf(c.x, c.y)));
-      }
-    }
-    mz = fmaxf(mz, __shfl_xor_sync(0xffffffffu, mz, 1));
-    mz = fmaxf(mz, __shfl_xor_sync(0xffffffffu, mz, 2));
-    if (q == 0 && r < na) s_skip[r] = mz < p.skip_below ? 1 : 0;
-    __syncthreads();
-  }
   for (int al = warp; al < na; al += 8) {
     float* dst = dst0 != nullptr ? dst0 + static_cast<size_t>(al) * no : nullptr;
     const __half* cls = cls0 + static_cast<size_t>(al) * p.cls_ld[lvl];
+    if (fast_skip && s_skip[al]) continue;
     if (p.boxes != nullptr && lane == 0)
       *reinterpret_cast<float4*>(p.boxes + (row0 + al) * 4) = make_float4(s_box[al][0], s_box[al][1], s_box[al][2], s_box[al][3]);
-    if (fast_skip) {
-      if (s_skip[al]) continue;
-    } else if (can_skip) {
+    if (!fast_skip && can_skip) {
       float mz = -INFINITY;
       for (int c = lane; c < p.nc; c += 32) mz = fmaxf(mz, __half2float(__ldg(cls + c)));
 #pragma unroll

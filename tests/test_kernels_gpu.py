@@ -415,7 +415,7 @@ def test_decode_detect_equals_decode_then_nms(cuda_device, kw):
     kw2 = dict(kw)
     want_det, want_cnt = mnn.non_max_suppression_padded(pred, **kw2)
     ref = onms.non_max_suppression(pred.cpu().numpy(), **kw)
-    boxes = torch.empty((n, a, 4), device=cuda_device)
+    boxes = torch.full((n, a, 4), float("nan"), device=cuda_device)
     ws = torch.empty((ops.nms_workspace_bytes(n, a, nc) + 7) // 8, dtype=torch.int64, device=cuda_device)
     filt = None
     if kw.get("classes") is not None:
@@ -427,7 +427,8 @@ def test_decode_detect_equals_decode_then_nms(cuda_device, kw):
     cnt = torch.full((n,), -1, dtype=torch.int32, device=cuda_device)
     ops.nms_select(boxes, nc, kw["iou_thres"], kw.get("agnostic", False), kw.get("max_det", 300), 30000, det, cnt, ws)
     torch.cuda.synchronize()
-    assert torch.equal(boxes, pred[..., :4])
+    cand = pred[..., 5:].max(-1).values > kw["conf_thres"]  # boxes are only defined (and only read) for candidate rows
+    assert torch.equal(boxes[cand], pred[..., :4][cand]) and int(cand.sum()) > 0
     assert torch.equal(cnt, want_cnt) and torch.equal(det, want_det)
     for i, r in enumerate(ref):
         assert np.array_equal(det[i, :int(cnt[i])].cpu().numpy(), r)
