@@ -46,11 +46,14 @@ struct DecodeParams {
 
 constexpr int kRowBuf = 160;  // floats per warp: one output row (5 + nc <= 160 in detect mode)
 
+// kDetect = false: the reference-shaped decode (writes pred); true: detect mode (candidate filter fused in).  Two
+// instantiations so that the plain path carries neither the extra shared memory nor the extra branches.
+template <bool kDetect>
 __global__ void __launch_bounds__(256) head_decode_kernel(const __grid_constant__ DecodeParams p) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float s_box[kAnchorsPerCta][4];
-  __shared__ float s_row[8][kRowBuf];  // detect mode: the row a warp just decoded, read back by the candidate filter
+  __shared__ float s_row[kDetect ? 8 : 1][kDetect ? kRowBuf : 1];  // detect mode: the row a warp just decoded, read back by the filter
   __shared__ __align__(16) __half s_reg[kAnchorsPerCta * 264];  // up to 4*(63+1)=256 (+pad) halves per anchor
   const int b = blockIdx.y;
   int lvl = 0;
@@ -63,11 +66,11 @@ __global__ void __launch_bounds__(256) head_decode_kernel(const __grid_constant_
   const int nreg = 4 * p.bins;
 
   const __half* cls0 = p.cls[lvl] + (static_cast<size_t>(b) * L + a0) * p.cls_ld[lvl];
-  const bool can_skip = p.emit && p.pred == nullptr;
+  const bool can_skip = kDetect && p.emit && p.pred == nullptr;
   // detect mode: ~99 % of the rows hold no candidate.  Decide that for all 64 rows of the CTA at once on the raw
   // logits (sigmoid is monotonic; `skip_below` sits a safety margin under logit(conf)): 4 lanes per row, every load of
   // the CTA in flight together, instead of one dependent row at a time per warp.
-  __shared__ uint8_t s_skip[kAnchorsPerCta];
+  __shared__ uint8_t s_skip[kDetect ? kAnchorsPerCta : 1];
   const bool fast_skip = can_skip && (p.nc & 15) == 0 && (p.cls_ld[lvl] & 3) == 0 &&
                          (reinterpret_cast<uintptr_t>(cls0) & 7) == 0;
   if (fast_skip) {
@@ -151,12 +154,12 @@ __global__ void __launch_bounds__(256) head_decode_kernel(const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t row0 = static_cast<size_t>(b) * p.total_anchors + p.anchor_off[lvl] + a0;
   float* dst0 = p.pred != nullptr ? p.pred + row0 * no : nullptr;
-  unsigned long long* keys_b = p.emit ? p.keys + static_cast<size_t>(b) * p.cap_pow2 : nullptr;
+  unsigned long long* keys_b = (kDetect && p.emit) ? p.keys + static_cast<size_t>(b) * p.cap_pow2 : nullptr;
   for (int al = warp; al < na; al += 8) {
     float* dst = dst0 != nullptr ? dst0 + static_cast<size_t>(al) * no : nullptr;
     const __half* cls = cls0 + static_cast<size_t>(al) * p.cls_ld[lvl];
     if (fast_skip && s_skip[al]) continue;
-    if (p.boxes != nullptr && lane == 0)
+    if (kDetect && p.boxes != nullptr && lane == 0)
       *reinterpret_cast<float4*>(p.boxes + (row0 + al) * 4) = make_float4(s_box[al][0], s_box[al][1], s_box[al][2], s_box[al][3]);
     if (!fast_skip && can_skip) {
       float mz = -INFINITY;
@@ -176,9 +179,9 @@ __global__ void __launch_bounds__(256) head_decode_kernel(const __grid_constant_
         v = p.cls_is_prob ? z : __fdividef(1.0f, 1.0f + __expf(-z));
       }
       if (dst != nullptr) dst[j] = v;
-      if (p.emit) s_row[warp][j] = v;
+      if (kDetect && p.emit) s_row[warp][j] = v;
     }
-    if (p.emit) {
+    if (kDetect && p.emit) {
       // the same fp32 values the reference-shaped path would read back from `pred`, so the candidate set is identical
       __syncwarp();
       nms_filter_row(s_row[warp], p.anchor_off[lvl] + a0 + al, p.nc, p.conf, p.multi_label, p.class_filter, &p.ncand[b],
@@ -286,8 +289,8 @@ static int32_t decode_common(const maf_tensor* cls_logits, const maf_tensor* reg
   int32_t rc = require_sm100();
   if (rc) return rc;
   if (p.emit)  // follows a memset node, not a kernel: plain stream-ordered launch
-    launch_pdl<false>(head_decode_kernel, dim3(ctas, n), dim3(256), 0, static_cast<cudaStream_t>(stream), p);
+    launch_pdl<false>(head_decode_kernel<true>, dim3(ctas, n), dim3(256), 0, static_cast<cudaStream_t>(stream), p);
   else
-    launch_pdl(head_decode_kernel, dim3(ctas, n), dim3(256), 0, static_cast<cudaStream_t>(stream), p);
+    launch_pdl(head_decode_kernel<false>, dim3(ctas, n), dim3(256), 0, static_cast<cudaStream_t>(stream), p);
   return check_launch("head_decode kernel launch");
 }
