@@ -376,7 +376,7 @@ def run_ours(a):
     kernel_names = {"conv1x1": "gemm_tc_kernel<false> (1x1 conv / fusion-stage GEMM, tcgen05+TMA)",
                     "conv3x3s2": "gemm_tc_kernel<true> (3x3 s2 implicit GEMM, tcgen05 + im2col TMA)",
                     "dwconv": "dwconv_kernel (depth-wise k x k)", "dwpw": "dwpw_kernel (depth-wise k x k + 1x1 fused)", "stem": "stem_conv_kernel",
-                    "maxpool2x2": "maxpool2x2_kernel", "sppf_pool": "sppf_pool_kernel", "decode": "head_decode_kernel"}
+                    "maxpool2x2": "maxpool2x2_kernel", "poolpw": "poolpw_kernel (2x2 max pool + 1x1 fused)", "sppf_pool": "sppf_pool_kernel", "decode": "head_decode_kernel"}
     roofline = {
         "bound": "hbm", "kernel": kernel_names.get(top, top), "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
         "frac": round(achieved / peak, 4), "traffic": profiled_traffic(top, a.variant, B), "peak_source": peak_src,

@@ -146,6 +146,13 @@ MAFB200_API int32_t mafb200_dwconv_conv1x1(const maf_tensor* src, const float* d
                                int32_t act1, const void* pw_packed, const float* pw_bias, int32_t act2,
                                const maf_tensor* dst, void* stream);
 
+/* ---- 2x2 max pool fused with the 1x1 conv that consumes it (C <= 256, cout <= 128) ------------------------
+ * dst = act(W * maxpool2x2(src) + bias): the first branch of MPRep, conv1(mp(x)) (common.py:787-792, MP at
+ * common.py:667-673); the pooled map never goes to HBM.  packed / bias as for mafb200_conv1x1 with one source of
+ * src->c channels; even h and w; dst [n, h/2, w/2, cout], 32-B aligned with c_stride % 16 == 0. */
+MAFB200_API int32_t mafb200_maxpool2x2_conv1x1(const maf_tensor* src, const void* packed, const float* bias, int32_t act,
+                                   const maf_tensor* dst, void* stream);
+
 /* ---- pooling / resampling ------------------------------------------------------------------- */
 MAFB200_API int32_t mafb200_maxpool2x2(const maf_tensor* src, const maf_tensor* dst, void* stream);
 /* y1 = maxpool5(x), y2 = maxpool5(y1), y3 = maxpool5(y2) (stride 1, pad 2, -inf padding). */

@@ -16,7 +16,7 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libmafb200.so"
-SOURCES = ["host.cu", "gemm_tc.cu", "stem_conv.cu", "dwconv.cu", "dwconv_tc.cu", "dwpw.cu", "pool.cu", "decode.cu", "nms.cu", "postprocess.cu", "preprocess.cu"]
+SOURCES = ["host.cu", "gemm_tc.cu", "stem_conv.cu", "dwconv.cu", "dwconv_tc.cu", "dwpw.cu", "poolpw.cu", "pool.cu", "decode.cu", "nms.cu", "postprocess.cu", "preprocess.cu"]
 EXTRA = os.environ.get("MAFB200_NVCC_EXTRA", "").split()
 NVCC_FLAGS = EXTRA + [
     "-gencode", "arch=compute_100a,code=sm_100a",

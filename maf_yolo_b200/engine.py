@@ -115,6 +115,8 @@ class Plan:
             op.flops_per_image = 2 * 9 * reads[0].c * writes[0].c * px_out
         elif kind == "dwconv":
             op.flops_per_image = 2 * kw["k"] * kw["k"] * writes[0].c * px_out
+        elif kind == "poolpw":
+            op.flops_per_image = 2 * reads[0].c * writes[0].c * px_out
         elif kind == "dwpw":
             op.flops_per_image = 2 * kw["k"] * kw["k"] * reads[0].c * px_out + 2 * reads[0].c * writes[0].c * px_out
         self.ops.append(op)
@@ -223,11 +225,15 @@ class Plan:
             elif l.kind == "mprep":
                 h, w = size(l)
                 src = out[l.frm[0]]
-                pooled = self._buf(h, w, l.c_in[0], f"L{i}.pool")
-                self._emit("maxpool2x2", f"L{i}.maxpool", [src], [pooled])
                 dst = self._buf(h, w, l.c_out, f"L{i}")
                 half = l.c_out // 2
-                self._emit("conv1x1", f"L{i}.conv1", [pooled], [dst.slice(0, half)], weight=i + ".conv1", act="silu")
+                if (os.environ.get("MAFB200_POOLPW", "1") != "0" and l.c_in[0] <= 256 and l.c_in[0] % 8 == 0 and
+                        half <= 128 and half % 8 == 0):  # max pool + conv1 in one kernel: no pooled map in HBM
+                    self._emit("poolpw", f"L{i}.maxpool+conv1", [src], [dst.slice(0, half)], weight=i + ".conv1", act="silu")
+                else:
+                    pooled = self._buf(h, w, l.c_in[0], f"L{i}.pool")
+                    self._emit("maxpool2x2", f"L{i}.maxpool", [src], [pooled])
+                    self._emit("conv1x1", f"L{i}.conv1", [pooled], [dst.slice(0, half)], weight=i + ".conv1", act="silu")
                 self._emit("conv3x3s2", f"L{i}.repvgg3x3s2", [src], [dst.slice(half, half)], weight=i + ".conv2",
                            act="relu")
                 out[l.i] = dst
@@ -422,6 +428,11 @@ class Engine:
             w, b = ops.pack_dw(wt, bs, device=dev)
             self._weights[op.name] = (w, b)
             return lambda: ops.dwconv(reads[0], w, b, op.k, op.act, writes[0])
+        if op.kind == "poolpw":
+            wt, bs = folded[op.weight]
+            w, b = ops.pack_conv1x1(wt.reshape(wt.shape[0], -1), bs, [reads[0].c], device=dev)
+            self._weights[op.name] = (w, b)
+            return lambda: ops.maxpool2x2_conv1x1(reads[0], w, b, op.act, writes[0])
         if op.kind == "maxpool2x2":
             return lambda: ops.maxpool2x2(reads[0], writes[0])
         if op.kind == "sppf_pool":

@@ -194,6 +194,11 @@ def dwconv_conv1x1(src: NHWC, dw_w: torch.Tensor, dw_b: torch.Tensor, k: int, ac
                                        pw_b.data_ptr(), _act(act2), dst.ref(), _stream()))
 
 
+def maxpool2x2_conv1x1(src: NHWC, w: torch.Tensor, b: torch.Tensor, act, dst: NHWC) -> None:
+    """2x2 stride-2 max pool fused with the 1x1 conv (+bias, act) that consumes it (MPRep's first branch)."""
+    check(lib().mafb200_maxpool2x2_conv1x1(src.ref(), w.data_ptr(), b.data_ptr(), _act(act), dst.ref(), _stream()))
+
+
 def maxpool2x2(src: NHWC, dst: NHWC) -> None:
     check(lib().mafb200_maxpool2x2(src.ref(), dst.ref(), _stream()))
 

@@ -228,7 +228,10 @@ def test_dwconv_tc(cuda_device, c, k, h, w, n, act):
 
 @pytest.mark.parametrize("c,cout,k,h,w,n,act1,act2", [(192, 64, 5, 40, 40, 2, "silu", "silu"), (128, 128, 5, 24, 30, 1, "none", "silu"),
                                                       (72, 24, 3, 40, 40, 1, "silu", "silu"), (64, 32, 3, 7, 9, 2, "relu", "none"),
-                                                      (144, 48, 5, 20, 20, 2, "silu", "silu"), (192, 64, 5, 80, 80, 1, "silu", "silu")])
+                                                      (144, 48, 5, 20, 20, 2, "silu", "silu"), (192, 64, 5, 80, 80, 1, "silu", "silu"),
+                                                      # k = 3 with 2, 3 and 4 channel blocks (the halo buffer and both W2 slots are reused)
+                                                      (144, 24, 3, 33, 41, 2, "silu", "silu"), (256, 32, 3, 20, 20, 1, "silu", "none"),
+                                                      (96, 32, 3, 160, 160, 1, "silu", "silu"), (72, 64, 3, 20, 20, 1, "silu", "silu")])
 def test_dwconv_conv1x1_fused(cuda_device, c, cout, k, h, w, n, act1, act2):
     """Fused depth-wise -> 1x1 kernel against the two reference ops in fp32 (the intermediate is rounded to fp16 once,
     exactly as the two separate kernels do)."""
@@ -249,6 +252,31 @@ def test_dwconv_conv1x1_fused(cuda_device, c, cout, k, h, w, n, act1, act2):
     ops.dwconv_conv1x1(src, dwp, dbp, k, act1, pwp, pbp, act2, dst)
     torch.cuda.synchronize()
     _close(dst.to_nchw(), ref, f"dwconv_conv1x1 c={c}->{cout} k={k}", rtol=3e-3, atol=3e-3)
+
+
+@pytest.mark.parametrize("c,cout,h,w,n,act,wide", [(48, 48, 40, 40, 2, "silu", True), (96, 96, 20, 24, 3, "silu", True),
+                                                   (256, 128, 16, 16, 2, "silu", False), (48, 24, 10, 14, 1, "none", False),
+                                                   (64, 48, 160, 160, 2, "silu", True), (192, 96, 40, 40, 1, "relu", True)])
+def test_maxpool2x2_conv1x1_fused(cuda_device, c, cout, h, w, n, act, wide):
+    """Fused 2x2 max pool -> 1x1 kernel against the two reference ops in fp32 (max of fp16 values is exact).  `wide`:
+    the output is the first half of a 2*cout-wide buffer (MPRep's concat); the other half must stay untouched."""
+    from maf_yolo_b200 import ops
+
+    g = torch.Generator().manual_seed(91 + c + cout)
+    x = torch.randn(n, c, h, w, generator=g).half().float()
+    pw_w = (torch.randn(cout, c, generator=g) / c ** 0.5).half().float()
+    pw_b = torch.randn(cout, generator=g)
+    ref = _act_ref(F.conv2d(F.max_pool2d(x, 2, 2), pw_w[:, :, None, None], pw_b), act)
+    src = ops.NHWC.from_nchw(x.to(cuda_device))
+    wp, bp = ops.pack_conv1x1(pw_w, pw_b, [c], cuda_device)
+    full = ops.NHWC.empty(n, h // 2, w // 2, 2 * cout if wide else cout, cuda_device,
+                          ld=((2 * cout if wide else cout) + 15) // 16 * 16)
+    full.buf.fill_(7.0)
+    dst = full.slice(0, cout)
+    ops.maxpool2x2_conv1x1(src, wp, bp, act, dst)
+    torch.cuda.synchronize()
+    _close(dst.to_nchw(), ref, f"maxpool2x2_conv1x1 c={c}->{cout}", rtol=3e-3, atol=3e-3)
+    assert (full.buf[..., cout:] == 7.0).all(), "maxpool2x2_conv1x1 wrote outside its channels"
 
 
 def test_pool_upsample_layout(cuda_device):
