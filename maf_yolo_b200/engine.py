@@ -34,10 +34,10 @@ def _ld(c: int) -> int:
 
 
 class _Buf:
-    __slots__ = ("h", "w", "ld", "first", "last", "offset", "name")
+    __slots__ = ("h", "w", "c", "ld", "first", "last", "offset", "name")
 
     def __init__(self, h, w, c, name):
-        self.h, self.w, self.ld, self.name = h, w, _ld(c), name
+        self.h, self.w, self.c, self.ld, self.name = h, w, c, _ld(c), name
         self.first, self.last, self.offset = None, None, None
 
     def touch(self, idx):
@@ -384,16 +384,35 @@ class Engine:
             self._views[key] = hit
         return hit
 
+    def _pad_fill(self, op: _Op, act: str, wt: torch.Tensor, bs: torch.Tensor):
+        """Whole-sector output rows.  When the op writes the LAST channels of a buffer whose channel stride is wider
+        (24 of 32, 72 of 80) and they end in the middle of a 32-byte sector, every pixel's last store is half a sector:
+        a slow 16-byte store and a DRAM read-modify-write (ncu: the stem read 96 MB more than its input).  The padding
+        channels belong to nobody, so give the op zero filters for them: act(0) = 0 lands there at no cost (the column
+        tile is already that wide).  Returns (output view, weight, bias), extended or as they were."""
+        v = op.writes[0]
+        b = v.buf
+        extra = b.ld - b.c if v.c_off + v.c == b.c else 0
+        if (extra <= 0 or len(op.writes) != 1 or act == "sigmoid" or ((v.c_off + v.c) * 2) % 32 == 0 or
+                os.environ.get("MAFB200_PAD_FILL", "1") == "0"):
+            return self.view(v), wt, bs
+        wt = torch.cat([wt, wt.new_zeros((extra,) + tuple(wt.shape[1:]))])
+        bs = torch.cat([bs, bs.new_zeros(extra)])
+        return self.view(_View(b, v.c_off, v.c + extra)), wt, bs
+
     def _bind(self, op: _Op, folded: Folded) -> Callable[[], None]:
         dev = self.device
         reads = [self.view(v) for v in op.reads]
         writes = [self.view(v) for v in op.writes]
         if op.kind == "stem":
-            w, b = ops.pack_stem(*folded[op.weight], device=dev)
+            dst, wt, bs = self._pad_fill(op, op.act, *folded[op.weight])
+            w, b = ops.pack_stem(wt, bs, device=dev)
             self._weights[op.name] = (w, b)
-            return lambda: ops.stem_conv3x3s2(self._x, w, b, op.act, writes[0])
+            return lambda: ops.stem_conv3x3s2(self._x, w, b, op.act, dst)
         if op.kind == "conv1x1":
             wt, bs = folded[op.weight]
+            if len(writes) == 1:
+                writes[0], wt, bs = self._pad_fill(op, op.act, wt, bs)
             w, b = ops.pack_conv1x1(wt.reshape(wt.shape[0], -1), bs, [r.c for r in reads], device=dev)
             self._weights[op.name] = (w, b)
             up = writes[1] if len(writes) > 1 else None
@@ -412,10 +431,10 @@ class Engine:
             return lambda: ops.conv3x3s2(reads[0], w, b, op.act, writes[0])
         if op.kind == "dwpw":
             dw_w, dw_b = ops.pack_dw(*folded[op.weight], device=dev)
-            wt2, bs2 = folded[op.weight2]
+            dst, wt2, bs2 = self._pad_fill(op, op.act2, *folded[op.weight2])
             pw_w, pw_b = ops.pack_conv1x1(wt2.reshape(wt2.shape[0], -1), bs2, [reads[0].c], device=dev)
             self._weights[op.name] = (dw_w, dw_b, pw_w, pw_b)
-            return lambda: ops.dwconv_conv1x1(reads[0], dw_w, dw_b, op.k, op.act, pw_w, pw_b, op.act2, writes[0])
+            return lambda: ops.dwconv_conv1x1(reads[0], dw_w, dw_b, op.k, op.act, pw_w, pw_b, op.act2, dst)
         if op.kind == "dwconv":
             wt, bs = folded[op.weight]
             if op.wslice is not None:
@@ -429,10 +448,10 @@ class Engine:
             self._weights[op.name] = (w, b)
             return lambda: ops.dwconv(reads[0], w, b, op.k, op.act, writes[0])
         if op.kind == "poolpw":
-            wt, bs = folded[op.weight]
+            dst, wt, bs = self._pad_fill(op, op.act, *folded[op.weight])
             w, b = ops.pack_conv1x1(wt.reshape(wt.shape[0], -1), bs, [reads[0].c], device=dev)
             self._weights[op.name] = (w, b)
-            return lambda: ops.maxpool2x2_conv1x1(reads[0], w, b, op.act, writes[0])
+            return lambda: ops.maxpool2x2_conv1x1(reads[0], w, b, op.act, dst)
         if op.kind == "maxpool2x2":
             return lambda: ops.maxpool2x2(reads[0], writes[0])
         if op.kind == "sppf_pool":
