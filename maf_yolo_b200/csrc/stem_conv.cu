@@ -21,37 +21,43 @@ namespace mafb200 {
 // `lut` (shared memory, 256 floats = u / 255.0f computed once per CTA with the fp32 division the reference
 // performs, evaler.py:163) is only read by the uint8 specialisations: one LDS instead of an IEEE division
 // (~10 instructions) per input element — the uint8 path was 0.1 ms per forward slower than fp32 without it.
+// Raw loads and their conversion are separate so that ALL loads of a tile can be issued before the first use (and a
+// whole tile ahead, see the kernel): Raw<T>::px = one pixel, Raw<T>::pair = the aligned pixel pair (2*ox, 2*ox+1).
 template <typename T>
-__device__ __forceinline__ float load_px(const T* p, const float* lut);
+struct Raw;
 template <>
-__device__ __forceinline__ float load_px<float>(const float* p, const float*) {
-  return __ldg(p);
-}
+struct Raw<float> {
+  using px = float;
+  using pair = float2;
+  static __device__ __forceinline__ px zero_px() { return 0.f; }
+  static __device__ __forceinline__ pair zero_pair() { return make_float2(0.f, 0.f); }
+  static __device__ __forceinline__ px ld_px(const float* p) { return __ldg(p); }
+  static __device__ __forceinline__ pair ld_pair(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+  static __device__ __forceinline__ float cvt(px v, const float*) { return v; }
+  static __device__ __forceinline__ float2 cvt(pair v, const float*) { return v; }
+};
 template <>
-__device__ __forceinline__ float load_px<__half>(const __half* p, const float*) {
-  return __half2float(__ldg(p));
-}
+struct Raw<__half> {
+  using px = __half;
+  using pair = __half2;
+  static __device__ __forceinline__ px zero_px() { return __float2half(0.f); }
+  static __device__ __forceinline__ pair zero_pair() { return __floats2half2_rn(0.f, 0.f); }
+  static __device__ __forceinline__ px ld_px(const __half* p) { return __ldg(p); }
+  static __device__ __forceinline__ pair ld_pair(const __half* p) { return __ldg(reinterpret_cast<const __half2*>(p)); }
+  static __device__ __forceinline__ float cvt(px v, const float*) { return __half2float(v); }
+  static __device__ __forceinline__ float2 cvt(pair v, const float*) { return __half22float2(v); }
+};
 template <>
-__device__ __forceinline__ float load_px<uint8_t>(const uint8_t* p, const float* lut) {
-  return lut[__ldg(p)];
-}
-
-// (x[2*ox], x[2*ox+1]) as one aligned vector load: lanes of a warp read one contiguous row segment
-template <typename T>
-__device__ __forceinline__ float2 load_pair(const T* p, const float* lut);
-template <>
-__device__ __forceinline__ float2 load_pair<float>(const float* p, const float*) {
-  return __ldg(reinterpret_cast<const float2*>(p));
-}
-template <>
-__device__ __forceinline__ float2 load_pair<__half>(const __half* p, const float*) {
-  return __half22float2(__ldg(reinterpret_cast<const __half2*>(p)));
-}
-template <>
-__device__ __forceinline__ float2 load_pair<uint8_t>(const uint8_t* p, const float* lut) {
-  const uchar2 u = __ldg(reinterpret_cast<const uchar2*>(p));
-  return make_float2(lut[u.x], lut[u.y]);
-}
+struct Raw<uint8_t> {
+  using px = uint8_t;
+  using pair = uchar2;
+  static __device__ __forceinline__ px zero_px() { return 0; }
+  static __device__ __forceinline__ pair zero_pair() { return make_uchar2(0, 0); }
+  static __device__ __forceinline__ px ld_px(const uint8_t* p) { return __ldg(p); }
+  static __device__ __forceinline__ pair ld_pair(const uint8_t* p) { return __ldg(reinterpret_cast<const uchar2*>(p)); }
+  static __device__ __forceinline__ float cvt(px v, const float* lut) { return lut[v]; }
+  static __device__ __forceinline__ float2 cvt(pair v, const float* lut) { return make_float2(lut[v.x], lut[v.y]); }
+};
 
 constexpr int kStemK = 32;                 // 27 taps padded to 2 x UMMA_K
 constexpr uint32_t kStemLBO = 128;         // bytes between the two 8-element K chunks of one core-matrix row group
@@ -71,7 +77,7 @@ __device__ __forceinline__ uint64_t umma_smem_desc_noswz(uint32_t smem_addr) {
 __device__ __forceinline__ uint32_t stem_off(int r, int kc) { return (r >> 3) * kStemSBO + kc * kStemLBO + (r & 7) * 16; }
 
 template <typename T>
-__global__ void __launch_bounds__(128) stem_conv_kernel(const T* __restrict__ x, const float* __restrict__ wgt,
+__global__ void __launch_bounds__(128, 8) stem_conv_kernel(const T* __restrict__ x, const float* __restrict__ wgt,
                                                          const float* __restrict__ bias, __half* __restrict__ out,
                                                          int n, int h, int w, int cout, int tile_n, int tmem_cols,
                                                          uint32_t idesc, int out_ld, int act, int st256) {
@@ -126,24 +132,23 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const T* __restrict__ x,
   const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
 
   // Persistent CTA: TMEM, barrier and the B operand are set up once; loop over 128-pixel tiles.
-  uint32_t phase = 0;
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, phase ^= 1) {
-  const long long idx = tile * 128 + t;
-  // A operand: one output pixel per thread, 27 taps in (ky, kx, ci) order
-  {
-    float v[kStemK];
-#pragma unroll
-    for (int k = 27; k < kStemK; ++k) v[k] = 0.0f;
-    // Taps kx = 1,2 of output pixel ox are the aligned pair (2*ox, 2*ox+1); tap kx = 0 (pixel 2*ox-1) is
-    // the left neighbour lane's second element (warp shuffle) — 9 coalesced vector loads per thread
-    // instead of 27 strided scalar ones.  (w is even, so the pair never crosses the row end.)
-    const bool live = idx < total;
-    const long long cidx = live ? idx : total - 1;
+  // One output pixel per thread, 27 taps in (ky, kx, ci) order.  Taps kx = 1,2 of output pixel ox are the aligned pair
+  // (2*ox, 2*ox+1); tap kx = 0 (pixel 2*ox-1) is the left neighbour lane's second element (warp shuffle) — 9 coalesced
+  // vector loads per thread instead of 27 strided scalar ones (w is even, so the pair never crosses the row end).
+  // The loads of tile i+1 are issued right after the MMA of tile i, so their latency hides behind the epilogue (ncu
+  // had half of the stall samples on the first use of each load group).
+  const int lane = t & 31;
+  typename Raw<T>::pair pr[9];
+  typename Raw<T>::px lf[9];
+  bool from_lane = false;
+  auto issue_loads = [&](long long tile) {
+    const long long idx = tile * 128 + t;
+    const long long cidx = idx < total ? idx : total - 1;
     const int ox = static_cast<int>(cidx % wo);
     const int oy = static_cast<int>((cidx / wo) % ho);
     const int b = static_cast<int>(cidx / (static_cast<long long>(wo) * ho));
-    const int lane = t & 31;
-    const bool from_lane = lane > 0 && ox > 0;  // lane-1 then holds output pixel ox-1 of the same row
+    from_lane = lane > 0 && ox > 0;  // lane-1 then holds output pixel ox-1 of the same row
+    const bool need_left = lane == 0 && ox > 0;  // ox == 0: the tap is padding
     const T* xb = x + static_cast<size_t>(b) * 3 * h * w;
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
@@ -152,16 +157,30 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const T* __restrict__ x,
 #pragma unroll
       for (int ci = 0; ci < 3; ++ci) {
         const T* rowp = xb + (static_cast<size_t>(ci) * h + (row_ok ? iy : 0)) * w + 2 * ox;
-        float2 pr = make_float2(0.f, 0.f);
-        if (row_ok) pr = load_pair<T>(rowp, s_lut);
-        float left = __shfl_up_sync(0xffffffffu, pr.y, 1);
-        if (!from_lane) left = (row_ok && ox > 0) ? load_px<T>(rowp - 1, s_lut) : 0.0f;
-        v[(ky * 3 + 0) * 3 + ci] = left;
-        v[(ky * 3 + 1) * 3 + ci] = pr.x;
-        v[(ky * 3 + 2) * 3 + ci] = pr.y;
+        pr[ky * 3 + ci] = row_ok ? Raw<T>::ld_pair(rowp) : Raw<T>::zero_pair();
+        lf[ky * 3 + ci] = (row_ok && need_left) ? Raw<T>::ld_px(rowp - 1) : Raw<T>::zero_px();
       }
     }
-    (void)live;
+  };
+
+  uint32_t phase = 0;
+  if (blockIdx.x < n_tiles) issue_loads(blockIdx.x);
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, phase ^= 1) {
+  const long long idx = tile * 128 + t;
+  {
+    float v[kStemK];
+#pragma unroll
+    for (int k = 27; k < kStemK; ++k) v[k] = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {  // j = ky * 3 + ci
+      const float2 p2 = Raw<T>::cvt(pr[j], s_lut);
+      float left = __shfl_up_sync(0xffffffffu, p2.y, 1);
+      if (!from_lane) left = Raw<T>::cvt(lf[j], s_lut);
+      const int ky = j / 3, ci = j - 3 * ky;
+      v[(ky * 3 + 0) * 3 + ci] = left;
+      v[(ky * 3 + 1) * 3 + ci] = p2.x;
+      v[(ky * 3 + 2) * 3 + ci] = p2.y;
+    }
 #pragma unroll
     for (int kc = 0; kc < 4; ++kc) {
       *reinterpret_cast<uint4*>(s_a + stem_off(t, kc)) =
@@ -182,6 +201,7 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const T* __restrict__ x,
     }
     tc_commit(&s_bar);
   }
+  if (tile + gridDim.x < n_tiles) issue_loads(tile + gridDim.x);  // next tile's inputs: in flight during the epilogue
   __syncwarp();
   mbar_wait(&s_bar, phase);
   tc_fence_after_sync();
