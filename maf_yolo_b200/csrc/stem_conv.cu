@@ -143,10 +143,11 @@ __global__ void __launch_bounds__(128, 8) stem_conv_kernel(const T* __restrict__
   bool from_lane = false;
   auto issue_loads = [&](long long tile) {
     const long long idx = tile * 128 + t;
-    const long long cidx = idx < total ? idx : total - 1;
-    const int ox = static_cast<int>(cidx % wo);
-    const int oy = static_cast<int>((cidx / wo) % ho);
-    const int b = static_cast<int>(cidx / (static_cast<long long>(wo) * ho));
+    const uint32_t cidx = static_cast<uint32_t>(idx < total ? idx : total - 1);  // total < 2^31 (checked by the host)
+    const uint32_t row = cidx / static_cast<uint32_t>(wo);                       // 32-bit divisions: 3x fewer instructions
+    const int ox = static_cast<int>(cidx - row * static_cast<uint32_t>(wo));
+    const int b = static_cast<int>(row / static_cast<uint32_t>(ho));
+    const int oy = static_cast<int>(row - static_cast<uint32_t>(b) * static_cast<uint32_t>(ho));
     from_lane = lane > 0 && ox > 0;  // lane-1 then holds output pixel ox-1 of the same row
     const bool need_left = lane == 0 && ox > 0;  // ox == 0: the tap is padding
     const T* xb = x + static_cast<size_t>(b) * 3 * h * w;
@@ -280,6 +281,7 @@ extern "C" int32_t mafb200_stem_conv3x3s2(const void* x_nchw, int32_t x_dtype, i
   while (tmem_cols < tile_n) tmem_cols <<= 1;
   const uint32_t idesc = umma_idesc_f16(128, tile_n);
   const long long total = static_cast<long long>(n) * (h / 2) * (w / 2);
+  if (total >= (1ll << 31)) return fail(MAF_E_ARG, "stem_conv: %lld output pixels (limit 2^31 - 1)", total);
   const long long tiles = (total + 127) / 128;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
