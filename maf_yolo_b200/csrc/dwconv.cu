@@ -132,9 +132,22 @@ __global__ void __launch_bounds__(128)
     if (ch_ok) bv = __ldg(reinterpret_cast<const float2*>(bias + c0 + 2 * pair));
     __syncthreads();  // mbarrier init visible to all threads before they wait on it
   } else {
-    for (int i = threadIdx.x; i < K * K * CB; i += blockDim.x) {
-      const int t = i / CB, c = i - t * CB;
-      s_w[i] = (c0 + c < C) ? __ldg(wgt + static_cast<size_t>(t) * C + c0 + c) : 0.0f;
+    // All of the thread's weight loads are issued before the first store (compile-time trip count, 8-byte loads): a
+    // rolled 4-byte loop was K*K*CB/128 = 13-20 DEPENDENT L2 round trips in front of every CTA's taps.
+    constexpr int kW2 = K * K * CB / 2;
+    constexpr int kWIters = (kW2 + 127) / 128;
+    float2 wtmp[kWIters];
+#pragma unroll
+    for (int it = 0; it < kWIters; ++it) {
+      const int i = threadIdx.x + it * 128;
+      const int t = i / (CB / 2), c = 2 * (i - t * (CB / 2));
+      wtmp[it] = (i < kW2 && c0 + c < C) ? __ldg(reinterpret_cast<const float2*>(wgt + static_cast<size_t>(t) * C + c0 + c))
+                                         : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int it = 0; it < kWIters; ++it) {
+      const int i = threadIdx.x + it * 128;
+      if (i < kW2) *reinterpret_cast<float2*>(s_w + 2 * i) = wtmp[it];
     }
     for (int i = threadIdx.x; i < CB; i += blockDim.x) s_b[i] = (c0 + i < C) ? __ldg(bias + c0 + i) : 0.0f;
     __syncthreads();
