@@ -110,7 +110,7 @@ def run_reference_arm(a):
                                    f"{cores} threads), {a.cpu_sample} images/step x {a.steps} steps"},
         "e2e": {"value": round(value, 3), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -218,7 +218,6 @@ def run_ours(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
     _lib.check(_lib.lib().mafb200_device_ok(-1))
 
@@ -419,15 +418,38 @@ def run_ours(a):
         "host_enqueue_ms_per_step": {"value_loop": round(host_enqueue_ms, 4), "e2e_loop": round(host_enqueue_e2e_ms, 4)},
         "clocks": clocks, "roofline": roofline, "whole_step": whole, "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
+_JSON_FD = None
+
+
+def _own_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL's version banner, warnings from
+    extensions), so from here on file descriptor 1 points at stderr and the JSON line goes to the saved original."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, data)
+
+
 def main():
     a = parse_args()
+    _own_stdout()
     if a.impl == "reference":
         return run_reference_arm(a)
     return run_ours(a)
