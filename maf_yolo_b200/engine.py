@@ -76,6 +76,19 @@ class _Op:
     bytes_per_image: int = 0   # algorithmic: activations read once + written once (fp16), weights excluded
 
 
+def pad_fill_channels(op: "_Op", act: str) -> int:
+    """How many padding channels behind the op's output it may fill with zeros (Engine._pad_fill): the op must be the
+    only writer of the LAST channels of its buffer, those must end inside a 32-byte sector, the channel stride must be
+    wider than the buffer's channels, and act(0) must be 0 (not sigmoid).  MAFB200_PAD_FILL=0 turns it off."""
+    v = op.writes[0]
+    b = v.buf
+    if len(op.writes) != 1 or v.c_off + v.c != b.c or b.ld <= b.c or act == "sigmoid":
+        return 0
+    if ((v.c_off + v.c) * 2) % 32 == 0 or os.environ.get("MAFB200_PAD_FILL", "1") == "0":
+        return 0
+    return b.ld - b.c
+
+
 class Plan:
     """Kernel-launch schedule + buffer liveness for one (graph, H, W); batch-size independent."""
 
@@ -392,9 +405,8 @@ class Engine:
         tile is already that wide).  Returns (output view, weight, bias), extended or as they were."""
         v = op.writes[0]
         b = v.buf
-        extra = b.ld - b.c if v.c_off + v.c == b.c else 0
-        if (extra <= 0 or len(op.writes) != 1 or act == "sigmoid" or ((v.c_off + v.c) * 2) % 32 == 0 or
-                os.environ.get("MAFB200_PAD_FILL", "1") == "0"):
+        extra = pad_fill_channels(op, act)
+        if extra == 0:
             return self.view(v), wt, bs
         wt = torch.cat([wt, wt.new_zeros((extra,) + tuple(wt.shape[1:]))])
         bs = torch.cat([bs, bs.new_zeros(extra)])

@@ -169,6 +169,38 @@ def test_plan_liveness_and_arena(variant):
     assert max(len(op.reads) for op in plan.ops if op.kind == "conv1x1") == 4
 
 
+@pytest.mark.parametrize("variant", ["n", "s", "m"])
+def test_pad_fill_only_touches_unowned_padding(variant, monkeypatch):
+    """Ops that end inside a 32-byte sector at the end of a padded buffer get zero filters for the padding channels
+    (whole-sector stores).  Those channels must belong to no other view, the op must be the buffer's last-channel
+    writer, and sigmoid outputs (act(0) != 0) are never extended."""
+    monkeypatch.delenv("MAFB200_PAD_FILL", raising=False)
+    plan = engine.Plan(topology.build_graph(variant), 640, 640)
+    extended = {}
+    for op in plan.ops:
+        if not op.writes or op.kind not in ("stem", "conv1x1", "dwpw", "poolpw"):
+            continue
+        act = op.act2 if op.kind == "dwpw" else op.act
+        extra = engine.pad_fill_channels(op, act)
+        v = op.writes[0]
+        if extra:
+            assert act != "sigmoid" and len(op.writes) == 1
+            assert v.c_off + v.c == v.buf.c and v.c_off + v.c + extra == v.buf.ld
+            assert ((v.c_off + v.c) * 2) % 32 != 0 and (v.buf.ld * 2) % 32 == 0
+            extended[op.name] = (id(v.buf), v.buf.c, v.buf.ld)
+        else:
+            assert ((v.c_off + v.c) * 2) % 32 == 0 or v.c_off + v.c != v.buf.c or len(op.writes) != 1 or act == "sigmoid"
+    # nobody reads or writes the padding channels as data
+    for op in plan.ops:
+        for v in op.reads + op.writes:
+            assert v.c_off + v.c <= v.buf.c, (op.name, v.buf.name)
+    if variant == "n":
+        assert sorted(extended) == ["L0.stem3x3s2", "L2.m0.conv1", "L2.m0.dw3+one_conv", "L31.reg_pred", "L32.reg_pred",
+                                    "L33.reg_pred"]
+    monkeypatch.setenv("MAFB200_PAD_FILL", "0")
+    assert all(engine.pad_fill_channels(op, op.act) == 0 for op in plan.ops if op.writes)
+
+
 def test_yaml_loader_accepts_reference_schema(tmp_path):
     import yaml
 
