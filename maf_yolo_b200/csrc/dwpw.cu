@@ -55,8 +55,8 @@ __device__ __forceinline__ void tma_load_tile_4d_fw(void* smem_dst, const CUtens
       : "memory");
 }
 
-template <int K>
-__global__ void __launch_bounds__(kFwThreads, 2) dwpw_kernel(const __grid_constant__ DwPwParams p) {
+template <int K, int kCtas>
+__global__ void __launch_bounds__(kFwThreads, kCtas) dwpw_kernel(const __grid_constant__ DwPwParams p) {
   constexpr int P = K / 2;
   constexpr int TW = kFwTX + K - 1, TH = kFwTY + K - 1;
   constexpr uint32_t kHaloBytes = TH * TW * kFwCB * 2;
@@ -219,20 +219,35 @@ __global__ void __launch_bounds__(kFwThreads, 2) dwpw_kernel(const __grid_consta
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
+template <int K, int kCtas>
+static int32_t launch_dwpw_as(DwPwParams& p, int n, int tiles, size_t smem, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(dwpw_kernel<K, kCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+    if (e != cudaSuccess) return fail(MAF_E_CUDA, "dwpw: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  launch_pdl(dwpw_kernel<K, kCtas>, dim3(tiles, n), dim3(kFwThreads), smem, st, p);
+  return check_launch("dwpw kernel launch");
+}
+
 template <int K>
 static int32_t launch_dwpw(DwPwParams& p, int n, int tiles, cudaStream_t st) {
   constexpr int TW = kFwTX + K - 1, TH = kFwTY + K - 1;
   const size_t smem = 1024 + static_cast<size_t>(kFwRows) * 128 + static_cast<size_t>(2) * p.tile_n * 128 +
                       ((static_cast<size_t>(TH) * TW * kFwCB * 2 + 127) / 128) * 128 + 64 + static_cast<size_t>(p.tile_n) * 4;
   if (smem > 113 * 1024) return fail(MAF_E_ARG, "dwpw: %zu B of shared memory needed (C=%d N=%d)", smem, p.C, p.N);
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(dwpw_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
-    if (e != cudaSuccess) return fail(MAF_E_CUDA, "dwpw: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    configured = true;
+  if constexpr (K == 3) {
+    // k = 3 needs 18 weight + 14 window registers beside the 50 accumulators: it fits 80 registers (4 bytes of spill),
+    // and with cout <= 32 three CTAs fit the SM's shared memory and TMEM -> 24 instead of 16 warps to cover the TMA /
+    // barrier / epilogue gaps of its short tap loop.  Opt-in (MAFB200_DWPW_3CTA=1) until it has been measured.
+    static const bool three = [] {
+      const char* e = getenv("MAFB200_DWPW_3CTA");
+      return e && e[0] == '1';
+    }();
+    if (three && 3 * (smem + 1024) <= 228 * 1024 && 3 * p.tmem_cols <= 512) return launch_dwpw_as<K, 3>(p, n, tiles, smem, st);
   }
-  launch_pdl(dwpw_kernel<K>, dim3(tiles, n), dim3(kFwThreads), smem, st, p);
-  return check_launch("dwpw kernel launch");
+  return launch_dwpw_as<K, 2>(p, n, tiles, smem, st);
 }
 
 }  // namespace mafb200
