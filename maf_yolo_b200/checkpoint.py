@@ -3,8 +3,9 @@
 `yolov6/utils/checkpoint.py:83-93` (`load_checkpoint`) does `torch.load(weights)` and takes `ckpt['ema']` or
 `ckpt['model']` — a pickled *nn.Module object*, so unpickling normally needs yolov6.models.yolo.Model,
 yolov6.layers.common.* ... importable under exactly those paths.  Here a restricted unpickler resolves only
-torch / numpy / builtins classes; every other class (the reference's modules, its Config objects, ...) becomes
-an inert stub that just holds its pickled `__dict__`.  The module tree is then walked (`_modules`,
+an explicit allow-list of tensor-rebuild functions and plain containers; every other global (the reference's modules, its Config objects, and any
+torch / numpy / builtins name that is not on the explicit allow-list below, e.g. builtins.eval or torch.hub.load)
+becomes an inert stub that just holds its pickled `__dict__`.  The module tree is then walked (`_modules`,
 `_parameters`, `_buffers`) into an ordinary `state_dict`, and `model.yaml` (yolo.py:145), `names` and `nc` are
 read off the stub — everything `from_state_dict` / `convert` need.  No code from the checkpoint is executed.
 
@@ -20,12 +21,35 @@ from typing import Dict, Tuple
 
 import torch
 
-_SAFE_PREFIXES = ("torch", "collections", "numpy", "builtins", "__builtin__", "_codecs", "copyreg", "pathlib", "argparse")
+# Explicit allow-list of (module, name) globals the unpickler may resolve to the REAL object: exactly what
+# torch.save needs to rebuild tensors / parameters and plain containers.  Everything else — the reference's classes,
+# torch.nn modules, argparse / pathlib objects, and every other torch / numpy / builtins name (eval, exec, getattr,
+# __import__, torch.hub.load, torch.utils.cpp_extension.load, numpy's pickle-calling `scalar`, ...) — becomes an inert
+# stub, so no callable chosen by the file ever runs.
+_TORCH_STORAGES = ("DoubleStorage", "FloatStorage", "HalfStorage", "BFloat16Storage", "LongStorage", "IntStorage",
+                   "ShortStorage", "CharStorage", "ByteStorage", "BoolStorage", "ComplexFloatStorage",
+                   "ComplexDoubleStorage", "UntypedStorage")
+_ALLOWED = {
+    ("collections", "OrderedDict"),
+    ("torch._utils", "_rebuild_tensor_v2"), ("torch._utils", "_rebuild_tensor"),
+    ("torch._utils", "_rebuild_parameter"), ("torch._utils", "_rebuild_parameter_with_state"),
+    ("torch._tensor", "_rebuild_from_type_v2"),
+    ("torch.nn.parameter", "Parameter"), ("torch", "Tensor"), ("torch", "Size"), ("torch", "device"),
+    ("torch.storage", "UntypedStorage"), ("torch.storage", "TypedStorage"),
+    ("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct"),
+    ("numpy", "ndarray"), ("numpy", "dtype"),
+    ("_codecs", "encode"),
+} | {("torch", n) for n in _TORCH_STORAGES} | {
+    (m, n) for m in ("builtins", "__builtin__")
+    for n in ("set", "frozenset", "dict", "list", "tuple", "int", "float", "bool", "str", "bytes", "bytearray", "slice",
+              "complex", "range", "object")}
 _stub_cache: Dict[Tuple[str, str], type] = {}
 
 
 class _Stub:
-    """Stands in for any class of the checkpoint that is not torch/numpy/builtin: keeps the pickled state only."""
+    """Stands in for any global of the checkpoint that is not on the allow-list: keeps the pickled state only.
+    Calling it, constructing it, or filling it (SETITEM / APPEND opcodes of dict / list subclasses) has no effect
+    beyond storing the arguments."""
 
     def __init__(self, *args, **kwargs):
         self._stub_args = (args, kwargs)
@@ -43,20 +67,57 @@ class _Stub:
     def __call__(self, *args, **kwargs):  # e.g. a pickled functools.partial-like reduce on a stubbed callable
         return _Stub(*args, **kwargs)
 
+    def __setitem__(self, key, value):
+        self.__dict__.setdefault("_stub_items", {})[key] = value
+
+    def append(self, value):
+        self.__dict__.setdefault("_stub_list", []).append(value)
+
+    def extend(self, values):
+        self.__dict__.setdefault("_stub_list", []).extend(values)
+
+    def add(self, value):
+        self.__dict__.setdefault("_stub_list", []).append(value)
+
 
 def _stub_class(module: str, name: str) -> type:
     key = (module, name)
     cls = _stub_cache.get(key)
     if cls is None:
-        cls = type(name, (_Stub,), {"__module__": module})
+        cls = type(name.rsplit(".", 1)[-1], (_Stub,), {"__module__": module})
         _stub_cache[key] = cls
     return cls
 
 
+def _safe_reconstructor(cls, base, state):
+    """copyreg._reconstructor for protocol < 2 pickles of plain objects: only ever instantiates stubs."""
+    if isinstance(cls, type) and issubclass(cls, _Stub):
+        obj = object.__new__(cls)
+        if state is not None:
+            obj.__dict__["_stub_base_state"] = state
+        return obj
+    raise pickle.UnpicklingError(f"refusing to reconstruct {cls!r} from a checkpoint")
+
+
+def _safe_numpy_scalar(dtype, data):
+    """numpy's pickled scalars; the real `scalar` unpickles `data` again when dtype is object — never allowed."""
+    import numpy as np
+
+    if not isinstance(dtype, np.dtype) or dtype.hasobject:
+        raise pickle.UnpicklingError("object-dtype numpy scalar in a checkpoint")
+    return np.frombuffer(data, dtype=dtype, count=1)[0]
+
+
 class _Unpickler(pickle.Unpickler):
     def find_class(self, module, name):
-        if module.split(".")[0] in _SAFE_PREFIXES or module in _SAFE_PREFIXES:
+        if module == "copyreg" and name == "_reconstructor":
+            return _safe_reconstructor
+        if module in ("numpy.core.multiarray", "numpy._core.multiarray") and name == "scalar":
+            return _safe_numpy_scalar
+        if (module, name) in _ALLOWED:
             return super().find_class(module, name)
+        if module == "torch" and isinstance(getattr(torch, name, None), torch.dtype):
+            return getattr(torch, name)
         return _stub_class(module, name)
 
 
@@ -94,6 +155,8 @@ def load_checkpoint(weights, map_location="cpu"):
     """Same selection rule as the reference (`ckpt['ema'] if ckpt.get('ema') else ckpt['model']`, then `.float()`).
     Also accepts a bare pickled module, or a plain (train- or deploy-form) state_dict file.
     Returns (state_dict, meta) with meta = {"yaml": model.yaml rows | None, "names", "nc", "which"}."""
+    # weights_only=False only because torch.load rejects a custom pickle_module otherwise; the pickle_module IS the
+    # restriction (explicit allow-list above; tests/test_checkpoint_cpu.py loads hostile pickles through it)
     ckpt = torch.load(weights, map_location=map_location, pickle_module=_pickle_module, weights_only=False)
     which, model = "state_dict", None
     if isinstance(ckpt, dict) and ("model" in ckpt or "ema" in ckpt):

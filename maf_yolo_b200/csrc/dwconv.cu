@@ -245,12 +245,10 @@ static int32_t launch_dw(const maf_tensor* src, const float* w, const float* bia
     return fail(MAF_E_CUDA, "dwconv: cuTensorMapEncodeTiled(c=%d w=%d h=%d n=%d) failed: %d", src->c, src->w, src->h,
                 src->n, (int)r);
   const size_t smem = static_cast<size_t>(TH) * TW * CB * 2 + (K <= 5 ? 0 : static_cast<size_t>(K * K + 1) * CB * 4) + 16;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e =
-        cudaFuncSetAttribute(dwconv_kernel<K, CB, kTma>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    if (e != cudaSuccess) return fail(MAF_E_CUDA, "dwconv: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    configured = true;
+  {
+    static SmemOptIn opt_in;  // per device (a process-wide flag skipped the opt-in on a second GPU)
+    const int32_t rc_attr = smem_opt_in(opt_in, dwconv_kernel<K, CB, kTma>, 100 * 1024, "dwconv");
+    if (rc_attr) return rc_attr;
   }
   const int tiles_x = ceil_div(src->w, kDwTXB), tiles_y = ceil_div(src->h, kDwTYB);
   dim3 grid(tiles_x * tiles_y, ceil_div(src->c, CB), src->n);

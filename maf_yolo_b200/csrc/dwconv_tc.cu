@@ -237,11 +237,10 @@ static int32_t launch_dw_tc(const maf_tensor* src, const void* table, const floa
   constexpr int PP = NPX + 8;
   const size_t in_bytes = (static_cast<size_t>(NPX) * kTcCB * 2 + 1023) / 1024 * 1024;
   const size_t smem = 512 + in_bytes + static_cast<size_t>(kTcCB) * PP * 2;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(dwconv_tc_kernel<K, kAct>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    if (e != cudaSuccess) return fail(MAF_E_CUDA, "dwconv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    configured = true;
+  {
+    static SmemOptIn opt_in;  // per device (a process-wide flag skipped the opt-in on a second GPU)
+    const int32_t rc_attr = smem_opt_in(opt_in, dwconv_tc_kernel<K, kAct>, 100 * 1024, "dwconv_tc");
+    if (rc_attr) return rc_attr;
   }
   const int tiles_x = ceil_div(src->w, kTcTile), tiles_y = ceil_div(src->h, kTcTile);
   dim3 grid(tiles_x * tiles_y, ceil_div(src->c, kTcCB), src->n);

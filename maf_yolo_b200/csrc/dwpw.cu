@@ -221,11 +221,10 @@ __global__ void __launch_bounds__(kFwThreads, kCtas) dwpw_kernel(const __grid_co
 
 template <int K, int kCtas>
 static int32_t launch_dwpw_as(DwPwParams& p, int n, int tiles, size_t smem, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(dwpw_kernel<K, kCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
-    if (e != cudaSuccess) return fail(MAF_E_CUDA, "dwpw: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    configured = true;
+  {
+    static SmemOptIn opt_in;  // per device (a process-wide flag skipped the opt-in on a second GPU)
+    const int32_t rc_attr = smem_opt_in(opt_in, dwpw_kernel<K, kCtas>, 113 * 1024, "dwpw");
+    if (rc_attr) return rc_attr;
   }
   launch_pdl(dwpw_kernel<K, kCtas>, dim3(tiles, n), dim3(kFwThreads), smem, st, p);
   return check_launch("dwpw kernel launch");

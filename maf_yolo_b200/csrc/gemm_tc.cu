@@ -527,12 +527,10 @@ static int32_t launch_gemm(GemmParams& p, int n_tiles, int total_kb, cudaStream_
                  : 0;
   const size_t smem = static_cast<size_t>(p.w_resident ? panel : 0) + static_cast<size_t>(stages) * slot_bytes +
                       (2 * stages + 5) * 8 + 16 + static_cast<size_t>(p.tile_n + 32) * 8 + 1024;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<kMode == kModeIm2colTma>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return fail(MAF_E_CUDA, "cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e));
-    configured = true;
+  {
+    static SmemOptIn opt_in;  // per device (a process-wide flag skipped the opt-in on a second GPU)
+    const int32_t rc_attr = smem_opt_in(opt_in, gemm_tc_kernel<kMode == kModeIm2colTma>, 227 * 1024, "gemm");
+    if (rc_attr) return rc_attr;
   }
   if (smem > 227 * 1024) return fail(MAF_E_ARG, "gemm: %zu B of shared memory needed", smem);
   launch_pdl(gemm_tc_kernel<kMode == kModeIm2colTma>, dim3(grid), dim3(kGemmThreads), smem, stream, p);

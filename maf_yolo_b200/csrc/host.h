@@ -8,6 +8,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/mafb200.h"
 
 namespace mafb200 {
@@ -55,6 +57,24 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   cfg.attrs = attr;
   cfg.numAttrs = (kPdl && pdl_enabled()) ? 1 : 0;
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);  // error picked up by check_launch()
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies per device (context): remembered per (kernel
+// instantiation, device) — each call site owns a zero-initialised `static SmemOptIn`.  Two threads racing on the first
+// call both set the same value, which is harmless.
+struct SmemOptIn {
+  std::atomic<int> bytes[64];
+};
+template <typename Kernel>
+inline int32_t smem_opt_in(SmemOptIn& st, Kernel kernel, int bytes, const char* what) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess || dev < 0 || dev >= 64) return fail(MAF_E_CUDA, "%s: cudaGetDevice: %s", what, cudaGetErrorString(e));
+  if (st.bytes[dev].load(std::memory_order_acquire) >= bytes) return MAF_OK;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return fail(MAF_E_CUDA, "%s: cudaFuncSetAttribute(%d B): %s", what, bytes, cudaGetErrorString(e));
+  st.bytes[dev].store(bytes, std::memory_order_release);
+  return MAF_OK;
 }
 
 inline bool valid_f16_view(const maf_tensor* t) {

@@ -380,11 +380,10 @@ static long long pow2_ceil(long long v) {
 static int32_t launch_select(const NmsParams& p, cudaStream_t st) {
   const size_t smem = static_cast<size_t>(kSortSmemKeys) * 8 + static_cast<size_t>(round_up(p.max_det, 2)) * 5 * 4 +
                       kChunk * 5 * 4 + kChunk * 4 * 8 + kChunk * 4 * 2 + (kChunk / 32) * 4;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(nms_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    if (e != cudaSuccess) return fail(MAF_E_CUDA, "nms: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    configured = true;
+  {
+    static SmemOptIn opt_in;  // per device (a process-wide flag skipped the opt-in on a second GPU)
+    const int32_t rc_attr = smem_opt_in(opt_in, nms_select_kernel, 160 * 1024, "nms_select");
+    if (rc_attr) return rc_attr;
   }
   launch_pdl<false>(nms_select_kernel, dim3(p.B), dim3(1024), smem, st, p);
   return check_launch("nms_select kernel launch");
@@ -449,11 +448,10 @@ extern "C" int32_t mafb200_nms(const float* pred, int32_t batch, int32_t anchors
   // follows a memset node, not a kernel: plain stream-ordered launch
   const size_t csmem = static_cast<size_t>(kCompactRows) * (5 + nc) * sizeof(float);
   if (csmem > 200 * 1024) return fail(MAF_E_ARG, "nms: nc=%d too large for the compaction tile", nc);
-  static size_t compact_smem_cfg = 48 * 1024;
-  if (csmem > compact_smem_cfg) {
-    e = cudaFuncSetAttribute(nms_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(csmem));
-    if (e != cudaSuccess) return fail(MAF_E_CUDA, "nms: cudaFuncSetAttribute(compact): %s", cudaGetErrorString(e));
-    compact_smem_cfg = csmem;
+  if (csmem > 48 * 1024) {
+    static SmemOptIn opt_in;  // per device, grows with nc
+    rc = smem_opt_in(opt_in, nms_compact_kernel, static_cast<int>(csmem), "nms_compact");
+    if (rc) return rc;
   }
   launch_pdl<false>(nms_compact_kernel, dim3(ceil_div(anchors, kCompactRows), batch), dim3(256), csmem, st, p);
   rc = check_launch("nms_compact kernel launch");

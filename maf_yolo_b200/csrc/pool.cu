@@ -209,11 +209,10 @@ extern "C" int32_t mafb200_sppf_pool(const maf_tensor* src, const maf_tensor* y1
   if (smem > 200 * 1024) return fail(MAF_E_ARG, "sppf_pool: map %dx%d too large for the one-CTA-per-map kernel", src->h, src->w);
   int32_t rc = require_sm100();
   if (rc) return rc;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(sppf_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return fail(MAF_E_CUDA, "sppf_pool: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    configured = true;
+  {
+    static SmemOptIn opt_in;  // per device (a process-wide flag skipped the opt-in on a second GPU)
+    const int32_t rc_attr = smem_opt_in(opt_in, sppf_pool_kernel, 200 * 1024, "sppf_pool");
+    if (rc_attr) return rc_attr;
   }
   const unsigned blocks = static_cast<unsigned>(src->n) * (src->c / 8);
   launch_pdl(sppf_pool_kernel, dim3(blocks), dim3(256), smem, static_cast<cudaStream_t>(stream),

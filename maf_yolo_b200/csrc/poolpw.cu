@@ -236,11 +236,10 @@ extern "C" int32_t mafb200_maxpool2x2_conv1x1(const maf_tensor* src, const void*
   p.idesc = umma_idesc_f16(128, tile_n);
   const size_t smem = 1024 + static_cast<size_t>(p.kblocks) * (kPpRows * 128 + tile_n * 128) + 32 +
                       static_cast<size_t>(tile_n) * 4;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(poolpw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    if (e != cudaSuccess) return fail(MAF_E_CUDA, "maxpool2x2_conv1x1: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    configured = true;
+  {
+    static SmemOptIn opt_in;  // per device (a process-wide flag skipped the opt-in on a second GPU)
+    const int32_t rc_attr = smem_opt_in(opt_in, poolpw_kernel, 160 * 1024, "maxpool2x2_conv1x1");
+    if (rc_attr) return rc_attr;
   }
   const long long ctas = (p.M + kPpRows - 1) / kPpRows;
   launch_pdl(poolpw_kernel, dim3(static_cast<unsigned>(ctas)), dim3(kPpThreads), smem, static_cast<cudaStream_t>(stream), p);

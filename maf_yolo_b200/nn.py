@@ -90,10 +90,13 @@ class B200DetectModel(torch.nn.Module):
     `.half()` / `.float()` (evaler.py:112) are accepted and change nothing: the compute type is
     fixed (fp16 operands, fp32 accumulate) and the output is fp32, as the reference's is.
     Engines (plan + arena + CUDA graph) are built lazily per (batch, H, W, device).
+    Output lifetime: `pred` is a fresh tensor per call (as in the reference) unless the model was built with
+    `borrow_output=True`, in which case it is one of two engine-owned buffers and stays valid until the second next
+    forward() of the same input shape.  `detect_async` results have their own documented lifetime (DetectTicket).
     """
 
     def __init__(self, graph, folded, names=None, use_cuda_graph: bool = True, return_featmaps: bool = False,
-                 n_streams: int = 4, in_flight: int = 1):
+                 n_streams: int = 4, in_flight: int = 1, borrow_output: bool = False):
         super().__init__()
         self.graph = graph
         self.folded = folded
@@ -103,6 +106,10 @@ class B200DetectModel(torch.nn.Module):
         self.use_cuda_graph = use_cuda_graph
         self.return_featmaps = return_featmaps
         self.n_streams = n_streams
+        # forward() returns a fresh tensor like the reference's Model.forward does (a caller may keep outputs across
+        # batches: `outs.append(model(x)[0])`).  borrow_output=True hands out the engine-owned buffer instead — no
+        # 2.9 MB/image copy — which is overwritten by the SECOND next forward() of the same (batch, H, W).
+        self.borrow_output = borrow_output
         # detect_async: decode fused with the NMS threshold / compaction pass (MAFB200_FUSED_DETECT=0 turns it off)
         self.fused_detect = os.environ.get("MAFB200_FUSED_DETECT", "1") != "0"
         self.in_flight = max(1, int(in_flight))  # detect_async: engine replicas (arena + graph + streams) used round-robin
@@ -142,6 +149,8 @@ class B200DetectModel(torch.nn.Module):
         eng = self.engine_for(x)
         with torch.cuda.device(x.device):
             pred = eng.forward(x)
+            if not self.borrow_output:
+                pred = pred.clone()
             feats = eng.head_outputs() if self.return_featmaps else []
         return [pred, feats]
 

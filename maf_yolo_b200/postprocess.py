@@ -9,6 +9,13 @@ The reference loops over images and detections in Python with a `.tolist()` / `.
 detection; here ONE kernel (mafb200_scale_detections) rescales, clips and converts the whole padded batch,
 one D2H copy brings it to the host, and only the json-dict packing (Python `round`, exactly the reference's
 expression on the same float values) stays on the CPU.
+
+`recip_mul` — which division the reference's `coords /= gain` (evaler.py:404-411) is:
+  False (default): IEEE division `a / b`, what torch computes for CPU tensors — bit-exact against the CPU oracle
+                   (oracle/postprocess.py) and the committed golden vectors, which is what the parity tests pin;
+  True:            `a * (1 / b)`, what torch's CUDA kernel computes when the divisor is a Python scalar, i.e. what the
+                   reference evaler produces when it runs on a GPU.  The two differ by at most 1 ulp per coordinate;
+                   pass True to reproduce a GPU run of the reference bit for bit.
 """
 from __future__ import annotations
 

@@ -2,8 +2,9 @@
 
   letterbox(im, new_shape, color, auto, scaleup, stride, return_int)   == yolov6/data/data_augment.py:53-83
   precess_image(img_src, img_size, stride, half)                        == Inferer.precess_image (inferer.py:168-178)
-  letterbox_batch(images, new_shape)                                    fixed-size batch for the evaluator path
-                                                                        (datasets.py:207-215, auto=False)
+  letterbox_batch(images, new_shape, orig_shapes=...)                   the evaluator's letterbox step for a fixed-size
+                                                                        batch (datasets.py:204-215, auto=False); input =
+                                                                        the output of load_image (datasets.py:280-301)
 
 The image is uploaded once as the raw uint8 HWC (BGR) array cv2 produced; ONE kernel (mafb200_letterbox_u8)
 resizes with OpenCV's exact 8-bit INTER_LINEAR arithmetic, pads with 114, converts HWC -> CHW / BGR -> RGB and
@@ -87,13 +88,24 @@ def precess_image(img_src, img_size, stride, half=False, device="cuda", as_uint8
 
 
 def letterbox_batch(images: Sequence, new_shape=(640, 640), scaleup: bool = False, device="cuda",
-                    color=(114, 114, 114)) -> Tuple[torch.Tensor, List[tuple]]:
-    """Evaluator-style batch (datasets.py:207-215: auto=False, scaleup=augment=False): uint8 [B,3,H,W] RGB on the
-    device + per image `shapes` = ((h0, w0), ((h*r/h0, w*r/w0), (dw, dh))) for the post-NMS rescale."""
+                    color=(114, 114, 114), orig_shapes: Sequence[Tuple[int, int]] = None) -> Tuple[torch.Tensor, List[tuple]]:
+    """The evaluator's letterbox step (datasets.py:204-215: `letterbox(img, shape, auto=False, scaleup=self.augment)`
+    with augment=False) for a fixed-size batch: uint8 [B,3,H,W] RGB on the device + per image the dataloader's
+    `shapes` = ((h0, w0), ((h*ratio/h0, w*ratio/w0), pad)) (datasets.py:215) for the post-NMS rescale.
+
+    Contract: `images[i]` is what the reference's `load_image` RETURNS (datasets.py:280-301) — the file already
+    resized so that its long side equals img_size (cv2 INTER_AREA when shrinking, INTER_LINEAR when enlarging,
+    `int()` geometry) — NOT the original file.  That resize is the step before this one and is not reproduced here
+    (its INTER_AREA path is a different algorithm); pass the original sizes as `orig_shapes[i]` = (h0, w0) so that
+    `shapes` carries the reference's values.  Without `orig_shapes` the images are taken to be the originals of a
+    dataset whose long side already equals img_size (h0, w0 = h, w).  With scaleup=False a smaller image is only
+    padded, exactly as the reference's letterbox does to it."""
     if isinstance(new_shape, int):
         new_shape = (new_shape, new_shape)
     if not torch.cuda.is_available():
         raise RuntimeError("maf_yolo_b200.preprocess needs a B200 GPU (no CPU fallback)")
+    if orig_shapes is not None and len(orig_shapes) != len(images):
+        raise ValueError("orig_shapes must give (h0, w0) for every image")
     dev = torch.device(device)
     with torch.cuda.device(dev):
         batch = torch.empty((len(images), 3, new_shape[0], new_shape[1]), dtype=torch.uint8, device=dev)
@@ -101,7 +113,15 @@ def letterbox_batch(images: Sequence, new_shape=(640, 640), scaleup: bool = Fals
         for i, im in enumerate(images):
             src = _to_device_u8(im, dev)
             h, w = src.shape[:2]
+            h0, w0 = (h, w) if orig_shapes is None else (int(orig_shapes[i][0]), int(orig_shapes[i][1]))
             g = letterbox_geometry((h, w), new_shape, False, scaleup, 32)
             _launch(src, batch[i], g, color, True)
-            shapes.append(((h, w), ((h * g["r"] / h, w * g["r"] / w), (g["dw"], g["dh"]))))
+            shapes.append(((h0, w0), ((h * g["r"] / h0, w * g["r"] / w0), (g["dw"], g["dh"]))))
     return batch, shapes
+
+
+def load_image_size(h0: int, w0: int, img_size: int) -> Tuple[int, int]:
+    """(h, w) the reference's load_image resizes an (h0, w0) file to (datasets.py:290-300: r = img_size / max,
+    `int(w0 * r), int(h0 * r)`), for callers that do that resize themselves."""
+    r = img_size / max(h0, w0)
+    return (h0, w0) if r == 1 else (int(h0 * r), int(w0 * r))

@@ -21,13 +21,23 @@ from .topology import Graph
 DIL_BRANCHES = {9: [7, 5, 3], 7: [5, 3], 5: [3, 1], 3: [3, 1]}  # yolov6/layers/common.py:2985-3008
 
 
-def random_state_dict(graph: Graph, seed: int = 0, head_std: float = 0.35, cls_bias: float = -4.595) -> Dict[str, torch.Tensor]:
+def random_state_dict(graph: Graph, seed: int = 0, head_std: float = 0.35, cls_bias: float = -4.595,
+                      conv_gain: float = 1.0, reg_peak: float = None, reg_sharp: float = 1.0,
+                      reg_std: float = None) -> Dict[str, torch.Tensor]:
+    """conv_gain scales every conv's init bound.  1.0 = PyTorch's default init, under which a signal decays by ~0.4x
+    per layer, so after 30+ layers the heads see almost only the last layers' biases (predictions barely depend on
+    the image).  sqrt(6) ~ 2.45 gives He-normalised weights (std sqrt(2 / fan_in)): activations keep their scale
+    through the whole network, as in a trained model — the setting of the conditioned parity fixtures
+    (tests/golden/make_golden_cond.py), where every layer's error reaches the output.
+    reg_peak / reg_sharp / reg_std shape the DFL head: reg_pred.bias of bin i becomes -reg_sharp * (i - reg_peak)^2
+    (the softmax expectation of every box side then sits near reg_peak grid units, i.e. boxes of ~2 * reg_peak cells
+    instead of the ~17-cell boxes a constant bias gives) and reg_pred.weight ~ N(0, reg_std)."""
     g = torch.Generator().manual_seed(seed)
     sd: Dict[str, torch.Tensor] = {}
 
     def conv(name, co, ci, k, groups=1):
         fan_in = (ci // groups) * k * k
-        bound = 1.0 / math.sqrt(fan_in)  # kaiming_uniform(a=sqrt(5)) == U(-1/sqrt(fan_in), 1/sqrt(fan_in))
+        bound = conv_gain / math.sqrt(fan_in)  # kaiming_uniform(a=sqrt(5)) == U(-1/sqrt(fan_in), 1/sqrt(fan_in))
         sd[name] = (torch.rand(co, ci // groups, k, k, generator=g) * 2 - 1) * bound
 
     def bn(name, c):
@@ -85,8 +95,13 @@ def random_state_dict(graph: Graph, seed: int = 0, head_std: float = 0.35, cls_b
             conv_mod(p + ".reg_conv_s", c, c)
             sd[p + ".cls_pred.weight"] = torch.randn(graph.nc, c, 1, 1, generator=g) * head_std
             sd[p + ".cls_pred.bias"] = torch.full((graph.nc,), cls_bias)
-            sd[p + ".reg_pred.weight"] = torch.randn(4 * (l.reg_max + 1), c, 1, 1, generator=g) * head_std
-            sd[p + ".reg_pred.bias"] = torch.full((4 * (l.reg_max + 1),), 1.0)
+            sd[p + ".reg_pred.weight"] = torch.randn(4 * (l.reg_max + 1), c, 1, 1, generator=g) * (
+                head_std if reg_std is None else reg_std)
+            if reg_peak is None:
+                sd[p + ".reg_pred.bias"] = torch.full((4 * (l.reg_max + 1),), 1.0)
+            else:
+                bins = torch.arange(l.reg_max + 1, dtype=torch.float32)
+                sd[p + ".reg_pred.bias"] = (-reg_sharp * (bins - reg_peak) ** 2).repeat(4)
     reg_max = graph.layers[graph.head_layers[0]].reg_max
     sd["detect.proj"] = torch.linspace(0, reg_max, reg_max + 1)
     sd["detect.proj_conv.weight"] = sd["detect.proj"].view(1, reg_max + 1, 1, 1).clone()

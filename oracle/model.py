@@ -13,7 +13,7 @@ Two executable forms, both driven by a reference-format `state_dict`:
                                     restated, and the deploy-form forward.  Used as the timed CPU
                                     baseline ("port") and to cross-check the product's own fold.
 
-Pinned (tests/test_oracle_vs_reference.py, run where /root/reference exists) against the real
+Pinned (tests/test_oracle_cpu.py, run where /root/reference exists) against the real
 reference modules loaded with the same state_dict, and against committed golden vectors
 (tests/golden/, made by tests/golden/make_golden.py from the reference).  The reference ships no
 tests / golden vectors of its own, so beyond that parity is unpinned.
@@ -212,7 +212,9 @@ def dist2bbox_xywh(distance, anchor_points):
 def detect_eval(head_outs, strides=(8, 16, 32), reg_max=16, nc=80):
     """Detect_yaml.forward eval branch (yolo.py:355-396).  head_outs: list of (stem, cls_prob, reg)."""
     anchor_points, stride_tensor = generate_anchors_eval([o[0].shape[2:] for o in head_outs], strides)
-    proj = torch.linspace(0, reg_max, reg_max + 1).view(1, reg_max + 1, 1, 1)  # yolo.py:328-330
+    # yolo.py:328-330; a parameter of the model, so `model.half()` (evaler.py:112) casts it with the convs while the
+    # anchor points stay fp32 (anchor_generator.py:18) and promote the boxes back to fp32
+    proj = torch.linspace(0, reg_max, reg_max + 1).view(1, reg_max + 1, 1, 1).to(head_outs[0][2].dtype)
     cls_l, reg_l = [], []
     for stem, cls, reg in head_outs:
         b, _, h, w = stem.shape

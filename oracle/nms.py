@@ -4,7 +4,7 @@ Follows yolov6/utils/nms.py:21-105 line by line and restates `torchvision.ops.nm
 0.26 CPU kernel `nms_kernel_impl`: stable descending sort, greedy suppression, IoU =
 inter / (area_i + area_j - inter) in fp32, threshold compared in double, strict '>').
 Pure numpy fp32 — index work must be bit-exact.  Pinned against the reference's own
-`non_max_suppression` (imported from /root/reference in this container; tests/test_oracle_vs_reference.py)
+`non_max_suppression` (imported from /root/reference in this container; tests/test_oracle_cpu.py)
 and against the committed golden vectors (tests/golden/).  Parity is otherwise unpinned: the
 reference ships no tests or golden vectors of its own.
 

@@ -22,3 +22,19 @@ def synthetic_image(b, h=640, w=640, seed=0, dtype=torch.float32):
     if dtype == torch.uint8:
         return (x * 255).round().to(torch.uint8)
     return x.to(dtype)
+
+
+def synthetic_scene(b, h=640, w=640, seed=7):
+    """Images with structure at every anchor scale and no flat regions: piecewise-constant random grids of 64 / 32 /
+    16 / 8 px cells (aligned with the stride-8/16/32 anchor cells, so neighbouring anchors see different content)
+    plus pixel noise.  With signal-preserving weights (synth.random_state_dict(conv_gain=...)) every anchor then has
+    its own features and the score maps have distinct peaks.  fp32 in [0, 1]."""
+    import torch.nn.functional as F
+
+    gen = torch.Generator().manual_seed(seed)
+    x = torch.zeros(b, 3, h, w)
+    for cell in (64, 32, 16, 8):
+        r = torch.rand(b, 3, h // cell, w // cell, generator=gen) - 0.5
+        x += 0.4 * F.interpolate(r, size=(h, w), mode="nearest")
+    x += 0.06 * (torch.rand(b, 3, h, w, generator=gen) - 0.5)
+    return (x + 0.5).clamp(0, 1)

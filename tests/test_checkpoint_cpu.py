@@ -94,3 +94,78 @@ def test_real_reference_checkpoint_round_trip(tmp_path):
     g = topology.build_graph(meta["yaml"], 80)
     a, b = fold.fold_state_dict(g, sd), fold.fold_state_dict(g, want)
     assert a.keys() == b.keys() and all(torch.equal(a[k][0], b[k][0]) and torch.equal(a[k][1], b[k][1]) for k in a)
+
+
+class _Evil:
+    """Pickles to REDUCE(callable, args) with a callable named by (module, name) — what a hostile checkpoint does."""
+
+    def __init__(self, module, name, args):
+        self.module, self.name, self.args = module, name, args
+
+    def __reduce__(self):
+        import importlib
+
+        fn = importlib.import_module(self.module)
+        for part in self.name.split("."):
+            fn = getattr(fn, part)
+        return fn, self.args
+
+
+@pytest.mark.parametrize("module,name,args", [
+    ("builtins", "eval", ("__import__('os').system('touch {marker}')",)),
+    ("builtins", "exec", ("import os; os.system('touch {marker}')",)),
+    ("os", "system", ("touch {marker}",)),
+    ("posix", "system", ("touch {marker}",)),
+    ("subprocess", "check_call", (["touch", "{marker}"],)),
+    ("builtins", "__import__", ("os",)),
+    ("builtins", "getattr", ("x", "upper")),
+    ("torch.hub", "load", ("{marker}", "x")),
+    ("torch.utils.cpp_extension", "load", ("x", ["{marker}"])),
+    ("pathlib", "Path", ("{marker}",)),
+])
+def test_hostile_pickles_execute_nothing(tmp_path, module, name, args):
+    """no global chosen by the file may run.  Every callable outside the explicit allow-list is an
+    inert stub, so the REDUCE only records its arguments."""
+    import pickle
+
+    marker = tmp_path / "pwned"
+    sub = lambda a: a.format(marker=marker) if isinstance(a, str) else ([x.format(marker=marker) for x in a] if isinstance(a, list) else a)
+    payload = {"model": _Evil(module, name, tuple(sub(a) for a in args)), "ema": None}
+    path = tmp_path / "evil.pt"
+    with open(path, "wb") as f:  # legacy (non-zip) torch format is a plain pickle stream as well; use both
+        pickle.dump(payload, f, protocol=2)
+    zpath = tmp_path / "evil_zip.pt"
+    torch.save(payload, zpath)
+    for p in (zpath, path):
+        try:
+            ck.load_checkpoint(p)
+        except Exception:
+            pass  # "neither a pickled model checkpoint nor a state_dict" etc. is fine: nothing ran
+        assert not marker.exists(), f"{module}.{name} from the checkpoint was executed"
+
+
+def test_numpy_object_scalar_is_refused(tmp_path):
+    """numpy's pickled `scalar(dtype('O'), bytes)` would call pickle.loads on the bytes with the STOCK unpickler."""
+    import pickle
+    import numpy as np
+
+    marker = tmp_path / "pwned"
+    inner = pickle.dumps(_Evil("os", "system", (f"touch {marker}",)))
+    stream = (b"\x80\x02cnumpy.core.multiarray\nscalar\n" + b"cnumpy\ndtype\n(U\x02O8K\x00K\x01tR" +
+              b"(K\x03U\x01|NNNJ\xff\xff\xff\xffJ\xff\xff\xff\xffK?tb" + pickle.dumps(inner, protocol=2)[2:-1] + b"\x86R.")
+    path = tmp_path / "np.pt"
+    path.write_bytes(stream)
+    with pytest.raises(Exception):
+        ck.load_checkpoint(path)
+    assert not marker.exists()
+
+
+def test_allow_list_is_explicit():
+    up = ck._Unpickler(__import__("io").BytesIO(b""))
+    for module, name in [("builtins", "eval"), ("builtins", "getattr"), ("torch.hub", "load"), ("torch", "load"),
+                         ("numpy", "load"), ("torch.serialization", "load"), ("copyreg", "__reduce_ex__"),
+                         ("argparse", "Namespace"), ("torch.nn.modules.conv", "Conv2d")]:
+        assert issubclass(up.find_class(module, name), ck._Stub), (module, name)
+    assert up.find_class("torch", "float16") is torch.float16
+    assert up.find_class("collections", "OrderedDict") is __import__("collections").OrderedDict
+    assert up.find_class("torch._utils", "_rebuild_tensor_v2") is torch._utils._rebuild_tensor_v2

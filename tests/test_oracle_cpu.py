@@ -117,3 +117,26 @@ def test_oracle_bitexact_vs_reference_modules():
     for kw in (dict(conf_thres=0.03, iou_thres=0.65, multi_label=True), dict(conf_thres=0.02, iou_thres=0.45)):
         for r, o in zip(ns.non_max_suppression(sp.clone(), **kw), onms.non_max_suppression(sp.numpy(), **kw)):
             assert np.array_equal(r.numpy(), o)
+
+
+@pytest.mark.parametrize("variant", ["n", "s", "m"])
+@pytest.mark.parametrize("kind", ["strict", "rich"])
+def test_oracle_reproduces_conditioned_fixtures(variant, kind):
+    """The conditioned end-to-end fixtures (tests/golden/make_golden_cond.py: reference Model.forward ->
+    reference non_max_suppression on He-scaled weights and a structured image) are reproduced bit for bit by the
+    oracle forward + oracle NMS, from the seeds alone."""
+    from tests import _cond
+
+    if variant != "n" and os.environ.get("MAFB200_SLOW_CPU_TESTS", "1") == "0":
+        pytest.skip("slow")
+    fx = _cond.load_fixture(variant, kind)
+    g, sd, x = _cond.fixture_inputs(variant, fx)
+    spec = om.parse_model(om.variant_rows(variant))
+    pred = om.forward_train_form(spec, sd, x)
+    assert np.array_equal(pred[0, ::16].numpy(), fx["pred_sample"])
+    dets = onms.non_max_suppression(pred.numpy(), float(fx["conf"]), float(fx["iou"]), multi_label=True)
+    assert np.array_equal(dets[0], fx["det0"])
+    # the certification stored with the fixture is consistent with the reference's own output
+    st, opt = fx["cand_status"], fx["cand_optional"]
+    r = _cond.check_against_fixture(fx["det0"], fx, f"{variant}/{kind} reference vs its own certification")
+    assert r["strict"] == (kind == "strict") and r["n_must"] == int(((st == 1) & ~opt).sum())
