@@ -20,7 +20,12 @@ def pair_iou(b):
 
 
 def load_fixture(variant: str, kind: str):
-    return np.load(os.path.join(GOLD, f"cond_{variant}_{kind}.npz"))
+    path = os.path.join(GOLD, f"cond_{variant}_{kind}.npz")
+    if not os.path.exists(path):
+        import pytest
+
+        pytest.skip(f"{path} not generated (python tests/golden/make_golden_cond.py {variant})")
+    return np.load(path)
 
 
 def fixture_inputs(variant: str, fx):
@@ -35,14 +40,12 @@ def fixture_inputs(variant: str, fx):
     return g, sd, synthetic_scene(1, seed=int(fx["scene_seed"]))
 
 
-def conditioned_inputs(variant: str, batch: int, seed: int = 417):
-    """The conditioned weight family + scene images WITHOUT a fixture (forward-parity tests at other batch sizes)."""
-    from maf_yolo_b200 import synth, topology
+def conditioned_inputs(variant: str, batch: int):
+    """The conditioned weight family (the strict fixture's weights) with `batch` DIFFERENT scene images — for
+    forward-parity tests at other batch sizes."""
     from tests._synthetic import synthetic_scene
 
-    g = topology.build_graph(variant)
-    sd = synth.random_state_dict(g, seed=seed, head_std=0.5, cls_bias=-6.0, conv_gain=2.15, reg_peak=8.0, reg_sharp=0.3,
-                                 reg_std=0.1)
+    g, sd, _ = fixture_inputs(variant, load_fixture(variant, "strict"))
     return g, sd, synthetic_scene(batch, seed=11)
 
 
