@@ -10,6 +10,8 @@
  *   mafb200_maxpool2x2       MP inside MPRep                               common.py:667-673,787-792
  *   mafb200_sppf_pool        SPPF's three chained 5x5 max-pools            common.py:114-129
  *   mafb200_upsample2x       nn.Upsample(None, 2, 'nearest')               configs/yaml/MAF-YOLO-n.yaml:21,26
+ *   mafb200_head_pred        Head_DepthUni cls_pred / reg_pred + sigmoid + common.py:1325-1336, yolov6/models/yolo.py:355-396
+ *                            DFL decode in the GEMM epilogue (K7)
  *   mafb200_head_decode      Head_DepthUni sigmoid + Detect_yaml eval      common.py:1332, yolov6/models/yolo.py:355-396,
  *                            branch + generate_anchors + dist2bbox         yolov6/assigners/anchor_generator.py:11-25,
  *                                                                          yolov6/utils/general.py:29-40
@@ -44,7 +46,7 @@
 extern "C" {
 #endif
 
-#define MAFB200_VERSION 100 /* 0.1.0 */
+#define MAFB200_VERSION 200 /* 0.2.0 */
 
 #if defined(__GNUC__)
 #define MAFB200_API __attribute__((visibility("default")))
@@ -200,6 +202,42 @@ MAFB200_API int32_t mafb200_head_decode_detect(const maf_tensor* cls_logits, con
 MAFB200_API int32_t mafb200_nms_select(const float* boxes, int32_t box_stride, int32_t batch, int32_t anchors, int32_t nc,
                            double iou_thres, int32_t agnostic, int32_t max_det, int32_t max_nms, float* det,
                            int32_t* count, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K7: the head's prediction convs with the detect path finished in their epilogues ---------------------------
+ * mafb200_head_pred = Head_DepthUni's `cls_pred` / `reg_pred` 1x1 conv (yolov6/layers/common.py:1325-1336) of ONE
+ * pyramid level with, in the epilogue of the tcgen05 GEMM and on the fp32 accumulators (the logits are never rounded
+ * to fp16 nor stored):
+ *   kind MAF_HEAD_CLS: the class sigmoid (common.py:1332) -> pred[b, a, 5:5+nc] (if pred) and / or the threshold pass
+ *       of non_max_suppression (yolov6/utils/nms.py:48-84) -> candidate keys + counts in `workspace` (if detect_cfg);
+ *   kind MAF_HEAD_REG: DFL softmax expectation + anchor decode + dist2bbox 'xywh' x stride (yolov6/models/yolo.py:
+ *       377-396, yolov6/assigners/anchor_generator.py:11-25, yolov6/utils/general.py:29-40) -> pred[b, a, 0:5]
+ *       = (cx, cy, w, h, 1) (if pred) and / or boxes[b, a, 0:4] (if boxes).
+ * src [n, h, w, C] is the level's cls / reg tower output; anchor a = anchor_off + y * w + x of `total_anchors`;
+ * pred is [n, total_anchors, 5+nc] fp32, boxes [n, total_anchors, 4] fp32 (16-B aligned).
+ * Weights: kind CLS — packed as for mafb200_conv1x1 (cout = nc <= 128); kind REG — reg_max must be 16 and the 68
+ * rows are permuted before packing: packed row j < 64 = channel (j / 16) * 17 + j % 16, row 64 + s = channel
+ * s * 17 + 16, rows 68..79 zero (so that a box side never straddles a 32-column TMEM load).
+ * detect_cfg: DEVICE copy of a maf_detect_cfg filled by mafb200_detect_cfg_fill (host); it is read when the kernel
+ * runs, so one captured CUDA graph serves every threshold.  workspace: layout / size of mafb200_nms; its per-image
+ * counters must be zeroed by mafb200_detect_reset (stream-ordered) before the CLS launches of a batch.
+ * With the three levels' CLS + REG launches followed by mafb200_nms_select the detections equal those of the
+ * pred-writing launches followed by mafb200_nms, bit for bit. */
+#define MAF_HEAD_CLS 0
+#define MAF_HEAD_REG 1
+typedef struct maf_detect_cfg {
+  float conf;          /* conf_thres as fp32 (torch compares in fp32) */
+  float skip_below;    /* logit bound under which sigmoid(z) cannot exceed conf */
+  int32_t multi_label; /* nms.py:57: multi_label && nc > 1 */
+  int32_t has_filter;  /* class_filter valid (the `classes` argument) */
+  uint8_t class_filter[256];
+} maf_detect_cfg;
+MAFB200_API int32_t mafb200_detect_cfg_fill(maf_detect_cfg* host_cfg, double conf_thres, int32_t multi_label, int32_t nc,
+                                const uint8_t* class_filter_host);
+MAFB200_API int32_t mafb200_detect_reset(void* workspace, int32_t batch, void* stream);
+MAFB200_API int32_t mafb200_head_pred(const maf_tensor* src, const void* w_packed, const float* bias, int32_t kind,
+                          int32_t anchor_off, int32_t total_anchors, float stride, int32_t nc, float* pred,
+                          float* boxes, const maf_detect_cfg* detect_cfg, void* workspace, size_t workspace_bytes,
+                          void* stream);
 
 /* ---- image pre-processing (the step right before the hot path) ------------------------------------
  * letterbox (yolov6/data/data_augment.py:53-83: cv2.resize INTER_LINEAR to new_w x new_h — reproduced bit for

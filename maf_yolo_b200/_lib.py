@@ -8,7 +8,10 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "libmafb200.so"
+import os
+
+# MAFB200_LIB: an A/B build of the SAME library (maf_yolo_b200/build.py, MAFB200_BUILD_SUFFIX) — never a fallback
+LIB_PATH = Path(os.environ.get("MAFB200_LIB") or Path(__file__).resolve().parent / "libmafb200.so")
 
 MAF_F16, MAF_F32, MAF_U8 = 0, 1, 2
 ACT_NONE, ACT_SILU, ACT_RELU, ACT_SIGMOID = 0, 1, 2, 3
@@ -82,8 +85,14 @@ _SIGNATURES = {
                                                C.c_size_t, C.c_void_p]),
     "mafb200_nms_select": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32,
                                        C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mafb200_detect_cfg_fill": (C.c_int32, [C.c_void_p, C.c_double, C.c_int32, C.c_int32, C.c_void_p]),
+    "mafb200_detect_reset": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "mafb200_head_pred": (C.c_int32, [_P(MafTensor), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                      C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "mafb200_launch_count": (C.c_int64, []),
 }
+DETECT_CFG_BYTES = 16 + 256  # sizeof(maf_detect_cfg)
+HEAD_CLS, HEAD_REG = 0, 1
 
 _lib = None
 

@@ -15,7 +15,10 @@ from pathlib import Path
 
 PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
-LIB_PATH = PKG_DIR / "libmafb200.so"
+# MAFB200_BUILD_SUFFIX=<name> (with MAFB200_NVCC_EXTRA=-D...) builds an A/B variant next to the default library:
+# libmafb200_<name>.so, loaded with MAFB200_LIB=<path> (maf_yolo_b200/_lib.py).  Same sources, same CUDA path.
+SUFFIX = os.environ.get("MAFB200_BUILD_SUFFIX", "")
+LIB_PATH = PKG_DIR / (f"libmafb200_{SUFFIX}.so" if SUFFIX else "libmafb200.so")
 SOURCES = ["host.cu", "gemm_tc.cu", "stem_conv.cu", "dwconv.cu", "dwconv_tc.cu", "dwpw.cu", "poolpw.cu", "pool.cu", "decode.cu", "nms.cu", "postprocess.cu", "preprocess.cu"]
 EXTRA = os.environ.get("MAFB200_NVCC_EXTRA", "").split()
 NVCC_FLAGS = EXTRA + [
@@ -42,8 +45,8 @@ def _stale(target: Path, deps: list[Path]) -> bool:
 
 def build_library(force: bool = False, verbose: bool = False) -> Path:
     nvcc = _nvcc()
-    obj_dir = PKG_DIR / "build"
-    obj_dir.mkdir(exist_ok=True)
+    obj_dir = PKG_DIR / "build" / SUFFIX if SUFFIX else PKG_DIR / "build"
+    obj_dir.mkdir(exist_ok=True, parents=True)
     headers = sorted(CSRC.glob("*.h")) + sorted(CSRC.glob("*.cuh")) + [PKG_DIR.parent / "include" / "mafb200.h"]
     jobs = []
     objs = []

@@ -29,10 +29,16 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 }
 
 // Epilogue variant with approximate transcendental units; the result is rounded to fp16 (2^-11) right after.
+// MAFB200_SILU_EXACT (build switch, A/B of the activation's contribution to the parity error): tanh from ex2 + rcp
+// (two MUFU ops, relative error ~1e-6) instead of tanh.approx.f32 (one MUFU op, relative error ~2^-11).
 __device__ __forceinline__ float tanh_approx(float x) {
+#ifdef MAFB200_SILU_EXACT
+  return __fmaf_rn(2.0f, __fdividef(1.0f, 1.0f + __expf(-2.0f * x)), -1.0f);
+#else
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+#endif
 }
 
 __device__ __forceinline__ float apply_act_fast(float x, int act) {

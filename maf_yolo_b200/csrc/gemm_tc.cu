@@ -34,6 +34,7 @@
 // (2) a 1-CTA/SM 216 KB shape keeping the 54-72 KB weight panels of the small-Cin layers resident: slower.
 // The im2col TMA itself costs ~0.35-0.55 us per 128-pixel box almost independently of the channel count
 // (one L2 request per pixel row), which is what bounds the 3x3 layers today.
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -69,6 +70,16 @@ struct GemmParams {
   int32_t st256;       // 1: every 16-column group of every output row starts 32-B aligned -> 256-bit stores
   int32_t pair;        // 3x3 s2 over PIXEL PAIRS (Cin <= 32): 6 taps (ky, pair offset) instead of 9 (ky, kx)
   uint32_t idesc;
+  // ---- K7: head-prediction epilogues (mafb200_head_pred; kEpi 1 = DFL box decode, 2 = class sigmoid / filter) ----
+  float* pred;                 // [B, A, no] fp32 or nullptr
+  float* boxes;                // [B, A, 4] fp32 or nullptr
+  const maf_detect_cfg* cfg;   // device memory; non-null = emit NMS candidates (kEpi 2)
+  int32_t* ncand;              // [B]
+  unsigned long long* keys;    // [B][cap_pow2]
+  long long cap_pow2;
+  int32_t lvl_L, lvl_w;        // anchors (= pixels) per image of this level, map width
+  int32_t anchor_off, total_anchors, no, nc;
+  float lvl_stride;
 };
 
 // 256-bit global store (SASS STG.E.ENL2.256): one full 32-byte sector per instruction
@@ -253,7 +264,160 @@ __device__ __forceinline__ void gemm_epilogue_loop(const GemmParams& p, const Ge
   }
 }
 
-template <bool kIm2col>
+// ---- K7 epilogues: the reg_pred / cls_pred GEMMs of Head_DepthUni (yolov6/layers/common.py:1325-1336) finish the
+// detect path in registers.  One thread owns one accumulator row = one anchor, so the whole eval branch of
+// Detect_yaml.forward (yolov6/models/yolo.py:355-396) is per-thread work on the fp32 accumulators — the 68 reg logits
+// and 80 class logits are never rounded to fp16 and never stored:
+//   kEpi 1 (reg_pred): softmax over the 17 bins of each side, expectation with proj = 0..16 (yolo.py:377-378), anchor
+//       point (x + .5, y + .5) (anchor_generator.py:11-25), dist2bbox 'xywh' (general.py:29-40), x stride (yolo.py:389)
+//       -> pred[b, a, 0:5] = (cx, cy, w, h, 1) and / or boxes[b, a, 0:4].
+//       The packed weight rows are permuted (ops.pack_head_reg) so that a side never straddles a TMEM load:
+//       column j < 64: side j / 16, bin j % 16;  64 <= j < 68: side j - 64, bin 16;  68..79: zero padding.
+//   kEpi 2 (cls_pred): sigmoid (common.py:1332) -> pred[b, a, 5:] and / or the candidate filter of
+//       non_max_suppression (yolov6/utils/nms.py:48-84: score = cls * obj with obj == 1) -> 64-bit keys.
+// The two warp sets (epilogue warps 0-3 / 4-7) take alternate accumulator stages, 4 arrivals free a stage.
+__device__ __forceinline__ float sigmoid_fast(float v) { return __fdividef(1.0f, __fadd_rn(1.0f, __expf(-v))); }
+
+__device__ __forceinline__ float dfl_side(const float (&v)[17]) {
+  float mx = v[0];
+#pragma unroll
+  for (int i = 1; i < 17; ++i) mx = fmaxf(mx, v[i]);
+  float s = 0.f, e = 0.f;
+#pragma unroll
+  for (int i = 0; i < 17; ++i) {
+    const float ex = __expf(v[i] - mx);
+    s += ex;
+    e = fmaf(static_cast<float>(i), ex, e);
+  }
+  return e / s;
+}
+
+template <int kEpi>
+__device__ __forceinline__ void head_epilogue_loop(const GemmParams& p, const GemmSmem& sm, uint32_t tmem_base,
+                                                   uint32_t acc_cols, int mt0, int mt_step, int m_tiles, int warp,
+                                                   int lane, int ew) {
+  const float* s_bias = sm.bias;
+  const int quarter = warp & 3;
+  const int set = ew >> 2;
+  const int row = quarter * 32 + lane;
+  float conf = 2.0f, skip_below = INFINITY;
+  int multi_label = 0;
+  const uint8_t* filt = nullptr;
+  if (kEpi == 2 && p.cfg != nullptr) {
+    conf = p.cfg->conf;
+    skip_below = p.cfg->skip_below;
+    multi_label = p.cfg->multi_label;
+    if (p.cfg->has_filter) filt = p.cfg->class_filter;
+  }
+  int it = 0;
+  for (int mt = mt0; mt < m_tiles; mt += mt_step, ++it) {
+    const int as = it & 1;
+    if (as != set) continue;  // the other warp set drains this accumulator stage
+    const int m = mt * kBlockM + row;
+    const bool row_ok = m < p.M;
+    mbar_wait(&sm.tmem_full_bar[as], (it >> 1) & 1);
+    tc_fence_after_sync();
+    const uint32_t taddr = tmem_base + as * acc_cols + (static_cast<uint32_t>(quarter * 32) << 16);
+    const int b = (row_ok ? m : 0) / p.lvl_L;
+    const int al = (row_ok ? m : 0) - b * p.lvl_L;
+    const size_t grow = static_cast<size_t>(b) * p.total_anchors + p.anchor_off + al;  // row of pred / boxes
+    if (kEpi == 1) {
+      float dist[4];
+      uint32_t t16[16];
+      __syncwarp();
+      tmem_ld_32x32b_x16(taddr + 64, t16);  // bin 16 of the four sides (+ padding columns)
+      tmem_ld_wait();
+      float last[4];
+#pragma unroll
+      for (int sd = 0; sd < 4; ++sd) last[sd] = __uint_as_float(t16[sd]) + s_bias[64 + sd];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t r[32];
+        __syncwarp();
+        tmem_ld_32x32b_x32(taddr + 32 * half, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2) {
+          float v[17];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[16 * s2 + i]) + s_bias[32 * half + 16 * s2 + i];
+          v[16] = last[2 * half + s2];
+          dist[2 * half + s2] = dfl_side(v);
+        }
+      }
+      if (row_ok) {
+        const int gy = al / p.lvl_w, gx = al - gy * p.lvl_w;
+        const float ax = static_cast<float>(gx) + 0.5f, ay = static_cast<float>(gy) + 0.5f;
+        const float x1 = ax - dist[0], y1 = ay - dist[1], x2 = ax + dist[2], y2 = ay + dist[3];
+        const float st = p.lvl_stride;
+        const float cx = ((x1 + x2) / 2.0f) * st, cy = ((y1 + y2) / 2.0f) * st, bw = (x2 - x1) * st, bh = (y2 - y1) * st;
+        if (p.pred != nullptr) {
+          float* dst = p.pred + grow * p.no;
+          dst[0] = cx;
+          dst[1] = cy;
+          dst[2] = bw;
+          dst[3] = bh;
+          dst[4] = 1.0f;
+        }
+        if (p.boxes != nullptr) *reinterpret_cast<float4*>(p.boxes + grow * 4) = make_float4(cx, cy, bw, bh);
+      }
+    } else {
+      float* dst = (p.pred != nullptr && row_ok) ? p.pred + grow * p.no + 5 : nullptr;
+      const bool emit = p.cfg != nullptr && row_ok;
+      const int a = p.anchor_off + al;
+      float best = -INFINITY;  // single-label: best class probability so far (first maximum)
+      int best_c = 0;
+#pragma unroll 1
+      for (int c = 0; c < p.tile_n; c += 32) {
+        uint32_t r[32];
+        __syncwarp();
+        if (p.tile_n - c >= 32) {
+          tmem_ld_32x32b_x32(taddr + c, r);
+        } else {
+          uint32_t q[16];
+          tmem_ld_32x32b_x16(taddr + c, q);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r[i] = q[i], r[16 + i] = 0u;
+        }
+        tmem_ld_wait();
+        const int valid = min(32, p.N - c);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (j >= valid) break;
+          const float v = __fadd_rn(__uint_as_float(r[j]), s_bias[c + j]);
+          if (dst != nullptr) dst[c + j] = sigmoid_fast(v);
+          if (emit && v > skip_below) {
+            const float s = sigmoid_fast(v);  // score = cls * obj, obj == 1 (nms.py:69)
+            if (multi_label) {
+              if (s > conf && (filt == nullptr || filt[c + j] != 0)) {
+                const long long slot = atomicAdd(&p.ncand[b], 1);
+                if (slot < p.cap_pow2)
+                  p.keys[static_cast<size_t>(b) * p.cap_pow2 + slot] =
+                      (static_cast<unsigned long long>(~__float_as_uint(s)) << 32) |
+                      static_cast<unsigned long long>(static_cast<unsigned>(a) * p.nc + (c + j));
+              }
+            } else if (s > best) {
+              best = s;
+              best_c = c + j;
+            }
+          }
+        }
+      }
+      if (emit && !multi_label && best > conf && (filt == nullptr || filt[best_c] != 0)) {
+        const long long slot = atomicAdd(&p.ncand[b], 1);
+        if (slot < p.cap_pow2)
+          p.keys[static_cast<size_t>(b) * p.cap_pow2 + slot] =
+              (static_cast<unsigned long long>(~__float_as_uint(best)) << 32) |
+              static_cast<unsigned long long>(static_cast<unsigned>(a) * p.nc + best_c);
+      }
+    }
+    tc_fence_before_sync();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.tmem_empty_bar[as]);
+  }
+}
+
+template <bool kIm2col, int kEpi = 0>
 __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // keep the shared address space (no generic-pointer arithmetic): pad up to the 1024-B swizzle alignment
@@ -295,7 +459,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], kEpiWarps);
+      mbar_init(&tmem_empty_bar[i], kEpi == 0 ? kEpiWarps : kEpiWarps / 2);
     }
     mbar_init(w_bar, 1);
     fence_barrier_init();
@@ -370,8 +534,10 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tc_kernel(const __grid_c
     }
   } else if (warp == 1) {
     if (lane == 0 && mt0 < m_tiles) gemm_mma_loop(p, sm, tmem_base, acc_cols, mt0, mt_step, m_tiles);
-  } else {
+  } else if (kEpi == 0) {
     gemm_epilogue_loop(p, sm, tmem_base, acc_cols, mt0, mt_step, m_tiles, n0, warp, lane, warp - 2);
+  } else {
+    head_epilogue_loop<kEpi>(p, sm, tmem_base, acc_cols, mt0, mt_step, m_tiles, warp, lane, warp - 2);
   }
 
   // ---- teardown -----------------------------------------------------------------------------------
@@ -474,7 +640,7 @@ static int sm_count() {
 
 enum GemmMode { kModeTma2d = 0, kModeIm2colTma = 1 };
 
-template <int kMode>
+template <int kMode, int kEpi = 0>
 static int32_t launch_gemm(GemmParams& p, int n_tiles, int total_kb, cudaStream_t stream) {
   const int b_bytes = p.tile_n * kBlockK * 2;
   const int m_tiles = ceil_div(p.M, kBlockM);
@@ -529,12 +695,12 @@ static int32_t launch_gemm(GemmParams& p, int n_tiles, int total_kb, cudaStream_
                       (2 * stages + 5) * 8 + 16 + static_cast<size_t>(p.tile_n + 32) * 8 + 1024;
   {
     static SmemOptIn opt_in;  // per device (a process-wide flag skipped the opt-in on a second GPU)
-    const int32_t rc_attr = smem_opt_in(opt_in, gemm_tc_kernel<kMode == kModeIm2colTma>, 227 * 1024, "gemm");
+    const int32_t rc_attr = smem_opt_in(opt_in, gemm_tc_kernel<kMode == kModeIm2colTma, kEpi>, 227 * 1024, "gemm");
     if (rc_attr) return rc_attr;
   }
   if (smem > 227 * 1024) return fail(MAF_E_ARG, "gemm: %zu B of shared memory needed", smem);
-  launch_pdl(gemm_tc_kernel<kMode == kModeIm2colTma>, dim3(grid), dim3(kGemmThreads), smem, stream, p);
-  return check_launch(kMode == kModeTma2d ? "conv1x1 kernel launch" : "conv3x3s2 kernel launch");
+  launch_pdl(gemm_tc_kernel<kMode == kModeIm2colTma, kEpi>, dim3(grid), dim3(kGemmThreads), smem, stream, p);
+  return check_launch(kEpi != 0 ? "head_pred kernel launch" : kMode == kModeTma2d ? "conv1x1 kernel launch" : "conv3x3s2 kernel launch");
 }
 
 }  // namespace mafb200
@@ -673,4 +839,94 @@ extern "C" int32_t mafb200_conv3x3s2_pair(const maf_tensor* src, const void* w_p
   p.out_w = dst->w;
   p.act = act;
   return launch_gemm<kModeIm2colTma>(p, n_tiles, 6, static_cast<cudaStream_t>(stream));
+}
+
+// ---- K7 host side ---------------------------------------------------------------------------------------------
+extern "C" int32_t mafb200_detect_cfg_fill(maf_detect_cfg* cfg, double conf_thres, int32_t multi_label, int32_t nc,
+                                           const uint8_t* class_filter_host) {
+  if (!cfg || nc < 1 || nc > 256) return fail(MAF_E_ARG, "detect_cfg_fill: bad arguments (nc=%d)", nc);
+  if (!(conf_thres >= 0.0 && conf_thres <= 1.0))
+    return fail(MAF_E_ARG, "detect_cfg_fill: conf_thres must be in [0,1], got %g", conf_thres);
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->conf = static_cast<float>(conf_thres);
+  // raw-value bound under which sigmoid(z) cannot exceed conf (a safety margin below logit(conf))
+  if (conf_thres <= 0.0) cfg->skip_below = -INFINITY;
+  else if (conf_thres >= 1.0) cfg->skip_below = 30.0f;
+  else cfg->skip_below = static_cast<float>(log(conf_thres / (1.0 - conf_thres)) - 0.05);
+  cfg->multi_label = (multi_label != 0 && nc > 1) ? 1 : 0;  // nms.py:57
+  if (class_filter_host) {
+    cfg->has_filter = 1;
+    memcpy(cfg->class_filter, class_filter_host, static_cast<size_t>(nc));
+  }
+  return MAF_OK;
+}
+
+extern "C" int32_t mafb200_detect_reset(void* workspace, int32_t batch, void* stream) {
+  if (!workspace || batch < 1) return fail(MAF_E_ARG, "detect_reset: bad arguments");
+  cudaError_t e = cudaMemsetAsync(workspace, 0, static_cast<size_t>(batch) * 4, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(MAF_E_CUDA, "detect_reset: cudaMemsetAsync: %s", cudaGetErrorString(e));
+  return MAF_OK;
+}
+
+extern "C" int32_t mafb200_head_pred(const maf_tensor* src, const void* w_packed, const float* bias, int32_t kind,
+                                     int32_t anchor_off, int32_t total_anchors, float stride, int32_t nc, float* pred,
+                                     float* boxes, const maf_detect_cfg* detect_cfg, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
+  if (!valid_f16_view(src) || !aligned_f16_view(src)) return fail(MAF_E_ARG, "head_pred: bad src tensor");
+  if (!w_packed || !bias || (reinterpret_cast<uintptr_t>(w_packed) & 15)) return fail(MAF_E_ARG, "head_pred: bad weights");
+  if (kind != MAF_HEAD_CLS && kind != MAF_HEAD_REG) return fail(MAF_E_ARG, "head_pred: kind %d", kind);
+  if (nc < 1 || nc > 128) return fail(MAF_E_ARG, "head_pred: nc=%d (1..128)", nc);
+  const long long L = static_cast<long long>(src->h) * src->w;
+  if (anchor_off < 0 || anchor_off + L > total_anchors) return fail(MAF_E_ARG, "head_pred: anchor range");
+  if (static_cast<long long>(total_anchors) * nc > 0x7fffffffll) return fail(MAF_E_ARG, "head_pred: anchors*nc overflows int32");
+  if (kind == MAF_HEAD_REG && !pred && !boxes) return fail(MAF_E_ARG, "head_pred(reg): neither pred nor boxes given");
+  if (kind == MAF_HEAD_CLS && !pred && !detect_cfg) return fail(MAF_E_ARG, "head_pred(cls): neither pred nor detect_cfg given");
+  if (boxes && (reinterpret_cast<uintptr_t>(boxes) & 15)) return fail(MAF_E_ALIGN, "head_pred: boxes must be 16-B aligned");
+  int32_t rc = require_sm100();
+  if (rc) return rc;
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  rc = encode_a_map_2d(&p.tmA[0], src);
+  if (rc) return rc;
+  const int cout = kind == MAF_HEAD_CLS ? nc : 68;
+  int n_tiles = 0, tile_n = 0;
+  mafb200_gemm_tiling(cout, &n_tiles, &tile_n);  // nc <= 128 and 68 -> one column tile
+  const int chans[1] = {src->c};
+  const int k_packed = mafb200_packed_k_1x1(chans, 1);
+  rc = encode_w_map(&p.tmW, w_packed, k_packed, tile_n, tile_n);
+  if (rc) return rc;
+  p.kblocks[0] = ceil_div(src->c, kBlockK);
+  p.nsrc = 1;
+  p.bias = bias;
+  p.M = src->n * src->h * src->w;
+  p.N = cout;
+  p.tile_n = tile_n;
+  p.out_h = src->h;
+  p.out_w = src->w;
+  p.pred = pred;
+  p.boxes = kind == MAF_HEAD_REG ? boxes : nullptr;
+  p.lvl_L = static_cast<int32_t>(L);
+  p.lvl_w = src->w;
+  p.anchor_off = anchor_off;
+  p.total_anchors = total_anchors;
+  p.no = 5 + nc;
+  p.nc = nc;
+  p.lvl_stride = stride;
+  if (kind == MAF_HEAD_CLS && detect_cfg) {
+    if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255)) return fail(MAF_E_ALIGN, "head_pred: workspace must be 256-B aligned");
+    if (workspace_bytes < mafb200_nms_workspace_bytes(src->n, total_anchors, nc))
+      return fail(MAF_E_WORKSPACE, "head_pred: workspace %zu < required %zu", workspace_bytes,
+                  mafb200_nms_workspace_bytes(src->n, total_anchors, nc));
+    const size_t hdr = ((static_cast<size_t>(src->n) * 4 + 255) / 256) * 256;
+    p.cfg = detect_cfg;
+    p.ncand = static_cast<int32_t*>(workspace);
+    p.keys = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(workspace) + hdr);
+    long long cap = 1;
+    while (cap < static_cast<long long>(total_anchors) * nc) cap <<= 1;
+    p.cap_pow2 = cap;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return kind == MAF_HEAD_REG ? launch_gemm<kModeTma2d, 1>(p, 1, p.kblocks[0], st)
+                              : launch_gemm<kModeTma2d, 2>(p, 1, p.kblocks[0], st);
 }

@@ -72,6 +72,11 @@ class _Op:
     act2: str = "none"
     wslice: Optional[Tuple[int, int]] = None  # channel range of the folded weight this op uses (split depth-wise convs)
     impl: str = ""                            # "" = default kernel, "tc" = tensor-core depth-wise kernel
+    level: int = -1                           # head_pred: pyramid level; anchor_off = first anchor of the level
+    anchor_off: int = 0
+    # dependencies through memory outside the arena (pred / boxes / NMS workspace), by name
+    tag_reads: Tuple[str, ...] = ()
+    tag_writes: Tuple[str, ...] = ()
     flops_per_image: int = 0
     bytes_per_image: int = 0   # algorithmic: activations read once + written once (fp16), weights excluded
 
@@ -93,13 +98,21 @@ class Plan:
     """Kernel-launch schedule + buffer liveness for one (graph, H, W); batch-size independent."""
 
     def __init__(self, graph: Graph, height: int, width: int, only_layer: Optional[int] = None,
-                 head_sigmoid: bool = False):
+                 head_sigmoid: bool = False, k7: Optional[bool] = None):
         """only_layer: plan a single yaml layer (block-level drop-in); its sources become input buffers
         (`self.inputs`), (height, width) is then the spatial size of those sources."""
         if only_layer is None:
             assert height % 32 == 0 and width % 32 == 0, "input size must be a multiple of the largest stride (32)"
         self.graph, self.height, self.width = graph, height, width
         self.only_layer, self.head_sigmoid = only_layer, head_sigmoid
+        # K7: cls_pred / reg_pred finish the detect path in their GEMM epilogues (mafb200_head_pred); no cls / reg maps,
+        # no decode kernel.  Needs the whole graph (anchor offsets), reg_max 16 and nc <= 128.  MAFB200_K7=0: the
+        # round-1 form (fp16 cls / reg maps + head_decode kernel).
+        if k7 is None:
+            k7 = os.environ.get("MAFB200_K7", "1") != "0"
+        heads = [graph.layers[i] for i in graph.head_layers]
+        self.k7 = bool(k7 and only_layer is None and not head_sigmoid and heads and
+                       all(h.reg_max == 16 for h in heads) and graph.nc <= 128)
         self.bufs: List[_Buf] = []
         self.ops: List[_Op] = []
         self.level_views: List[Tuple[_View, _View, _View]] = []  # (stem, cls_logits, reg) per head
@@ -278,6 +291,9 @@ class Plan:
                 stem = self._buf(h, w, c, f"L{i}.stem")
                 self._emit("conv1x1", f"L{i}.stem", srcs_of(l), [stem], weight=i + ".stem", act="silu")
                 res = {}
+                lvl = len(self.level_views)
+                if self.k7 and lvl == 0:  # zero the NMS candidate counters once per forward, ahead of every cls_pred
+                    self._emit("detect_reset", "detect.reset", [], [], tag_writes=("ncand",))
                 for br, cout in (("cls", g.nc), ("reg", 4 * (l.reg_max + 1))):
                     f2 = self._buf(h, w, c, f"L{i}.{br}_s")
                     if self._dwpw_ok(c, c, l.k):
@@ -287,6 +303,14 @@ class Plan:
                         t = self._buf(h, w, c, f"L{i}.{br}_dw")
                         self._emit_dw(f"L{i}.{br}_dw{l.k}", stem, t, f"{i}.{br}_dw", "none", l.k)
                         self._emit("conv1x1", f"L{i}.{br}_s", [t], [f2], weight=f"{i}.{br}_s", act="silu")
+                    if self.k7:
+                        op = self._emit("head_pred", f"L{i}.{br}_pred+{'sigmoid' if br == 'cls' else 'dfl_decode'}", [f2], [],
+                                        weight=f"{i}.{br}_pred", act=br, level=lvl, anchor_off=self.anchors,
+                                        tag_reads=("ncand",) if br == "cls" else (), tag_writes=(f"out.{br}{lvl}",))
+                        op.flops_per_image = 2 * c * cout * h * w
+                        op.bytes_per_image += 16 * h * w if br == "reg" else 0  # serving path: boxes only (fp32 x 4)
+                        res[br] = None
+                        continue
                     o = self._buf(h, w, cout, f"L{i}.{br}_pred")
                     self._emit("conv1x1", f"L{i}.{br}_pred", [f2], [o], weight=f"{i}.{br}_pred",
                                act="sigmoid" if (br == "cls" and self.head_sigmoid) else "none")
@@ -295,9 +319,11 @@ class Plan:
                 self.level_views.append(out[l.i])
                 self.anchors += h * w
             elif l.kind == "out":
+                if self.k7:
+                    continue
                 cls = [out[s][1] for s in l.frm]
                 reg = [out[s][2] for s in l.frm]
-                op = self._emit("decode", "detect.decode", cls + reg, [])
+                op = self._emit("decode", "detect.decode", cls + reg, [], tag_writes=("out",))
                 op.bytes_per_image += self.anchors * (5 + g.nc) * 4
             else:
                 raise NotImplementedError(l.kind)
@@ -340,12 +366,12 @@ class Engine:
 
     def __init__(self, graph: Graph, folded: Folded, batch: int, height: int = 640, width: int = 640,
                  device: Optional[torch.device] = None, use_cuda_graph: bool = True, reuse_buffers: Optional[bool] = None,
-                 n_streams: int = 4):
+                 n_streams: int = 4, k7: Optional[bool] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("maf_yolo_b200.Engine needs a B200 GPU: the hot path has no CPU fallback")
         self.device = torch.device(device if device is not None else "cuda")
         self.graph, self.batch, self.height, self.width = graph, batch, height, width
-        self.plan = Plan(graph, height, width)
+        self.plan = Plan(graph, height, width, k7=k7)
         self.use_cuda_graph = use_cuda_graph
         # Branch-level concurrency (captured into the CUDA graph): independent chains of the yaml graph —
         # the three heads and their cls / reg towers, the MAFPN down-sampling convs — run on side streams.
@@ -381,7 +407,12 @@ class Engine:
         self._detect_filters: Dict[Tuple[int, ...], torch.Tensor] = {}
         self.boxes: Optional[List[torch.Tensor]] = None
         self.nms_ws: Optional[List[torch.Tensor]] = None
-        self.launches_per_forward = len(self._calls)
+        # K7 detect mode: thresholds / class filter live in a small DEVICE struct the cls_pred epilogues read when they
+        # run, so one captured graph serves every (conf_thres, multi_label, classes); host copies are immutable, cached
+        self.detect_cfg_dev: Optional[torch.Tensor] = None
+        self._detect_cfg_host: Dict[object, torch.Tensor] = {}
+        self._detect_cfg_current = None
+        self.launches_per_forward = sum(1 for o in self.plan.ops if o.kind != "detect_reset")  # the reset is a memset
         self._schedule = self._make_schedule() if self.n_streams > 1 else None
         self._side_streams = [torch.cuda.Stream(device=self.device) for _ in range(self.n_streams - 1)]
 
@@ -470,6 +501,32 @@ class Engine:
             return lambda: ops.sppf_pool(reads[0], writes[0], writes[1], writes[2])
         if op.kind == "upsample2x":
             return lambda: ops.upsample2x(reads[0], writes[0])
+        if op.kind == "detect_reset":
+            def reset():
+                if self._detect is not None:
+                    ops.detect_reset(self.nms_ws[self.last_index], self.batch)
+
+            return reset
+        if op.kind == "head_pred":
+            wt, bs = folded[op.weight]
+            nc, total = self.graph.nc, self.plan.anchors
+            stride = float(self.graph.strides[op.level])
+            if op.act == "cls":
+                w, b = ops.pack_conv1x1(wt.reshape(wt.shape[0], -1), bs, [reads[0].c], device=dev)
+            else:
+                w, b = ops.pack_head_reg(wt, bs, device=dev)
+            self._weights[op.name] = (w, b)
+
+            def head_pred():
+                if self._detect is None:
+                    ops.head_pred(reads[0], w, b, op.act, op.anchor_off, total, stride, nc, pred=self.pred)
+                elif op.act == "cls":
+                    ops.head_pred(reads[0], w, b, "cls", op.anchor_off, total, stride, nc, detect_cfg=self.detect_cfg_dev,
+                                  workspace=self.nms_ws[self.last_index])
+                else:
+                    ops.head_pred(reads[0], w, b, "reg", op.anchor_off, total, stride, nc, boxes=self.boxes[self.last_index])
+
+            return head_pred
         if op.kind == "decode":
             nl = len(reads) // 2
             strides = [float(s) for s in self.graph.strides]
@@ -497,11 +554,13 @@ class Engine:
         def ranges(views):  # (byte range of the buffer, buffer identity, channel range of the view)
             return [(v.buf.offset, v.buf.offset + v.buf.nbytes(self.batch), id(v.buf), v.c_off, v.c_off + v.c) for v in views]
 
-        rd = [ranges(o.reads) for o in ops_]
-        wr = [ranges(o.writes) for o in ops_]
-        for j, o in enumerate(ops_):
-            if o.kind == "decode":
-                wr[j] = wr[j] + [(-2, -1, -1, 0, 1)]  # the pred tensor (outside the arena)
+        tags: Dict[str, int] = {}
+
+        def tag_ranges(names):  # memory outside the arena (pred / boxes / NMS workspace): one fake byte range per name
+            return [(-2 * tags.setdefault(t, len(tags)) - 2, -2 * tags[t] - 1, -1, 0, 1) for t in names]
+
+        rd = [ranges(o.reads) + tag_ranges(o.tag_reads) for o in ops_]
+        wr = [ranges(o.writes) + tag_ranges(o.tag_writes) for o in ops_]
 
         def hit(a, b):
             # byte ranges overlap, and — inside ONE buffer — so do the channel slices (disjoint channel slices of a
@@ -581,6 +640,7 @@ class Engine:
         if self.last_async_forward is not None:
             torch.cuda.current_stream(self.device).wait_event(self.last_async_forward)
             self.last_async_forward = None
+        self._upload_detect_cfg()
         for call in self._calls:
             call()
         return self.pred
@@ -597,12 +657,39 @@ class Engine:
                 nbytes = ops.nms_workspace_bytes(self.batch, a, nc)
                 self.nms_ws = [torch.empty((nbytes + 7) // 8, dtype=torch.int64, device=self.device) for _ in range(2)]
         classes = detect[2]
+        if self.plan.k7:
+            if self.detect_cfg_dev is None:
+                from ._lib import DETECT_CFG_BYTES
+
+                self.detect_cfg_dev = torch.zeros(DETECT_CFG_BYTES, dtype=torch.uint8, device=self.device)
+            if detect not in self._detect_cfg_host:
+                if len(self._detect_cfg_host) >= 64:  # bounded: drop the oldest configuration
+                    self._detect_cfg_host.pop(next(iter(self._detect_cfg_host)))
+                self._detect_cfg_host[detect] = ops.detect_cfg_host(detect[0], detect[1], self.graph.nc, classes)
+            return
         if classes is not None and classes not in self._detect_filters:
             filt = torch.zeros(self.graph.nc, dtype=torch.uint8)
             for c in classes:
                 if 0 <= int(c) < self.graph.nc:
                     filt[int(c)] = 1
             self._detect_filters[classes] = filt.to(self.device)
+
+    def _upload_detect_cfg(self) -> None:
+        """K7 detect mode: stream-ordered copy of the configuration struct (only when it changed).  Called after the
+        waits that order this forward behind the previous one, so no launch in flight still reads the old values."""
+        if self._detect is not None and self.plan.k7 and self._detect_cfg_current != self._detect:
+            self.detect_cfg_dev.copy_(self._detect_cfg_host[self._detect], non_blocking=True)
+            self._detect_cfg_current = self._detect
+
+    def _graph_key(self, k: int, detect):
+        """Captured graphs: per prediction buffer and — K7 — per MODE only (thresholds are read from device memory);
+        without K7 the thresholds are launch arguments, so per configuration, bounded to the 8 most recent."""
+        if self.plan.k7:
+            return (k, detect is not None)
+        key = (k, detect)
+        if key not in self._graphs and len(self._graphs) >= 8:
+            self._graphs.pop(next(iter(self._graphs)))
+        return key
 
     def forward(self, x: torch.Tensor, detect=None) -> torch.Tensor:
         """x: NCHW fp32/fp16 in [0,1] or uint8 -> pred [B, A, 5+nc] fp32 (engine-owned buffer); with `detect`
@@ -623,10 +710,11 @@ class Engine:
         if self.last_async_forward is not None:
             torch.cuda.current_stream(self.device).wait_event(self.last_async_forward)
             self.last_async_forward = None
+        self._upload_detect_cfg()
         # The stem kernel reads the caller's tensor (its address changes per call), so it is launched
         # eagerly; everything behind it only touches engine-owned memory and is replayed as one graph.
         self._calls[0]()
-        gkey = (k, detect)
+        gkey = self._graph_key(k, detect)
         if gkey not in self._graphs:
             for call in self._calls[1:]:  # warm-up outside capture (sets func attributes, loads modules)
                 call()

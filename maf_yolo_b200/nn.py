@@ -136,7 +136,9 @@ class B200DetectModel(torch.nn.Module):
         key = (b, h, w, str(x.device), slot)
         eng = self._engines.get(key)
         if eng is None:
-            eng = Engine(self.graph, self.folded, b, h, w, x.device, self.use_cuda_graph, n_streams=self.n_streams)
+            # return_featmaps needs the heads' cls / reg maps in memory: the round-1 form without the K7 epilogues
+            eng = Engine(self.graph, self.folded, b, h, w, x.device, self.use_cuda_graph, n_streams=self.n_streams,
+                         k7=False if self.return_featmaps else None)
             self._engines[key] = eng
         return eng
 

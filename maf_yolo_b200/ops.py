@@ -154,9 +154,50 @@ def pack_dw_tc(weight: torch.Tensor, bias: torch.Tensor, device="cuda"):
     return table.to(device), bias.to(torch.float32).contiguous().to(device)
 
 
+def pack_head_reg(weight: torch.Tensor, bias: torch.Tensor, device="cuda"):
+    """reg_pred weight [68, C(,1,1)] / bias [68] -> packed for mafb200_head_pred(kind=REG): rows permuted so that packed
+    row j < 64 is channel (j // 16) * 17 + j % 16 and row 64 + s is channel s * 17 + 16 (reg_max = 16)."""
+    w = weight.reshape(weight.shape[0], -1)
+    assert w.shape[0] == 68 and bias.numel() == 68, "K7 DFL epilogue is built for reg_max = 16 (68 channels)"
+    perm = [(j // 16) * 17 + j % 16 for j in range(64)] + [s * 17 + 16 for s in range(4)]
+    return pack_conv1x1(w[perm], bias[perm], [w.shape[1]], device=device)
+
+
+def detect_cfg_host(conf_thres: float, multi_label: bool, nc: int, classes=None) -> torch.Tensor:
+    """maf_detect_cfg (include/mafb200.h) as a pinned uint8 host tensor, filled by the library."""
+    buf = torch.zeros(_lib.DETECT_CFG_BYTES, dtype=torch.uint8).pin_memory()
+    filt = None
+    if classes is not None:
+        filt = torch.zeros(nc, dtype=torch.uint8)
+        for c in classes:
+            if 0 <= int(c) < nc:
+                filt[int(c)] = 1
+    check(lib().mafb200_detect_cfg_fill(buf.data_ptr(), float(conf_thres), int(bool(multi_label)), nc,
+                                        filt.data_ptr() if filt is not None else None))
+    return buf
+
+
 # ------------------------------------------------------------------------------------------------
 # ops
 # ------------------------------------------------------------------------------------------------
+def detect_reset(workspace: torch.Tensor, batch: int) -> None:
+    check(lib().mafb200_detect_reset(workspace.data_ptr(), batch, _stream()))
+
+
+def head_pred(src: NHWC, w_packed: torch.Tensor, bias: torch.Tensor, kind: str, anchor_off: int, total_anchors: int,
+              stride: float, nc: int, pred: Optional[torch.Tensor] = None, boxes: Optional[torch.Tensor] = None,
+              detect_cfg: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None) -> None:
+    """K7: cls_pred / reg_pred 1x1 conv of one level with sigmoid / DFL decode / candidate filter in the epilogue."""
+    check(lib().mafb200_head_pred(src.ref(), w_packed.data_ptr(), bias.data_ptr(),
+                                  _lib.HEAD_CLS if kind == "cls" else _lib.HEAD_REG, anchor_off, total_anchors,
+                                  float(stride), nc, pred.data_ptr() if pred is not None else None,
+                                  boxes.data_ptr() if boxes is not None else None,
+                                  detect_cfg.data_ptr() if detect_cfg is not None else None,
+                                  workspace.data_ptr() if workspace is not None else None,
+                                  workspace.numel() * workspace.element_size() if workspace is not None else 0, _stream()))
+
+
+
 def conv1x1(srcs: Sequence[NHWC], w_packed: torch.Tensor, bias: torch.Tensor, act, dst: NHWC,
             dst_up2x: Optional[NHWC] = None) -> None:
     arr = (MafTensor * len(srcs))(*[s.maf() for s in srcs])

@@ -46,6 +46,9 @@ REG = dict(reg_peak=8.0, reg_sharp=0.3, reg_std=0.1)
 PEAK_LOGIT = 1.5
 SCENE_SEED = 7
 KEPT, SUP, UNK = 1, 2, 0
+RICH_MIN = {"n": 15, "s": 15, "m": 8}      # surely-kept / surely-suppressed candidates a "rich" fixture needs
+RICH_LOOSE = {"n": 0.3, "s": 0.3, "m": 0.45}
+STRICT_MIN = {"n": 3, "s": 3, "m": 2}
 
 
 def certify(pred_img, conf, m_score=M_SCORE, m_iou=M_IOU):
@@ -130,9 +133,10 @@ def search(variant, ns, seeds=range(380, 440)):
             nk, nsup = int((c["status"] == KEPT).sum()), int((c["status"] == SUP).sum())
             loose = int(((c["status"] == UNK) | (c["optional"] & (c["status"] != SUP))).sum())
             cand = dict(seed=seed, bias=bias, conf=conf, pred=pred, cert=c, nk=nk, nsup=nsup, loose=loose)
-            if loose == 0 and nk >= 3 and (strict is None or nk + nsup > strict["nk"] + strict["nsup"]):
+            if loose == 0 and nk >= STRICT_MIN[variant] and (strict is None or nk + nsup > strict["nk"] + strict["nsup"]):
                 strict = cand
-            if nk >= 15 and nsup >= 15 and loose <= 0.3 * len(c["status"]) and (rich is None or nk > rich["nk"]):
+            if (nk >= RICH_MIN[variant] and nsup >= RICH_MIN[variant] and loose <= RICH_LOOSE[variant] * len(c["status"])
+                    and (rich is None or nk > rich["nk"])):
                 rich = cand
         print(f"  {variant}: seed {seed} (bias {bias}) -> rich {None if rich is None else (rich['seed'], rich['nk'], rich['nsup'], rich['loose'])}"
               f" strict {None if strict is None else (strict['seed'], strict['nk'], strict['nsup'])}", flush=True)

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.lib()
     for name in declared:
         assert hasattr(lib, name), f"libmafb200.so does not export {name}"
-    assert lib.mafb200_version() == 100
+    assert lib.mafb200_version() == 200
 
 
 def test_tiling_and_packed_k():
@@ -159,11 +159,23 @@ def test_plan_liveness_and_arena(variant):
                 assert w.shape[0] == op.reads[0].c == bias.shape[0] and w2.shape[0] == op.writes[0].c == b2.shape[0], op.name
                 assert w2.reshape(w2.shape[0], -1).shape[1] == op.reads[0].c, op.name
                 continue
+            if op.kind == "head_pred":  # K7: no arena output; cls_pred -> nc scores, reg_pred -> 4 * 17 bins
+                assert not op.writes and w.shape[0] == bias.shape[0] == (g.nc if op.act == "cls" else 68), op.name
+                assert w.reshape(w.shape[0], -1).shape[1] == op.reads[0].c, op.name
+                continue
             if op.wslice is not None:  # a split depth-wise conv uses a channel range of the folded weight
                 w, bias = w[op.wslice[0]:op.wslice[1]], bias[op.wslice[0]:op.wslice[1]]
             assert w.shape[0] == op.writes[0].c == bias.shape[0], op.name
             if op.kind == "conv1x1":
                 assert w.shape[1] == sum(v.c for v in op.reads), op.name
+    # K7: six head-prediction launches carry the decode; anchor offsets tile [0, 8400); the counter reset precedes them
+    hp = [op for op in plan.ops if op.kind == "head_pred"]
+    assert plan.k7 and len(hp) == 6 and not any(op.kind == "decode" for op in plan.ops)
+    assert sorted({(op.level, op.anchor_off) for op in hp}) == [(0, 0), (1, 6400), (2, 8000)] and plan.anchors == 8400
+    kinds = [op.kind for op in plan.ops]
+    assert kinds.count("detect_reset") == 1 and kinds.index("detect_reset") < kinds.index("head_pred")
+    old = engine.Plan(g, 640, 640, k7=False)
+    assert not old.k7 and sum(op.kind == "decode" for op in old.ops) == 1 and len(old.ops) == len(plan.ops)
     # MAFPN fusion concats became multi-source GEMMs, upsample was fused away
     assert not any(op.kind == "upsample2x" for op in plan.ops)
     assert max(len(op.reads) for op in plan.ops if op.kind == "conv1x1") == 4
@@ -194,9 +206,8 @@ def test_pad_fill_only_touches_unowned_padding(variant, monkeypatch):
     for op in plan.ops:
         for v in op.reads + op.writes:
             assert v.c_off + v.c <= v.buf.c, (op.name, v.buf.name)
-    if variant == "n":
-        assert sorted(extended) == ["L0.stem3x3s2", "L2.m0.conv1", "L2.m0.dw3+one_conv", "L31.reg_pred", "L32.reg_pred",
-                                    "L33.reg_pred"]
+    if variant == "n":  # (reg_pred no longer writes a padded map: K7 decodes in its epilogue)
+        assert sorted(extended) == ["L0.stem3x3s2", "L2.m0.conv1", "L2.m0.dw3+one_conv"]
     monkeypatch.setenv("MAFB200_PAD_FILL", "0")
     assert all(engine.pad_fill_channels(op, op.act) == 0 for op in plan.ops if op.writes)
 

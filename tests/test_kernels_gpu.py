@@ -354,6 +354,57 @@ def test_head_decode(cuda_device):
     _close(pred[..., 5:], ref[..., 5:], "decode scores", rtol=0, atol=1e-6)
 
 
+@pytest.mark.parametrize("c_in,sizes", [(128, [(16, 24), (8, 12), (5, 6)]), (192, [(40, 40), (20, 20), (10, 10)])])
+def test_head_pred_epilogues(cuda_device, c_in, sizes):
+    """K7 (mafb200_head_pred): cls_pred / reg_pred 1x1 conv + sigmoid / DFL decode in the GEMM epilogue against fp32
+    torch (conv on the fp16-rounded operands, then the reference decode), and its detect mode — boxes + candidate keys
+    -> mafb200_nms_select — against mafb200_nms on the pred tensor the same kernels wrote: bit for bit."""
+    from maf_yolo_b200 import nn as mnn, ops
+
+    g = torch.Generator().manual_seed(23)
+    n, nc, strides = 2, 80, [8.0, 16.0, 32.0]
+    feats = [(torch.randn(n, c_in, h, w, generator=g)).half().float() for h, w in sizes]
+    wc = [(torch.randn(nc, c_in, generator=g) * 0.25).half().float() for _ in sizes]
+    bc = [torch.randn(nc, generator=g) * 0.5 - 3.0 for _ in sizes]
+    wr = [(torch.randn(68, c_in, generator=g) * 0.2).half().float() for _ in sizes]
+    br = [torch.randn(68, generator=g) for _ in sizes]
+    cls = [torch.einsum("nchw,oc->nohw", f, w_) + b_.view(1, -1, 1, 1) for f, w_, b_ in zip(feats, wc, bc)]
+    reg = [torch.einsum("nchw,oc->nohw", f, w_) + b_.view(1, -1, 1, 1) for f, w_, b_ in zip(feats, wr, br)]
+    ref = _decode_ref(cls, reg, strides)
+    total = sum(h * w for h, w in sizes)
+    pred = torch.full((n, total, 5 + nc), float("nan"), device=cuda_device)
+    boxes = torch.full((n, total, 4), float("nan"), device=cuda_device)
+    ws = torch.empty((ops.nms_workspace_bytes(n, total, nc) + 7) // 8, dtype=torch.int64, device=cuda_device)
+    packed, off = [], 0
+    for (h, w), f, w_c, b_c, w_r, b_r, st in zip(sizes, feats, wc, bc, wr, br, strides):
+        src = ops.NHWC.from_nchw(f.to(cuda_device))
+        pc = ops.pack_conv1x1(w_c, b_c, [c_in], device=cuda_device)
+        pr = ops.pack_head_reg(w_r, b_r, device=cuda_device)
+        packed.append((src, pc, pr, off, st))
+        ops.head_pred(src, *pc, "cls", off, total, st, nc, pred=pred)
+        ops.head_pred(src, *pr, "reg", off, total, st, nc, pred=pred)
+        off += h * w
+    torch.cuda.synchronize()
+    assert not torch.isnan(pred).any(), "every element of pred must be written by the six launches"
+    _close(pred[..., :4], ref[..., :4], "K7 boxes", rtol=1e-5, atol=2e-3)
+    assert (pred[..., 4] == 1).all()
+    _close(pred[..., 5:], ref[..., 5:], "K7 scores", rtol=0, atol=2e-5)
+    for kw in (dict(conf_thres=0.03, multi_label=True), dict(conf_thres=0.05, multi_label=False),
+               dict(conf_thres=0.03, multi_label=True, classes=[1, 5, 7, 40])):
+        want_d, want_c = mnn.non_max_suppression_padded(pred, iou_thres=0.65, **kw)
+        cfg = ops.detect_cfg_host(kw["conf_thres"], kw["multi_label"], nc, kw.get("classes")).to(cuda_device)
+        ops.detect_reset(ws, n)
+        for src, pc, pr, off, st in packed:
+            ops.head_pred(src, *pc, "cls", off, total, st, nc, detect_cfg=cfg, workspace=ws)
+            ops.head_pred(src, *pr, "reg", off, total, st, nc, boxes=boxes)
+        det = torch.empty_like(want_d)
+        cnt = torch.empty_like(want_c)
+        ops.nms_select(boxes, nc, 0.65, False, 300, 30000, det, cnt, ws)
+        torch.cuda.synchronize()
+        assert int(want_c.sum()) > 0 and torch.equal(cnt, want_c) and torch.equal(det, want_d), kw
+    assert torch.equal(boxes, pred[..., :4])
+
+
 from tests._synthetic import synthetic_pred as _synthetic_pred  # noqa: E402
 
 

@@ -212,7 +212,9 @@ def test_conditioned_detections_match_reference(cuda_device, variant, kind):
     g, sd, x = _cond.fixture_inputs(variant, fx)
     spec = om.parse_model(om.variant_rows(variant))
     ref = om.forward_train_form(spec, sd, x)
-    assert np.array_equal(ref[0, ::16].numpy(), fx["pred_sample"]), "oracle forward != committed reference output"
+    # (not bit-equal across machines: torch's CPU conv kernels differ by host; the build container's run IS bit-equal,
+    # tests/test_oracle_cpu.py)
+    assert np.allclose(ref[0, ::16].numpy(), fx["pred_sample"], rtol=2e-4, atol=2e-5), "oracle forward != committed reference output"
     conf, iou = float(fx["conf"]), float(fx["iou"])
     model = mb.from_state_dict(sd, variant, in_flight=2)
     xd = x.to(cuda_device)

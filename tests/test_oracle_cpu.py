@@ -133,9 +133,13 @@ def test_oracle_reproduces_conditioned_fixtures(variant, kind):
     g, sd, x = _cond.fixture_inputs(variant, fx)
     spec = om.parse_model(om.variant_rows(variant))
     pred = om.forward_train_form(spec, sd, x)
-    assert np.array_equal(pred[0, ::16].numpy(), fx["pred_sample"])
     dets = onms.non_max_suppression(pred.numpy(), float(fx["conf"]), float(fx["iou"]), multi_label=True)
-    assert np.array_equal(dets[0], fx["det0"])
+    if ref_loader.available():  # the machine that generated the fixtures: bit for bit
+        assert np.array_equal(pred[0, ::16].numpy(), fx["pred_sample"])
+        assert np.array_equal(dets[0], fx["det0"])
+    else:  # another host CPU: torch's conv kernels differ in the last bits
+        assert np.allclose(pred[0, ::16].numpy(), fx["pred_sample"], rtol=2e-4, atol=2e-5)
+        _cond.check_against_fixture(dets[0], fx, f"{variant}/{kind} oracle on this host")
     # the certification stored with the fixture is consistent with the reference's own output
     st, opt = fx["cand_status"], fx["cand_optional"]
     r = _cond.check_against_fixture(fx["det0"], fx, f"{variant}/{kind} reference vs its own certification")

@@ -63,9 +63,11 @@ def test_batch_feeds_the_model(cuda_device):
     assert shapes[0][0] == (480, 640) and shapes[0][1][1] == (0.0, 80.0)
     # the dataloader's `shapes` when the images are load_image outputs of larger files (datasets.py:215, 280-301)
     orig = [(960, 1280), (1000, 750)]
-    assert [pre.load_image_size(h0, w0, 640) for h0, w0 in orig] == [(480, 640), (500, 375)]
-    _, shapes2 = pre.letterbox_batch(ims, 640, device=cuda_device, orig_shapes=orig)
-    for (h, w), (h0, w0), sh in zip([(480, 640), (500, 375)], orig, shapes2):
+    sizes = [pre.load_image_size(h0, w0, 640) for h0, w0 in orig]
+    assert sizes == [(480, 640), (640, 480)]
+    ims2 = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for (h, w) in sizes]
+    _, shapes2 = pre.letterbox_batch(ims2, 640, device=cuda_device, orig_shapes=orig)
+    for (h, w), (h0, w0), sh in zip(sizes, orig, shapes2):
         _, ratio, pad = opre.letterbox(np.zeros((h, w, 3), np.uint8), 640, auto=False, scaleup=False)
         assert sh == ((h0, w0), ((h * ratio / h0, w * ratio / w0), pad))
     g = topology.build_graph("n")
