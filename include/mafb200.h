@@ -7,6 +7,7 @@
  *   mafb200_conv3x3s2        RepVGGBlock / ConvWrapper 3x3 stride 2        common.py:76-83,166-283,776-792
  *   mafb200_conv1x1          Conv(k=1) incl. the Concat that feeds it      common.py:29-50,148-154,938-946
  *   mafb200_dwconv           UniRepLKNetBlock / DilatedReparamBlock deploy common.py:2948-3100
+ *   mafb200_bottleneck       DepthBottleneckUni, all three convs (K4)       common.py:898-927
  *   mafb200_maxpool2x2       MP inside MPRep                               common.py:667-673,787-792
  *   mafb200_sppf_pool        SPPF's three chained 5x5 max-pools            common.py:114-129
  *   mafb200_upsample2x       nn.Upsample(None, 2, 'nearest')               configs/yaml/MAF-YOLO-n.yaml:21,26
@@ -147,6 +148,20 @@ MAFB200_API int32_t mafb200_dwconv_tc(const maf_tensor* src, const void* table, 
 MAFB200_API int32_t mafb200_dwconv_conv1x1(const maf_tensor* src, const float* dw_weight, const float* dw_bias, int32_t k,
                                int32_t act1, const void* pw_packed, const float* pw_bias, int32_t act2,
                                const maf_tensor* dst, void* stream);
+
+/* ---- K4: the whole DepthBottleneckUni in one kernel (k in 3,5; c_in <= 64, mid <= 192, c_out <= 64) -------------
+ * dst = SiLU(W2 * SiLU(DW_k(SiLU(W1 * src + b1)) + dw_bias) + b2): conv1 (1x1, c_in -> mid) -> UniRepLKNetBlock deploy
+ * form (depth-wise k x k) -> SiLU -> one_conv (1x1, mid -> c_out), yolov6/layers/common.py:898-927.  The mid-wide
+ * (3 c_) intermediate never goes to HBM: a persistent warp-specialised CTA per SM computes it per 10x20-pixel tile
+ * (with its k-1 halo) into shared memory from a TMA halo tile of src and feeds the taps from there.
+ * Packed operands, with mid_pad = round_up(mid, 64) and tile_n = round_up(dst->c, 16):
+ *   w1_packed fp16 [mid_pad][64] (row = mid channel; zero beyond mid / c_in), b1 fp32 [mid_pad];
+ *   dw_weight fp32 [k*k][mid_pad] tap-major, dw_bias fp32 [mid_pad];  w2_packed fp16 [tile_n][mid_pad], b2 fp32 [tile_n].
+ * mafb200_bottleneck_supported: 1 if the shape fits this kernel (pure host arithmetic), else 0. */
+MAFB200_API int32_t mafb200_bottleneck_supported(int32_t c_in, int32_t mid, int32_t c_out, int32_t k);
+MAFB200_API int32_t mafb200_bottleneck(const maf_tensor* src, int32_t mid, const void* w1_packed, const float* b1,
+                           const float* dw_weight, const float* dw_bias, int32_t k, const void* w2_packed,
+                           const float* b2, const maf_tensor* dst, void* stream);
 
 /* ---- 2x2 max pool fused with the 1x1 conv that consumes it (C <= 256, cout <= 128) ------------------------
  * dst = act(W * maxpool2x2(src) + bias): the first branch of MPRep, conv1(mp(x)) (common.py:787-792, MP at

@@ -64,6 +64,9 @@ _SIGNATURES = {
                                       C.c_void_p]),
     "mafb200_dwconv_conv1x1": (C.c_int32, [_P(MafTensor), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                            C.c_void_p, C.c_int32, _P(MafTensor), C.c_void_p]),
+    "mafb200_bottleneck_supported": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "mafb200_bottleneck": (C.c_int32, [_P(MafTensor), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                       C.c_void_p, C.c_void_p, _P(MafTensor), C.c_void_p]),
     "mafb200_maxpool2x2_conv1x1": (C.c_int32, [_P(MafTensor), C.c_void_p, C.c_void_p, C.c_int32, _P(MafTensor), C.c_void_p]),
     "mafb200_maxpool2x2": (C.c_int32, [_P(MafTensor), _P(MafTensor), C.c_void_p]),
     "mafb200_sppf_pool": (C.c_int32, [_P(MafTensor), _P(MafTensor), _P(MafTensor), _P(MafTensor), C.c_void_p]),

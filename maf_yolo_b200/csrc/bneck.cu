@@ -1,0 +1,480 @@
+// K4 — the whole DepthBottleneckUni (yolov6/layers/common.py:898-927, deploy form) in ONE kernel:
+//
+//     y = SiLU( W2 * SiLU( DW_k( SiLU( W1 * x + b1 ) ) + bd ) + b2 )
+//         x : [n,h,w,c_] fp16 NHWC (a channel slice of the RepHDW concat buffer)      c_  <= 64
+//         t1: 3c_ = `mid` channels, NEVER in HBM (round 1: written by one GEMM, re-read by dwpw_kernel)  mid <= 192
+//         y : [n,h,w,c_] (the next channel slice of the same buffer)
+//
+// Persistent, warp-specialised CTA, one per SM (it owns the SM's 512 TMEM columns and ~226 KB of shared memory);
+// a CTA loops over 10 x 20-pixel output tiles, and per tile over 64-channel blocks `cb` of the mid channels:
+//
+//   warp 13 lane 0  TMA: W1 / W2 panels once (resident), then per tile the HALO tile of x — (10+k-1) x (20+k-1) pixels
+//                   x 64 channels as ONE 4-D box, SWIZZLE_128B: rows = halo pixels, i.e. directly the K-major A operand
+//                   of the expand GEMM (out-of-image pixels and channels >= c_ are zero-filled by the TMA unit)
+//   warp 12 lane 0  tcgen05.mma issuer:  MMA1(cb): acc1[cb&1][3 M tiles x 64 cols] = Xhalo[384 x 64] * W1[cb]^T
+//                                        MMA2(cb): acc2[2 M tiles x c_ cols]     += A2[256 x 64]    * W2[cb]^T
+//   warps 8-11      epilogue 1: acc1 -> +b1 -> SiLU -> 0 for pixels outside the image (the depth-wise conv pads t1, not
+//                   x) -> fp16 -> T1[cb&1] in shared memory (pixel rows of 128 B, 16-byte chunk ^ (row & 7): conflict
+//                   free for one-row-per-thread writes);  epilogue 2 (once per tile): acc2 -> +b2 -> SiLU -> global
+//   warps 0-7       depth-wise taps: warp = 5 x 5 pixel unit, lane = channel pair; 25 x k*k packed FFMA2 from T1, +bd,
+//                   SiLU, fp16 pairs into the hand-swizzled SW128 A2 tile -> fence.proxy.async -> MMA2
+//
+// so that the three pipes the block needs run CONCURRENTLY: FFMA (taps), MUFU (the three SiLUs, mostly in the epilogue
+// warps) and the tensor core; T1 and acc1 are double buffered (epilogue 1 of block cb+1 overlaps the taps of block cb).
+// All barriers are mbarriers with explicit phase arithmetic on the running step s = tile_iteration * nblk + cb.
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "host.h"
+
+namespace mafb200 {
+
+constexpr int kBnTX = 20, kBnTY = 10;      // output tile
+constexpr int kBnCB = 64;                  // mid channels per block = one 128-byte swizzle row
+constexpr int kBnTapWarps = 8, kBnEpiWarps = 4;
+constexpr int kBnThreads = 32 * (kBnTapWarps + kBnEpiWarps + 2);  // + MMA warp + TMA warp = 448
+constexpr int kBnMaxMid = 192, kBnMaxCin = 64;
+constexpr int kBnAcc1Cols = 3 * kBnCB;     // 192: three M tiles of the halo
+constexpr int kBnAcc2Col0 = 2 * kBnAcc1Cols;  // 384
+constexpr int kBnA2Bytes = kBnTX * kBnTY * 128;  // 25600: 200 pixel rows (the MMA reads 256; the rest is never used)
+
+struct BneckParams {
+  CUtensorMap tm_x;    // x as {c_, W, H, N}, box {64, TW, TH, 1}, SWIZZLE_128B
+  CUtensorMap tm_w1;   // W1 packed fp16 [mid_pad][64], box {64, mid_pad}, SWIZZLE_128B
+  CUtensorMap tm_w2;   // W2 packed fp16 [tile_n][mid_pad], box {64, tile_n}, SWIZZLE_128B
+  const float* b1;     // [mid_pad]
+  const float* dw_w;   // [k*k][mid_pad] fp32
+  const float* dw_b;   // [mid_pad]
+  const float* b2;     // [tile_n]
+  __half* out;
+  int32_t out_ld;
+  int32_t H, W, N, tile_n, mid_pad, nblk;
+  int32_t tiles_x, tiles_y, tiles;  // tiles = n * tiles_y * tiles_x
+  uint32_t idesc1, idesc2;
+};
+
+__device__ __forceinline__ float silu_fast(float x) {
+  const float h = 0.5f * x;
+  return fmaf(h, tanh_approx(h), h);
+}
+
+template <int K>
+__global__ void __launch_bounds__(kBnThreads, 1) bneck_kernel(const __grid_constant__ BneckParams p) {
+  constexpr int P = K / 2;
+  constexpr int TW = kBnTX + K - 1, TH = kBnTY + K - 1;
+  constexpr int kHaloRows = TH * TW;
+  constexpr uint32_t kXBytes = kHaloRows * 128;  // a multiple of 1024 for K = 3 (33792) and K = 5 (43008)
+  static_assert(kXBytes % 1024 == 0 && kHaloRows <= 384, "halo tile must be whole swizzle atoms and fit 3 M tiles");
+
+  extern __shared__ uint8_t smem_bn_raw[];
+  uint8_t* smem = smem_bn_raw + ((1024u - (smem_u32(smem_bn_raw) & 1023u)) & 1023u);
+  const int nblk = p.nblk, mid_pad = p.mid_pad;
+  const int w2_blk = p.tile_n * 128;
+  uint8_t* s_w1 = smem;                                   // [mid_pad rows][128 B]
+  uint8_t* s_w2 = s_w1 + mid_pad * 128;                   // nblk x [tile_n rows][128 B]
+  uint8_t* s_x = s_w2 + nblk * w2_blk;                    // [kHaloRows][128 B]; MMA1 reads 384 rows (tail = garbage rows)
+  uint8_t* s_a2 = s_x + kXBytes;                          // [200 rows][128 B]; MMA2 reads 256 rows
+  uint8_t* s_t1 = s_a2 + kBnA2Bytes;                      // 2 x [kHaloRows][128 B], chunk-swizzled by hand
+  float* s_dw = reinterpret_cast<float*>(s_t1 + 2 * kXBytes);  // [K*K][mid_pad]
+  float* s_b1 = s_dw + K * K * mid_pad;                   // [mid_pad]
+  float* s_bd = s_b1 + mid_pad;                           // [mid_pad]
+  float* s_b2 = s_bd + mid_pad;                           // [tile_n]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_b2 + p.tile_n + (p.tile_n & 1));
+  uint64_t* bar_w = bars;                // W1 + W2 landed
+  uint64_t* bar_x_full = bars + 1;       // halo tile landed (phase per tile)
+  uint64_t* bar_x_empty = bars + 2;      // last MMA1 of the tile has read it
+  uint64_t* bar_acc1_full = bars + 3;    // [2] MMA1(s) complete
+  uint64_t* bar_acc1_empty = bars + 5;   // [2] epilogue 1 has drained acc1[s & 1]        (4 warps)
+  uint64_t* bar_t1_full = bars + 7;      // [2] epilogue 1 has written T1[s & 1]          (4 warps)
+  uint64_t* bar_t1_empty = bars + 9;     // [2] the tap warps have read T1[s & 1]         (8 warps)
+  uint64_t* bar_a2_full = bars + 11;     // the tap warps have written A2                 (8 warps)
+  uint64_t* bar_a2_empty = bars + 12;    // MMA2(s) complete
+  uint64_t* bar_acc2_full = bars + 13;   // last MMA2 of the tile complete
+  uint64_t* bar_acc2_empty = bars + 14;  // epilogue 2 has drained acc2                   (4 warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int my_tiles = (p.tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int total_steps = my_tiles * nblk;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(bar_x_full, 1);
+    mbar_init(bar_x_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_acc1_full[i], 1);
+      mbar_init(&bar_acc1_empty[i], kBnEpiWarps);
+      mbar_init(&bar_t1_full[i], kBnEpiWarps);
+      mbar_init(&bar_t1_empty[i], kBnTapWarps);
+    }
+    mbar_init(bar_a2_full, kBnTapWarps);
+    mbar_init(bar_a2_empty, 1);
+    mbar_init(bar_acc2_full, 1);
+    mbar_init(bar_acc2_empty, kBnEpiWarps);
+    fence_barrier_init();
+  }
+  if (warp == kBnTapWarps + kBnEpiWarps) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  // constants of the whole kernel (weights of the model): read before griddepcontrol.wait
+  for (int i = threadIdx.x; i < K * K * mid_pad; i += kBnThreads) s_dw[i] = __ldg(p.dw_w + i);
+  for (int i = threadIdx.x; i < mid_pad; i += kBnThreads) {
+    s_b1[i] = __ldg(p.b1 + i);
+    s_bd[i] = __ldg(p.dw_b + i);
+  }
+  for (int i = threadIdx.x; i < p.tile_n; i += kBnThreads) s_b2[i] = __ldg(p.b2 + i);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) pdl_launch_dependents();
+
+  if (warp == kBnTapWarps + kBnEpiWarps + 1) {
+    // ================================ TMA producer ===========================================================
+    if (lane == 0 && my_tiles > 0) {
+      tma_prefetch_desc(&p.tm_x);
+      mbar_arrive_expect_tx(bar_w, mid_pad * 128 + nblk * w2_blk);
+      tma_load_2d(s_w1, &p.tm_w1, bar_w, 0, 0);
+      for (int cb = 0; cb < nblk; ++cb) tma_load_2d(s_w2 + cb * w2_blk, &p.tm_w2, bar_w, cb * kBnCB, 0);
+      pdl_wait();  // x is produced by the previous kernel; every store of this kernel follows causally
+      int it = 0;
+      for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++it) {
+        const int img = t / tiles_per_img, r = t - img * tiles_per_img;
+        const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+        mbar_wait(bar_x_empty, (it & 1) ^ 1);
+        mbar_arrive_expect_tx(bar_x_full, kXBytes);
+        tma_load_tile_4d(s_x, &p.tm_x, bar_x_full, 0, tx * kBnTX - P, ty * kBnTY - P, img);
+      }
+    }
+  } else if (warp == kBnTapWarps + kBnEpiWarps) {
+    // ================================ MMA issuer =============================================================
+    if (lane == 0 && my_tiles > 0) {
+      mbar_wait(bar_w, 0);
+      tc_fence_after_sync();
+      auto mma1 = [&](int s) {
+        const int it = s / nblk, cb = s - it * nblk, buf = s & 1;
+        if (cb == 0) {
+          mbar_wait(bar_x_full, it & 1);
+          tc_fence_after_sync();
+        }
+        mbar_wait(&bar_acc1_empty[buf], ((s >> 1) & 1) ^ 1);
+        tc_fence_after_sync();
+        const uint64_t db = umma_smem_desc_sw128(smem_u32(s_w1 + cb * (kBnCB * 128)));
+#pragma unroll
+        for (int mt = 0; mt < 3; ++mt) {
+          const uint64_t da = umma_smem_desc_sw128(smem_u32(s_x + mt * 16384));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc_mma_f16(tmem_base + buf * kBnAcc1Cols + mt * kBnCB, da + 2 * k, db + 2 * k, p.idesc1, k != 0 ? 1u : 0u);
+        }
+        tc_commit(&bar_acc1_full[buf]);
+        if (cb == nblk - 1) tc_commit(bar_x_empty);  // the halo tile may be overwritten once these MMAs are done
+      };
+      auto mma2 = [&](int s) {
+        const int it = s / nblk, cb = s - it * nblk;
+        if (cb == 0) {
+          mbar_wait(bar_acc2_empty, (it & 1) ^ 1);
+          tc_fence_after_sync();
+        }
+        mbar_wait(bar_a2_full, s & 1);
+        tc_fence_after_sync();
+        const uint64_t db = umma_smem_desc_sw128(smem_u32(s_w2 + cb * w2_blk));
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          const uint64_t da = umma_smem_desc_sw128(smem_u32(s_a2 + mt * 16384));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc_mma_f16(tmem_base + kBnAcc2Col0 + mt * p.tile_n, da + 2 * k, db + 2 * k, p.idesc2, (cb | k) != 0 ? 1u : 0u);
+        }
+        tc_commit(bar_a2_empty);
+        if (cb == nblk - 1) tc_commit(bar_acc2_full);
+      };
+      mma1(0);
+      if (total_steps > 1) mma1(1);
+      for (int s = 0; s < total_steps; ++s) {
+        mma2(s);
+        if (s + 2 < total_steps) mma1(s + 2);
+      }
+    }
+  } else if (warp >= kBnTapWarps) {
+    // ================================ epilogue warps =========================================================
+    const int q = warp & 3;  // TMEM lane quarter of this warp (kBnTapWarps % 4 == 0)
+    auto epilogue2 = [&](int it) {
+      const int t = blockIdx.x + it * gridDim.x;
+      const int img = t / tiles_per_img, r = t - img * tiles_per_img;
+      const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+      mbar_wait(bar_acc2_full, it & 1);
+      tc_fence_after_sync();
+#pragma unroll 1
+      for (int mt = 0; mt < 2; ++mt) {
+        const int prow = mt * 128 + q * 32 + lane;
+        const int py = prow / kBnTX, px = prow - py * kBnTX;
+        const int gy = ty * kBnTY + py, gx = tx * kBnTX + px;
+        const bool ok = prow < kBnTX * kBnTY && gy < p.H && gx < p.W;
+        __half* orow = p.out + ((static_cast<size_t>(img) * p.H + (ok ? gy : 0)) * p.W + (ok ? gx : 0)) * p.out_ld;
+        const uint32_t taddr = tmem_base + kBnAcc2Col0 + mt * p.tile_n + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+        for (int c = 0; c < p.tile_n; c += 16) {
+          uint32_t rr[16];
+          __syncwarp();
+          tmem_ld_32x32b_x16(taddr + c, rr);
+          tmem_ld_wait();
+          if (ok && c < p.N) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              pk[j] = pack_half2(silu_fast(__uint_as_float(rr[2 * j]) + s_b2[c + 2 * j]),
+                                 silu_fast(__uint_as_float(rr[2 * j + 1]) + s_b2[c + 2 * j + 1]));
+            if (c + 16 <= p.N) {
+              asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(orow + c), "r"(pk[0]),
+                           "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
+                           : "memory");
+            } else {  // N % 16 == 8
+              *reinterpret_cast<uint4*>(orow + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+          }
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acc2_empty);
+    };
+
+    for (int s = 0; s < total_steps; ++s) {
+      const int it = s / nblk, cb = s - it * nblk, buf = s & 1;
+      const int t = blockIdx.x + it * gridDim.x;
+      const int img_r = t % tiles_per_img;
+      const int ty = img_r / p.tiles_x, tx = img_r - ty * p.tiles_x;
+      const int hy0 = ty * kBnTY - P, hx0 = tx * kBnTX - P;  // image coordinates of halo pixel (0, 0)
+      mbar_wait(&bar_acc1_full[buf], (s >> 1) & 1);
+      tc_fence_after_sync();
+      mbar_wait(&bar_t1_empty[buf], ((s >> 1) & 1) ^ 1);
+      uint8_t* t1 = s_t1 + buf * kXBytes;
+      const float* b1 = s_b1 + cb * kBnCB;
+#pragma unroll 1
+      for (int mt = 0; mt < 3; ++mt) {
+        const int prow = mt * 128 + q * 32 + lane;  // halo pixel of this thread
+        const int py = prow / TW, px = prow - py * TW;
+        const int gy = hy0 + py, gx = hx0 + px;
+        const bool row_ok = prow < kHaloRows;
+        const bool inside = row_ok && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
+        uint8_t* trow = t1 + prow * 128;
+        const uint32_t taddr = tmem_base + buf * kBnAcc1Cols + mt * kBnCB + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t rr[32];
+          __syncwarp();
+          tmem_ld_32x32b_x32(taddr + 32 * half, rr);
+          tmem_ld_wait();
+          if (row_ok) {
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {  // 16-byte chunks (8 channels) of this half
+              uint32_t pk[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int c = 8 * ch + 2 * j;
+                const float a = silu_fast(__uint_as_float(rr[c]) + b1[32 * half + c]);
+                const float b = silu_fast(__uint_as_float(rr[c + 1]) + b1[32 * half + c + 1]);
+                pk[j] = inside ? pack_half2(a, b) : 0u;  // the depth-wise conv zero-pads t1 (common.py:915-923)
+              }
+              const int chunk = 4 * half + ch;
+              *reinterpret_cast<uint4*>(trow + ((chunk ^ (prow & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+          }
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&bar_acc1_empty[buf]);
+        mbar_arrive(&bar_t1_full[buf]);
+      }
+      // the output tile whose last block was step s - 1: its MMA2 completes while the taps of step s run
+      if (s >= 1 && (s - 1) % nblk == nblk - 1) epilogue2((s - 1) / nblk);
+    }
+    if (total_steps > 0) epilogue2(my_tiles - 1);
+  } else {
+    // ================================ depth-wise tap warps ===================================================
+    const int uy = warp >> 2, ux = warp & 3;  // 2 x 4 units of 5 x 5 pixels
+    const int oy0 = uy * 5, ox0 = ux * 5;
+    const int p0 = oy0 * TW + ox0;            // halo row of the unit's first window pixel
+    for (int s = 0; s < total_steps; ++s) {
+      const int cb = s % nblk, buf = s & 1;
+      const int c0 = cb * kBnCB;
+      float2 wreg[K * K];
+#pragma unroll
+      for (int t = 0; t < K * K; ++t) wreg[t] = *reinterpret_cast<const float2*>(s_dw + t * mid_pad + c0 + 2 * lane);
+      const float2 bv = *reinterpret_cast<const float2*>(s_bd + c0 + 2 * lane);
+      // T1 row r holds its 16-byte chunk j at position j ^ (r & 7): one base pointer per value of (row & 7), so that
+      // every window load below is [base + immediate]
+      const uint8_t* t1 = s_t1 + buf * kXBytes + p0 * 128 + ((lane & 3) << 2);
+      const uint8_t* tb[8];
+#pragma unroll
+      for (int v = 0; v < 8; ++v) tb[v] = t1 + ((((p0 + v) & 7) ^ (lane >> 2)) << 4);
+
+      mbar_wait(&bar_t1_full[buf], (s >> 1) & 1);
+
+      float2 acc[5][5];
+#pragma unroll
+      for (int i = 0; i < 5; ++i)
+#pragma unroll
+        for (int r = 0; r < 5; ++r) acc[i][r] = bv;
+#pragma unroll
+      for (int d = 0; d < 5 + K - 1; ++d) {
+        float2 win[5 + K - 1];
+#pragma unroll
+        for (int j = 0; j < 5 + K - 1; ++j)
+          win[j] = __half22float2(*reinterpret_cast<const __half2*>(tb[(d * TW + j) & 7] + (d * TW + j) * 128));
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+          const int ky = d - i;
+          if (ky < 0 || ky >= K) continue;
+#pragma unroll
+          for (int r = 0; r < 5; ++r)
+#pragma unroll
+            for (int kx = 0; kx < K; ++kx) acc[i][r] = ffma2(win[r + kx], wreg[ky * K + kx], acc[i][r]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_t1_empty[buf]);  // this warp's reads of T1[buf] are complete
+
+      mbar_wait(bar_a2_empty, (s & 1) ^ 1);  // MMA2 of the previous step has read the A2 tile
+#pragma unroll
+      for (int i = 0; i < 5; ++i)
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+          const int prow = (oy0 + i) * kBnTX + ox0 + r;
+          *reinterpret_cast<uint32_t*>(s_a2 + prow * 128 + ((((lane >> 2) ^ (prow & 7)) << 4) | ((lane & 3) << 2))) =
+              pack_half2(silu_fast(acc[i][r].x), silu_fast(acc[i][r].y));
+        }
+      fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_a2_full);
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == kBnTapWarps + kBnEpiWarps) tmem_dealloc(tmem_base, 512);
+}
+
+static size_t bneck_smem_bytes(int k, int mid_pad, int nblk, int tile_n) {
+  const size_t halo = static_cast<size_t>(kBnTX + k - 1) * (kBnTY + k - 1) * 128;
+  return 1024 + static_cast<size_t>(mid_pad) * 128 + static_cast<size_t>(nblk) * tile_n * 128 + halo + kBnA2Bytes + 2 * halo +
+         (static_cast<size_t>(k) * k * mid_pad + 2 * mid_pad + tile_n + 2) * 4 + 16 * 8 + 16;
+}
+
+template <int K>
+static int32_t launch_bneck(BneckParams& p, size_t smem, cudaStream_t st) {
+  {
+    static SmemOptIn opt_in;
+    const int32_t rc = smem_opt_in(opt_in, bneck_kernel<K>, 227 * 1024, "bottleneck");
+    if (rc) return rc;
+  }
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    sms = 148;
+  const int grid = p.tiles < sms ? p.tiles : sms;
+  launch_pdl(bneck_kernel<K>, dim3(grid), dim3(kBnThreads), smem, st, p);
+  return check_launch("bottleneck kernel launch");
+}
+
+}  // namespace mafb200
+
+using namespace mafb200;
+
+// Can mafb200_bottleneck run this shape?  (pure host arithmetic; the engine asks before planning the fused op)
+extern "C" int32_t mafb200_bottleneck_supported(int32_t c_in, int32_t mid, int32_t c_out, int32_t k) {
+  if ((k != 3 && k != 5) || c_in < 8 || c_in > kBnMaxCin || c_in % 8 || mid < 8 || mid > kBnMaxMid || mid % 8 ||
+      c_out < 8 || c_out > 64 || c_out % 8)
+    return 0;
+  const int mid_pad = round_up(mid, kBnCB), tile_n = round_up(c_out, 16);
+  return bneck_smem_bytes(k, mid_pad, mid_pad / kBnCB, tile_n) <= 227 * 1024 ? 1 : 0;
+}
+
+// dst = SiLU(W2 * SiLU(DW_k(SiLU(W1 * src + b1)) + dw_bias) + b2)     (DepthBottleneckUni, common.py:898-927)
+//   w1_packed fp16 [mid_pad][64]  (row = mid channel, zero rows / columns beyond mid / c_in),  b1 fp32 [mid_pad]
+//   dw_weight fp32 [k*k][mid_pad] (tap-major, zero beyond mid),                                 dw_bias fp32 [mid_pad]
+//   w2_packed fp16 [tile_n][mid_pad] (row = output channel),                                    b2 fp32 [tile_n]
+// with mid_pad = round_up(mid, 64), tile_n = round_up(dst->c, 16).
+extern "C" int32_t mafb200_bottleneck(const maf_tensor* src, int32_t mid, const void* w1_packed, const float* b1,
+                                      const float* dw_weight, const float* dw_bias, int32_t k, const void* w2_packed,
+                                      const float* b2, const maf_tensor* dst, void* stream) {
+  if (!valid_f16_view(src) || !valid_f16_view(dst)) return fail(MAF_E_ARG, "bottleneck: bad src/dst");
+  if (!w1_packed || !b1 || !dw_weight || !dw_bias || !w2_packed || !b2) return fail(MAF_E_ARG, "bottleneck: null weights");
+  if (!same_nhw(src, dst)) return fail(MAF_E_ARG, "bottleneck: src/dst n/h/w differ");
+  if (!mafb200_bottleneck_supported(src->c, mid, dst->c, k))
+    return fail(MAF_E_ARG, "bottleneck: unsupported shape (c_in=%d mid=%d c_out=%d k=%d)", src->c, mid, dst->c, k);
+  if (!aligned_f16_view(src)) return fail(MAF_E_ALIGN, "bottleneck: src must be 16-B aligned with c_stride %% 8 == 0");
+  if ((reinterpret_cast<uintptr_t>(dst->ptr) & 31) || (dst->c_stride % 16) != 0)
+    return fail(MAF_E_ALIGN, "bottleneck: dst must be 32-B aligned with c_stride %% 16 == 0");
+  if ((reinterpret_cast<uintptr_t>(w1_packed) & 15) || (reinterpret_cast<uintptr_t>(w2_packed) & 15) ||
+      (reinterpret_cast<uintptr_t>(dw_weight) & 7) || (reinterpret_cast<uintptr_t>(dw_bias) & 7))
+    return fail(MAF_E_ALIGN, "bottleneck: weight alignment");
+  int32_t rc = require_sm100();
+  if (rc) return rc;
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return fail(MAF_E_ARCH, "cuTensorMapEncodeTiled entry point not available");
+
+  BneckParams p;
+  memset(&p, 0, sizeof(p));
+  const int mid_pad = round_up(mid, kBnCB), tile_n = round_up(dst->c, 16);
+  {
+    const int TW = kBnTX + k - 1, TH = kBnTY + k - 1;
+    const cuuint64_t px = static_cast<cuuint64_t>(src->c_stride) * 2;
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(src->c), static_cast<cuuint64_t>(src->w),
+                          static_cast<cuuint64_t>(src->h), static_cast<cuuint64_t>(src->n)};
+    cuuint64_t strides[3] = {px, px * src->w, px * src->w * src->h};
+    cuuint32_t box[4] = {kBnCB, static_cast<cuuint32_t>(TW), static_cast<cuuint32_t>(TH), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&p.tm_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, src->ptr, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(MAF_E_CUDA, "bottleneck: cuTensorMapEncodeTiled(src) failed: %d", (int)r);
+  }
+  {
+    cuuint64_t dims[2] = {kBnCB, static_cast<cuuint64_t>(mid_pad)};
+    cuuint64_t strides[1] = {kBnCB * 2};
+    cuuint32_t box[2] = {kBnCB, static_cast<cuuint32_t>(mid_pad)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&p.tm_w1, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(w1_packed), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(MAF_E_CUDA, "bottleneck: cuTensorMapEncodeTiled(W1) failed: %d", (int)r);
+  }
+  {
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(mid_pad), static_cast<cuuint64_t>(tile_n)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(mid_pad) * 2};
+    cuuint32_t box[2] = {kBnCB, static_cast<cuuint32_t>(tile_n)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&p.tm_w2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(w2_packed), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(MAF_E_CUDA, "bottleneck: cuTensorMapEncodeTiled(W2) failed: %d", (int)r);
+  }
+  p.b1 = b1;
+  p.dw_w = dw_weight;
+  p.dw_b = dw_bias;
+  p.b2 = b2;
+  p.out = static_cast<__half*>(dst->ptr);
+  p.out_ld = dst->c_stride;
+  p.H = src->h;
+  p.W = src->w;
+  p.N = dst->c;
+  p.tile_n = tile_n;
+  p.mid_pad = mid_pad;
+  p.nblk = mid_pad / kBnCB;
+  p.tiles_x = ceil_div(src->w, kBnTX);
+  p.tiles_y = ceil_div(src->h, kBnTY);
+  const long long tiles = static_cast<long long>(src->n) * p.tiles_x * p.tiles_y;
+  if (tiles > 0x7fffffff) return fail(MAF_E_ARG, "bottleneck: too many tiles");
+  p.tiles = static_cast<int32_t>(tiles);
+  p.idesc1 = umma_idesc_f16(128, kBnCB);
+  p.idesc2 = umma_idesc_f16(128, tile_n);
+  const size_t smem = bneck_smem_bytes(k, mid_pad, p.nblk, tile_n);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return k == 3 ? launch_bneck<3>(p, smem, st) : launch_bneck<5>(p, smem, st);
+}

@@ -160,6 +160,19 @@ __device__ __forceinline__ void tma_load_im2col_4d(void* smem_dst, const CUtenso
       : "memory");
 }
 
+// Tiled-mode 4-D load (NHWC tensor as {C, W, H, N}): the halo tile of a depth-wise / fused kernel; out-of-bounds
+// coordinates are zero-filled, which is the convolution's padding.
+__device__ __forceinline__ void tma_load_tile_4d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int32_t c0,
+                                                 int32_t c1, int32_t c2, int32_t c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+        "r"(c3)
+      : "memory");
+}
+
 // ----------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, MMA issue, commit, TMEM loads.  SASS: UTCHMMA / LDTM / UTCBAR.
 // ----------------------------------------------------------------------------------------------

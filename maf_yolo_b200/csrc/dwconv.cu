@@ -34,17 +34,6 @@ constexpr int kDwTY = 5;    // output rows per thread
 constexpr int kDwTXB = 20;  // output tile per CTA
 constexpr int kDwTYB = 10;
 
-__device__ __forceinline__ void tma_load_tile_4d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int32_t c0,
-                                                 int32_t c1, int32_t c2, int32_t c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      :
-      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
-        "r"(c3)
-      : "memory");
-}
-
 template <int K, int CB, bool kTma>
 __global__ void __launch_bounds__(128)
     dwconv_kernel(const __grid_constant__ CUtensorMap tm_in, const __half* __restrict__ in, int in_ld,

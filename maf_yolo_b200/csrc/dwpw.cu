@@ -44,17 +44,6 @@ struct DwPwParams {
   uint32_t idesc;
 };
 
-__device__ __forceinline__ void tma_load_tile_4d_fw(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int32_t c0,
-                                                    int32_t c1, int32_t c2, int32_t c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      :
-      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
-        "r"(c3)
-      : "memory");
-}
-
 template <int K, int kCtas>
 __global__ void __launch_bounds__(kFwThreads, kCtas) dwpw_kernel(const __grid_constant__ DwPwParams p) {
   constexpr int P = K / 2;
@@ -102,7 +91,7 @@ __global__ void __launch_bounds__(kFwThreads, kCtas) dwpw_kernel(const __grid_co
     mbar_arrive_expect_tx(bar_in, kHaloBytes + b_bytes);
     tma_load_2d(s_w, &p.tm_w, bar_in, 0, 0);  // weights are constants: may start before the previous kernel ends
     pdl_wait();  // the input tile (and, causally, every output store) follows the previous kernels
-    tma_load_tile_4d_fw(s_in, &p.tm_in, bar_in, 0, x0 - P, y0 - P, img);
+    tma_load_tile_4d(s_in, &p.tm_in, bar_in, 0, x0 - P, y0 - P, img);
   }
 
   // this warp's 5 x 5 unit of the tile; lane = channel pair of the block
@@ -151,7 +140,7 @@ __global__ void __launch_bounds__(kFwThreads, kCtas) dwpw_kernel(const __grid_co
     if (threadIdx.x == 0 && cb + 1 < kblocks) {  // next block's halo tile + W2 block: overlaps the A-tile writes + MMA
       mbar_arrive_expect_tx(bar_in, kHaloBytes + b_bytes);
       tma_load_2d(s_w + ((cb + 1) & 1) * b_bytes, &p.tm_w, bar_in, c0 + kFwCB, 0);
-      tma_load_tile_4d_fw(s_in, &p.tm_in, bar_in, c0 + kFwCB, x0 - P, y0 - P, img);
+      tma_load_tile_4d(s_in, &p.tm_in, bar_in, c0 + kFwCB, x0 - P, y0 - P, img);
     }
 
     // bias is already in the accumulator; act1, fp16, SW128 K-major A tile: row = pixel, 4 bytes per lane

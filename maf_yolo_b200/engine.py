@@ -69,6 +69,7 @@ class _Op:
     act: str = "none"
     k: int = 0
     weight2: Optional[str] = None             # fused depth-wise + 1x1 ("dwpw"): the 1x1's folded weight
+    weight3: Optional[str] = None             # fused bottleneck ("bneck"): weight = expand 1x1, weight3 = depth-wise, weight2 = project 1x1
     act2: str = "none"
     wslice: Optional[Tuple[int, int]] = None  # channel range of the folded weight this op uses (split depth-wise convs)
     impl: str = ""                            # "" = default kernel, "tc" = tensor-core depth-wise kernel
@@ -129,6 +130,7 @@ class Plan:
 
     def _emit(self, kind, name, reads, writes, **kw) -> _Op:
         idx = len(self.ops)
+        mid = kw.pop("mid", None)  # accounting only (fused bottleneck)
         for v in list(reads) + list(writes):
             v.buf.touch(idx)
         op = _Op(kind, name, list(reads), list(writes), **kw)
@@ -145,6 +147,8 @@ class Plan:
             op.flops_per_image = 2 * reads[0].c * writes[0].c * px_out
         elif kind == "dwpw":
             op.flops_per_image = 2 * kw["k"] * kw["k"] * reads[0].c * px_out + 2 * reads[0].c * writes[0].c * px_out
+        elif kind == "bneck":  # expand 1x1 + depth-wise + project 1x1 (no halo recompute counted: algorithmic)
+            op.flops_per_image = 2 * px_out * (reads[0].c * mid + kw["k"] * kw["k"] * mid + mid * writes[0].c)
         self.ops.append(op)
         return op
 
@@ -175,6 +179,14 @@ class Plan:
         tile_n = (cout + 15) // 16 * 16
         halo = (10 + k - 1) * (20 + k - 1) * 64 * 2
         return 1024 + 32768 + 2 * tile_n * 128 + (halo + 127) // 128 * 128 + 64 + tile_n * 4 <= 113 * 1024
+
+    @staticmethod
+    def _bneck_ok(c_: int, mid: int, k: int) -> bool:
+        """Can the whole DepthBottleneckUni run as ONE kernel (mafb200_bottleneck, K4)?  MAFB200_BNECK=0: round-1 form
+        (expand GEMM, then depth-wise + project)."""
+        if os.environ.get("MAFB200_BNECK", "1") == "0":
+            return False
+        return ops.bottleneck_supported(c_, mid, (c_ + 15) // 16 * 16, k)
 
     # ---- the schedule ----------------------------------------------------------------------------
     def _plan(self):
@@ -229,6 +241,11 @@ class Plan:
                 cat = self._buf(h, w, (2 + l.depth) * c_, f"L{i}.cat")
                 self._emit("conv1x1", f"L{i}.conv1", srcs_of(l), [cat.slice(0, 2 * c_)], weight=i + ".conv1", act="silu")
                 for j in range(l.depth):
+                    if self._bneck_ok(c_, mid, l.k):  # K4: expand + depth-wise + project in one kernel, no 3c_ buffer
+                        self._emit("bneck", f"L{i}.m{j}.bottleneck(k{l.k})", [cat.slice((1 + j) * c_, c_)],
+                                   [cat.slice((2 + j) * c_, c_)], weight=f"{i}.m.{j}.conv1", weight3=f"{i}.m.{j}.dw",
+                                   weight2=f"{i}.m.{j}.one_conv", act="silu", act2="silu", k=l.k, mid=mid)
+                        continue
                     t1 = self._buf(h, w, mid, f"L{i}.m{j}.expand")
                     self._emit("conv1x1", f"L{i}.m{j}.conv1", [cat.slice((1 + j) * c_, c_)], [t1],
                                weight=f"{i}.m.{j}.conv1", act="silu")
@@ -472,6 +489,11 @@ class Engine:
             w, b = ops.pack_conv3x3(*folded[op.weight], device=dev)
             self._weights[op.name] = (w, b)
             return lambda: ops.conv3x3s2(reads[0], w, b, op.act, writes[0])
+        if op.kind == "bneck":
+            dst, wt2, bs2 = self._pad_fill(op, op.act2, *folded[op.weight2])
+            packed = ops.pack_bottleneck(*folded[op.weight], *folded[op.weight3], wt2, bs2, device=dev)
+            self._weights[op.name] = packed
+            return lambda: ops.bottleneck(reads[0], packed, dst)
         if op.kind == "dwpw":
             dw_w, dw_b = ops.pack_dw(*folded[op.weight], device=dev)
             dst, wt2, bs2 = self._pad_fill(op, op.act2, *folded[op.weight2])

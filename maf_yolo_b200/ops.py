@@ -154,6 +154,41 @@ def pack_dw_tc(weight: torch.Tensor, bias: torch.Tensor, device="cuda"):
     return table.to(device), bias.to(torch.float32).contiguous().to(device)
 
 
+def bottleneck_supported(c_in: int, mid: int, c_out: int, k: int) -> bool:
+    return bool(lib().mafb200_bottleneck_supported(c_in, mid, c_out, k))
+
+
+def pack_bottleneck(w1, b1, wd, bd, w2, b2, device="cuda"):
+    """Folded weights of a DepthBottleneckUni -> the operands of mafb200_bottleneck (layouts in include/mafb200.h):
+    w1 [mid, c_in(,1,1)], wd [mid, 1, k, k], w2 [c_out, mid(,1,1)] and their biases."""
+    w1 = w1.reshape(w1.shape[0], -1)
+    w2 = w2.reshape(w2.shape[0], -1)
+    mid, c_in = w1.shape
+    c_out, k = w2.shape[0], wd.shape[-1]
+    assert w2.shape[1] == mid and wd.shape[0] == mid and c_in <= 64
+    mid_pad, tile_n = (mid + 63) // 64 * 64, (c_out + 15) // 16 * 16
+    w1p = torch.zeros((mid_pad, 64), dtype=torch.float16)
+    w1p[:mid, :c_in] = w1.to(torch.float16)
+    b1p = torch.zeros(mid_pad, dtype=torch.float32)
+    b1p[:mid] = b1.to(torch.float32)
+    dwp = torch.zeros((k * k, mid_pad), dtype=torch.float32)
+    dwp[:, :mid] = wd.reshape(mid, k * k).t().to(torch.float32)
+    bdp = torch.zeros(mid_pad, dtype=torch.float32)
+    bdp[:mid] = bd.to(torch.float32)
+    w2p = torch.zeros((tile_n, mid_pad), dtype=torch.float16)
+    w2p[:c_out, :mid] = w2.to(torch.float16)
+    b2p = torch.zeros(tile_n, dtype=torch.float32)
+    b2p[:c_out] = b2.to(torch.float32)
+    return tuple(t.contiguous().to(device) for t in (w1p, b1p, dwp, bdp, w2p, b2p)) + (mid, k)
+
+
+def bottleneck(src: NHWC, packed, dst: NHWC) -> None:
+    """K4: the whole DepthBottleneckUni (1x1 expand -> depth-wise k x k -> 1x1 project, SiLU after each) in one kernel."""
+    w1p, b1p, dwp, bdp, w2p, b2p, mid, k = packed
+    check(lib().mafb200_bottleneck(src.ref(), mid, w1p.data_ptr(), b1p.data_ptr(), dwp.data_ptr(), bdp.data_ptr(), k,
+                                   w2p.data_ptr(), b2p.data_ptr(), dst.ref(), _stream()))
+
+
 def pack_head_reg(weight: torch.Tensor, bias: torch.Tensor, device="cuda"):
     """reg_pred weight [68, C(,1,1)] / bias [68] -> packed for mafb200_head_pred(kind=REG): rows permuted so that packed
     row j < 64 is channel (j // 16) * 17 + j % 16 and row 64 + s is channel s * 17 + 16 (reg_max = 16)."""

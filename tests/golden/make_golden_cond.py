@@ -37,6 +37,9 @@ from oracle import ref_loader  # noqa: E402
 from tests._cond import pair_iou  # noqa: E402
 from tests._synthetic import synthetic_scene  # noqa: E402
 
+# margins: >= 2x the score error measured on B200 for the variant's fixtures (profiles/r02_b_parity_k7on.txt: N 2.2e-3,
+# S 8.0e-3; deeper variants amplify more), IoU margin far above the measured 1.5e-4
+M_SCORE_V = {"n": 1.0e-2, "s": 2.0e-2, "m": 2.0e-2}
 M_SCORE, M_IOU = 1.0e-2, 0.05
 IOU_THRES = 0.65
 MAX_CAND = 600
@@ -127,7 +130,7 @@ def search(variant, ns, seeds=range(380, 440)):
         top = np.sort(p[:, 5:].reshape(-1))[::-1][:MAX_CAND + 1]
         for k in range(4, MAX_CAND, 2):
             conf = float((top[k - 1] + top[k]) / 2)
-            c = certify(p, conf)
+            c = certify(p, conf, M_SCORE_V[variant])
             if c is None:
                 continue
             nk, nsup = int((c["status"] == KEPT).sum()), int((c["status"] == SUP).sum())
@@ -149,7 +152,7 @@ def save(variant, kind, fx, ns):
     out = {"seed": np.int64(fx["seed"]), "conf": np.float64(fx["conf"]), "iou": np.float64(IOU_THRES),
            "head_std": np.float64(HEAD_STD), "cls_bias": np.float64(fx["bias"]), "conv_gain": np.float64(CONV_GAIN[variant]),
            "scene_seed": np.int64(SCENE_SEED), **{k: np.float64(v) for k, v in REG.items()},
-           "margin_score": np.float64(M_SCORE), "margin_iou": np.float64(M_IOU),
+           "margin_score": np.float64(M_SCORE_V[variant]), "margin_iou": np.float64(M_IOU),
            "det0": dets[0].numpy(), "pred_sample": fx["pred"][0, ::16].numpy(),
            **{"cand_" + k: v for k, v in c.items()}}
     np.savez_compressed(os.path.join(HERE, f"cond_{variant}_{kind}.npz"), **out)

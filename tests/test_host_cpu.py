@@ -159,6 +159,13 @@ def test_plan_liveness_and_arena(variant):
                 assert w.shape[0] == op.reads[0].c == bias.shape[0] and w2.shape[0] == op.writes[0].c == b2.shape[0], op.name
                 assert w2.reshape(w2.shape[0], -1).shape[1] == op.reads[0].c, op.name
                 continue
+            if op.kind == "bneck":  # K4: expand 1x1 (c_ -> mid), depth-wise (mid), project 1x1 (mid -> c_)
+                wd, bd = folded[op.weight3]
+                w2, b2 = folded[op.weight2]
+                mid = w.shape[0]
+                assert w.reshape(mid, -1).shape[1] == op.reads[0].c and wd.shape[0] == mid == bd.shape[0], op.name
+                assert w2.shape[0] == op.writes[0].c == b2.shape[0] and w2.reshape(w2.shape[0], -1).shape[1] == mid, op.name
+                continue
             if op.kind == "head_pred":  # K7: no arena output; cls_pred -> nc scores, reg_pred -> 4 * 17 bins
                 assert not op.writes and w.shape[0] == bias.shape[0] == (g.nc if op.act == "cls" else 68), op.name
                 assert w.reshape(w.shape[0], -1).shape[1] == op.reads[0].c, op.name
@@ -190,9 +197,9 @@ def test_pad_fill_only_touches_unowned_padding(variant, monkeypatch):
     plan = engine.Plan(topology.build_graph(variant), 640, 640)
     extended = {}
     for op in plan.ops:
-        if not op.writes or op.kind not in ("stem", "conv1x1", "dwpw", "poolpw"):
+        if not op.writes or op.kind not in ("stem", "conv1x1", "dwpw", "poolpw", "bneck"):
             continue
-        act = op.act2 if op.kind == "dwpw" else op.act
+        act = op.act2 if op.kind in ("dwpw", "bneck") else op.act
         extra = engine.pad_fill_channels(op, act)
         v = op.writes[0]
         if extra:
@@ -207,7 +214,8 @@ def test_pad_fill_only_touches_unowned_padding(variant, monkeypatch):
         for v in op.reads + op.writes:
             assert v.c_off + v.c <= v.buf.c, (op.name, v.buf.name)
     if variant == "n":  # (reg_pred no longer writes a padded map: K7 decodes in its epilogue)
-        assert sorted(extended) == ["L0.stem3x3s2", "L2.m0.conv1", "L2.m0.dw3+one_conv"]
+        # (K4: L2's bottleneck is one kernel; its expand output no longer exists as a buffer)
+        assert sorted(extended) == ["L0.stem3x3s2", "L2.m0.bottleneck(k3)"]
     monkeypatch.setenv("MAFB200_PAD_FILL", "0")
     assert all(engine.pad_fill_channels(op, op.act) == 0 for op in plan.ops if op.writes)
 

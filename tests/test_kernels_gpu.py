@@ -254,6 +254,46 @@ def test_dwconv_conv1x1_fused(cuda_device, c, cout, k, h, w, n, act1, act2):
     _close(dst.to_nchw(), ref, f"dwconv_conv1x1 c={c}->{cout} k={k}", rtol=3e-3, atol=3e-3)
 
 
+# every (c_, 3 c_, k) of the N / S / M graphs the fused kernel takes (c_ <= 64, k <= 5), full tiles and ragged edges,
+# one to three 64-channel blocks (incl. the 8- and 16-channel tails of mid = 72 / 144), many tiles per CTA (persistence)
+@pytest.mark.parametrize("c_,k,h,w,n", [(24, 3, 40, 44, 2), (48, 5, 24, 40, 2), (64, 5, 20, 30, 2), (32, 3, 16, 20, 1),
+                                        (64, 5, 80, 80, 2), (48, 3, 13, 27, 3), (24, 3, 160, 160, 2), (64, 3, 7, 9, 1),
+                                        (16, 5, 10, 20, 1), (64, 5, 160, 160, 4)])
+def test_bottleneck_fused(cuda_device, c_, k, h, w, n):
+    """K4 (mafb200_bottleneck): the whole DepthBottleneckUni against its three reference ops in fp32, the two
+    intermediates rounded to fp16 once each (as the kernel keeps them in shared memory).  Source and destination are
+    channel slices of one wider buffer, as in RepHDW's concat; the other channels must stay untouched."""
+    from maf_yolo_b200 import ops
+
+    mid = 3 * c_
+    g = torch.Generator().manual_seed(131 + c_ + k + h)
+    x = torch.randn(n, c_, h, w, generator=g).half().float()
+    w1 = (torch.randn(mid, c_, generator=g) / c_ ** 0.5).half().float()
+    b1 = torch.randn(mid, generator=g) * 0.5
+    wd = torch.randn(mid, 1, k, k, generator=g) / k
+    bd = torch.randn(mid, generator=g) * 0.5
+    w2 = (torch.randn(c_, mid, generator=g) / mid ** 0.5).half().float()
+    b2 = torch.randn(c_, generator=g)
+    assert ops.bottleneck_supported(c_, mid, c_, k)
+    t1 = F.silu(F.conv2d(x, w1[:, :, None, None], b1)).half().float()
+    t2 = F.silu(F.conv2d(t1, wd, bd, padding=k // 2, groups=mid)).half().float()
+    ref = F.silu(F.conv2d(t2, w2[:, :, None, None], b2))
+    ld = (3 * c_ + 15) // 16 * 16
+    cat = ops.NHWC(torch.full((n, h, w, ld), 7.0, dtype=torch.float16, device=cuda_device), 0, 3 * c_)
+    cat.buf[..., c_:2 * c_] = x.permute(0, 2, 3, 1).to(cuda_device).half()
+    packed = ops.pack_bottleneck(w1, b1, wd, bd, w2, b2, device=cuda_device)
+    ops.bottleneck(cat.slice(c_, c_), packed, cat.slice(2 * c_, c_))
+    torch.cuda.synchronize()
+    _close(cat.slice(2 * c_, c_).to_nchw(), ref, f"bottleneck c_={c_} k={k} {h}x{w}", rtol=4e-3, atol=4e-3)
+    assert (cat.buf[..., :c_] == 7.0).all() and (cat.buf[..., 3 * c_:] == 7.0).all(), "bottleneck wrote outside its slice"
+    assert torch.equal(cat.buf[..., c_:2 * c_].cpu(), x.permute(0, 2, 3, 1).half()), "bottleneck modified its input"
+    # twice in a row on the same stream (barrier phases / TMEM re-allocation across launches) and bit-identical
+    first = cat.slice(2 * c_, c_).to_nchw().clone()
+    ops.bottleneck(cat.slice(c_, c_), packed, cat.slice(2 * c_, c_))
+    torch.cuda.synchronize()
+    assert torch.equal(cat.slice(2 * c_, c_).to_nchw(), first)
+
+
 @pytest.mark.parametrize("c,cout,h,w,n,act,wide", [(48, 48, 40, 40, 2, "silu", True), (96, 96, 20, 24, 3, "silu", True),
                                                    (256, 128, 16, 16, 2, "silu", False), (48, 24, 10, 14, 1, "none", False),
                                                    (64, 48, 160, 160, 2, "silu", True), (192, 96, 40, 40, 1, "relu", True)])

@@ -182,10 +182,13 @@ def test_end_to_end_detections(cuda_device):
         assert 0 < d.shape[0] <= 300 and (np.diff(d[:, 4]) <= 0).all() and (d[:, 2] > d[:, 0]).all()
 
 
-# Gates of the CONDITIONED family (He-scaled weights: every layer's error reaches the heads; scores up to ~0.8 where
-# the sigmoid is steep).  Set from the measured values with head-room; the reference's own fp16
-# mode measured on the same inputs is printed next to ours.
-COND_SCORE_TOL, COND_ELEM_TOL, COND_GRID_TOL = 5e-3, 5e-2, 5e-2
+# Gates of the CONDITIONED family (He-scaled weights at the edge of stability: every layer's error reaches the heads
+# and is amplified on the way; scores up to ~0.8 where the sigmoid is steepest).  Boxes: the same three readings, gated
+# at 1e-3 norm-wise AND element-wise (measured 2.5e-5 .. 5e-5 / 4e-4 .. 9e-4: the boxes of this family are large), 1e-2
+# stride-normalised.  Scores: an absolute 1e-3 is out of reach of ANY fp16 path on these inputs — the reference's own
+# `--half` mode deviates by 2e-3 .. 4e-3 from its fp32 result — so the gate is relative to that measured deviation
+# (<= COND_SCORE_VS_HALF x the reference-fp16 error of the same input, never above COND_SCORE_CAP), both printed.
+COND_ELEM_TOL, COND_GRID_TOL, COND_SCORE_VS_HALF, COND_SCORE_CAP = 1e-3, 1e-2, 3.0, 1e-2
 
 
 def _reference_half_errors(spec, sd, x, ref):
@@ -219,11 +222,12 @@ def test_conditioned_detections_match_reference(cuda_device, variant, kind):
     model = mb.from_state_dict(sd, variant, in_flight=2)
     xd = x.to(cuda_device)
     pred = model(xd)[0]
-    e = _check_pred(pred, ref, f"conditioned {kind} MAF-YOLO-{variant} vs oracle", score_tol=COND_SCORE_TOL,
-                    elem_tol=COND_ELEM_TOL, grid_tol=COND_GRID_TOL)
     eh = _reference_half_errors(spec, sd, x, ref)
     print(f"PARITY   (reference's own fp16 mode on the same input: box {eh['abs_px']:.3e} px, grid {eh['grid']:.2e}, "
           f"score {eh['score']:.3e})")
+    e = _check_pred(pred, ref, f"conditioned {kind} MAF-YOLO-{variant} vs oracle",
+                    score_tol=min(COND_SCORE_CAP, COND_SCORE_VS_HALF * eh["score"]), elem_tol=COND_ELEM_TOL,
+                    grid_tol=COND_GRID_TOL)
     # preconditions of the certification: our scores move by < margin_score / 2, candidate-pair IoUs by < margin_iou
     assert e["score"] < float(fx["margin_score"]) / 2
     ca = torch.from_numpy(fx["cand_anchor"])
@@ -257,8 +261,12 @@ def test_full_size_configs_match_oracle(cuda_device, variant, batch):
     ref = om.forward_train_form(spec, sd, x[pick])
     pred = mb.from_state_dict(sd, variant)(x.to(cuda_device))[0]
     assert pred.shape == (batch, 8400, 85)
-    _check_pred(pred[pick], ref, f"full-size MAF-YOLO-{variant} bs{batch}, images {pick}", score_tol=COND_SCORE_TOL,
-                elem_tol=COND_ELEM_TOL, grid_tol=COND_GRID_TOL)
+    eh = _reference_half_errors(spec, sd, x[pick], ref)
+    print(f"PARITY   (reference's own fp16 mode on the same images: box {eh['abs_px']:.3e} px, grid {eh['grid']:.2e}, "
+          f"score {eh['score']:.3e})")
+    _check_pred(pred[pick], ref, f"full-size MAF-YOLO-{variant} bs{batch}, images {pick}",
+                score_tol=min(COND_SCORE_CAP, COND_SCORE_VS_HALF * eh["score"]), elem_tol=COND_ELEM_TOL,
+                grid_tol=COND_GRID_TOL)
 
 
 @pytest.mark.parametrize("in_flight", [1, 2, 3])
