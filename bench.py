@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=32, help="images per GPU")
     ap.add_argument("--cpu-sample", type=int, default=4, help="images per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-library-baseline", action="store_true", help="skip the torch-eager cuDNN fp16 leg on the same GPU")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--streams", type=int, default=4, help="streams captured into the CUDA graph (branch concurrency)")
     ap.add_argument("--in-flight", type=int, default=2, help="batches in flight in model.detect_async (engine replicas)")
@@ -78,9 +79,64 @@ def cpu_reference_step_fn(variant: str, sample: int):
 
     def step():
         pred = om.forward_deploy(spec, dd, x)
-        return onms.non_max_suppression(pred.numpy(), **EVAL_NMS)
+        return onms.non_max_suppression_tv(pred, **EVAL_NMS)  # torchvision.ops.nms, the reference's own library call
 
     return step
+
+
+# block-fused algorithmic bytes and conv FLOPs per image (fp16 activations, weights excluded)
+FUSED_MB_PER_IMAGE = {"n": 58.2, "s": 78.9, "m": 121.3}
+GFLOP_PER_IMAGE = {"n": 10.508, "s": 25.448, "m": 76.650}
+
+
+def gpu_library_baseline(variant: str, batch: int, dev, steps: int = 10):
+    """The bar on the same box: the reference's deploy-form forward as plain
+    torch-eager library calls on this GPU — cuDNN / cuBLAS convs in fp16, channels_last — + the reference's NMS with
+    torchvision.ops.nms, timed outside our timed region with CUDA events.  Uses the oracle's restatement of the
+    reference graph as the carrier of those library calls (the reference tree does not travel to the GPU box)."""
+    from maf_yolo_b200 import synth, topology
+    from oracle import model as om
+    from oracle import nms as onms
+
+    try:
+        g = topology.build_graph(variant)
+        spec = om.parse_model(om.variant_rows(variant))
+        dd = {k: (w.to(dev).half().contiguous(memory_format=torch.channels_last) if w.dim() == 4 else w.to(dev).half(),
+                  b.to(dev).half()) for k, (w, b) in om.fold_deploy(spec, synth.random_state_dict(g, seed=0)).items()}
+        x = torch.rand(batch, 3, 640, 640, device=dev).half().contiguous(memory_format=torch.channels_last)
+        orig_anchors = om.generate_anchors_eval
+
+        def anchors_on_device(sizes, strides, offset=0.5):
+            a, st = orig_anchors(sizes, strides, offset)
+            return a.to(dev), st.to(dev)
+
+        om.generate_anchors_eval = anchors_on_device
+        try:
+            def fwd():
+                return om.forward_deploy(spec, dd, x).float()
+
+            def full():
+                return onms.non_max_suppression_tv(fwd(), **EVAL_NMS)
+
+            res = {}
+            for name, fn in (("forward_decode", fwd), ("forward_decode_nms", full)):
+                for _ in range(3):
+                    fn()
+                torch.cuda.synchronize()
+                s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s_ev.record()
+                for _ in range(steps):
+                    fn()
+                e_ev.record()
+                torch.cuda.synchronize()
+                res[name] = round(batch * steps / (s_ev.elapsed_time(e_ev) / 1e3), 1)
+        finally:
+            om.generate_anchors_eval = orig_anchors
+        return {"value": res["forward_decode_nms"], "forward_decode_only": res["forward_decode"], "unit": "images/s",
+                "kind": "torch-eager library calls (cuDNN/cuBLAS fp16, channels_last) for the deploy-form forward + "
+                        "torchvision.ops.nms; one batch at a time, CUDA events", "batch": batch, "steps": steps}
+    except Exception as exc:  # noqa: BLE001 — a missing library op must not take the bench line down
+        return {"value": None, "unavailable": f"{type(exc).__name__}: {exc}"[:300]}
 
 
 def time_cpu(step, steps: int, warmup: int):
@@ -106,7 +162,7 @@ def run_reference_arm(a):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "sample": f"{a.cpu_sample} images per step on the host CPU"},
         "cpu_baseline": {"value": round(value, 3), "unit": "images/s", "cores": cores, "kind": "port",
-                         "sample": f"oracle port of the reference deploy-form forward + NMS (torch CPU fp32, "
+                         "sample": f"oracle port of the reference deploy-form forward + NMS with torchvision.ops.nms (torch CPU fp32, "
                                    f"{cores} threads), {a.cpu_sample} images/step x {a.steps} steps"},
         "e2e": {"value": round(value, 3), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -160,6 +216,15 @@ def measured_hbm_peak():
         except Exception:
             pass
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def measured_tensor_peak():
+    """Sustained dense bf16 TFLOP/s of this pool's B200s (MEASURED_PEAKS.json), else the profiling guide's fallback."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["bf16_tflops_sustained"])
+    except Exception:
+        return 1382.0
 
 
 def profiled_traffic(kind: str, variant: str, batch: int):
@@ -224,7 +289,9 @@ def run_ours(a):
     g = topology.build_graph(a.variant)
     sd = synth.random_state_dict(g, seed=0)
     in_flight = 1 if a.no_pipeline else max(1, a.in_flight)
-    model = mb.from_state_dict(sd, a.variant, use_cuda_graph=not a.no_graph, n_streams=a.streams, in_flight=in_flight)
+    # borrow_output: model(x) hands out the engine-owned prediction buffer (no 91 MB copy per call in the breakdown legs)
+    model = mb.from_state_dict(sd, a.variant, use_cuda_graph=not a.no_graph, n_streams=a.streams, in_flight=in_flight,
+                               borrow_output=True)
     B = a.batch
     gen = torch.Generator().manual_seed(1000 + rank)
     host_u8 = [torch.randint(0, 256, (B, 3, 640, 640), generator=gen, dtype=torch.uint8).pin_memory() for _ in range(2)]
@@ -296,7 +363,9 @@ def run_ours(a):
     ms = timed(lambda i: step(x_f32[i % 2]), a.steps)
     clocks = sampler.stop()
     eng = model.engine_for(x_f32[0])
-    per_step_launches = eng.launches_per_forward + 2  # + the two NMS kernels
+    # kernels of libmafb200.so per step: the forward's launches (the counter reset is a memset, not counted) + NMS
+    # (one nms_select kernel on the serving path whose candidate filter runs in the cls_pred epilogues, else two)
+    per_step_launches = eng.launches_per_forward + (1 if (pipelined and model.fused_detect) else 2)
     counted = _lib.launch_count() - launches0  # eager launches only; graph replays are not API calls
     value = B * world * a.steps / (ms / 1e3)
     host_enqueue_ms = host_ms[0]
@@ -308,17 +377,29 @@ def run_ours(a):
     ms_nms = timed(lambda i: mb.non_max_suppression_padded(pred_static, **EVAL_NMS, det=det, count=cnt), a.steps)
 
     # ---- per-batch latency (sequential: one batch at a time, forward -> decode -> NMS), p50 / p90 --------------
-    lat = []
+    lat, lat_pred = [], []
     for i in range(min(a.steps, 100)):
+        s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_ev.record()
+        t = model.detect_async(x_f32[i % 2], **EVAL_NMS)  # the serving call, ONE batch in flight (synchronised below)
+        torch.cuda.current_stream().wait_event(t.done)
+        e_ev.record()
+        e_ev.synchronize()
+        lat.append(s_ev.elapsed_time(e_ev))
+    for i in range(min(a.steps, 50)):
         s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s_ev.record()
         mb.non_max_suppression_padded(model(x_f32[i % 2])[0], **EVAL_NMS, det=det, count=cnt)
         e_ev.record()
         e_ev.synchronize()
-        lat.append(s_ev.elapsed_time(e_ev))
+        lat_pred.append(s_ev.elapsed_time(e_ev))
     lat.sort()
+    lat_pred.sort()
     latency = {"p50": round(lat[len(lat) // 2], 4), "p90": round(lat[int(len(lat) * 0.9)], 4), "samples": len(lat),
-               "what": "one batch at a time: forward + decode + NMS, device events, input resident in HBM"}
+               "what": "one batch at a time through model.detect_async: forward + decode + NMS, device events, input "
+                       "resident in HBM",
+               "p50_reference_shaped_calls": round(lat_pred[len(lat_pred) // 2], 4),
+               "reference_shaped_calls": "pred = model(x)[0] (materialises [B,8400,85] fp32); non_max_suppression(pred)"}
 
     # ---- end to end from host buffers ---------------------------------------------------------------
     # H2D of step i+1 overlaps the compute of step i (copy stream + events); every step's copy, compute
@@ -367,6 +448,7 @@ def run_ours(a):
 
     # ---- roofline of the dominant kernel (rank 0; eager, event pair per launch) -------------------------
     fam = kernel_profile(eng, x_f32[0])
+    fam.pop("detect_reset", None)  # a 128-byte memset, not a kernel
     tot_ms = sum(f["ms"] for f in fam.values())
     top = max(fam, key=lambda k: fam[k]["ms"])
     ft = fam[top]
@@ -375,7 +457,9 @@ def run_ours(a):
     kernel_names = {"conv1x1": "gemm_tc_kernel<false> (1x1 conv / fusion-stage GEMM, tcgen05+TMA)",
                     "conv3x3s2": "gemm_tc_kernel<true> (3x3 s2 implicit GEMM, tcgen05 + im2col TMA)",
                     "dwconv": "dwconv_kernel (depth-wise k x k)", "dwpw": "dwpw_kernel (depth-wise k x k + 1x1 fused)", "stem": "stem_conv_kernel",
-                    "maxpool2x2": "maxpool2x2_kernel", "poolpw": "poolpw_kernel (2x2 max pool + 1x1 fused)", "sppf_pool": "sppf_pool_kernel", "decode": "head_decode_kernel"}
+                    "maxpool2x2": "maxpool2x2_kernel", "poolpw": "poolpw_kernel (2x2 max pool + 1x1 fused)", "sppf_pool": "sppf_pool_kernel", "decode": "head_decode_kernel",
+                    "bneck": "bneck_kernel (whole DepthBottleneckUni: 1x1 -> depth-wise -> 1x1, K4)",
+                    "head_pred": "gemm_tc_kernel<false, 1|2> (cls_pred / reg_pred + sigmoid / DFL decode epilogues, K7)"}
     roofline = {
         "bound": "hbm", "kernel": kernel_names.get(top, top), "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
         "frac": round(achieved / peak, 4), "traffic": profiled_traffic(top, a.variant, B), "peak_source": peak_src,
@@ -385,9 +469,20 @@ def run_ours(a):
                          "TFLOP/s": round(v["flops"] / 1e12 / (v["ms"] / 1e3), 2)} for k, v in sorted(fam.items())},
     }
     plan = eng.plan
+    tf_peak = measured_tensor_peak()
+    per_gpu = value / world
     whole = {"algorithmic_MB_per_image": round(plan.bytes_per_image() / 1e6, 1),
              "GFLOP_per_image": round(plan.flops_per_image() / 1e9, 3),
-             "hbm_frac_of_peak": round(plan.bytes_per_image() * value / world / 1e9 / peak, 4)}
+             "hbm_frac_of_peak": round(plan.bytes_per_image() * per_gpu / 1e9 / peak, 4),
+             "what": "hbm_frac_of_peak counts the bytes THIS plan moves (kernel granularity); the two fractions below "
+                     "are SURVEY 8(d)'s: block-fused bytes (one pass per yaml block) and conv FLOPs against the "
+                     "measured peaks",
+             "block_fused_MB_per_image": FUSED_MB_PER_IMAGE[a.variant],
+             "achieved_bw_frac": round(FUSED_MB_PER_IMAGE[a.variant] * 1e6 * per_gpu / (peak * 1e9), 4),
+             "achieved_flops_frac": round(GFLOP_PER_IMAGE[a.variant] * 1e9 * per_gpu / (tf_peak * 1e12), 4),
+             "tensor_peak_TFLOPs": tf_peak,
+             "ceiling_images_per_s_per_gpu": round(1.0 / max(FUSED_MB_PER_IMAGE[a.variant] * 1e6 / (peak * 1e9),
+                                                             GFLOP_PER_IMAGE[a.variant] * 1e9 / (tf_peak * 1e12)), 0)}
 
     cpu = None
     if world == 1 and not a.no_cpu_baseline:
@@ -395,8 +490,14 @@ def run_ours(a):
         sec = time_cpu(stepf, 3, 1)
         cores = torch.get_num_threads()
         cpu = {"value": round(a.cpu_sample / sec, 3), "unit": "images/s", "cores": cores, "kind": "port",
-               "sample": f"oracle port of the reference deploy-form forward + NMS, {a.cpu_sample} images/step x 3 steps, "
+               "sample": f"oracle port of the reference deploy-form forward + NMS (torchvision.ops.nms), {a.cpu_sample} images/step x 3 steps, "
                          f"torch CPU fp32, {cores} threads"}
+
+    lib_base = None
+    if world == 1 and not a.no_library_baseline:
+        del x_u8, det_host
+        torch.cuda.empty_cache()
+        lib_base = gpu_library_baseline(a.variant, B, dev)
 
     line = {
         "metric": "images/sec @ 640x640 (forward + decode + NMS)", "value": round(value, 1), "unit": "images/s",
@@ -417,6 +518,7 @@ def run_ours(a):
         "latency_ms_per_batch": latency,
         "host_enqueue_ms_per_step": {"value_loop": round(host_enqueue_ms, 4), "e2e_loop": round(host_enqueue_e2e_ms, 4)},
         "clocks": clocks, "roofline": roofline, "whole_step": whole, "cpu_baseline": cpu,
+        "gpu_library_baseline": lib_base,
     }
     emit(line)
     if world > 1:

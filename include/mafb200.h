@@ -159,6 +159,8 @@ MAFB200_API int32_t mafb200_dwconv_conv1x1(const maf_tensor* src, const float* d
  *   dw_weight fp32 [k*k][mid_pad] tap-major, dw_bias fp32 [mid_pad];  w2_packed fp16 [tile_n][mid_pad], b2 fp32 [tile_n].
  * mafb200_bottleneck_supported: 1 if the shape fits this kernel (pure host arithmetic), else 0. */
 MAFB200_API int32_t mafb200_bottleneck_supported(int32_t c_in, int32_t mid, int32_t c_out, int32_t k);
+/* debug: clock64 trace of CTA 0 of the following mafb200_bottleneck calls of this thread (device int64 [3][64][4]) */
+MAFB200_API int32_t mafb200_bottleneck_trace(long long* trace_device);
 MAFB200_API int32_t mafb200_bottleneck(const maf_tensor* src, int32_t mid, const void* w1_packed, const float* b1,
                            const float* dw_weight, const float* dw_bias, int32_t k, const void* w2_packed,
                            const float* b2, const maf_tensor* dst, void* stream);
@@ -253,6 +255,14 @@ MAFB200_API int32_t mafb200_head_pred(const maf_tensor* src, const void* w_packe
                           int32_t anchor_off, int32_t total_anchors, float stride, int32_t nc, float* pred,
                           float* boxes, const maf_detect_cfg* detect_cfg, void* workspace, size_t workspace_bytes,
                           void* stream);
+
+/* mafb200_nms_select writing the packed rows of the multi-GPU detection all-gather directly: image b's [max_det, 6]
+ * detections at packed + b * row_floats and its count (int32 bits) in the float behind them (row_floats >= max_det*6+1).
+ * The rank's slice of the gather buffer is filled in place; one NCCL all-gather then moves detections and counts. */
+MAFB200_API int32_t mafb200_nms_select_packed(const float* boxes, int32_t box_stride, int32_t batch, int32_t anchors,
+                                  int32_t nc, double iou_thres, int32_t agnostic, int32_t max_det, int32_t max_nms,
+                                  float* packed, int32_t row_floats, void* workspace, size_t workspace_bytes,
+                                  void* stream);
 
 /* ---- image pre-processing (the step right before the hot path) ------------------------------------
  * letterbox (yolov6/data/data_augment.py:53-83: cv2.resize INTER_LINEAR to new_w x new_h — reproduced bit for

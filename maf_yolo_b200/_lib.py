@@ -65,6 +65,7 @@ _SIGNATURES = {
     "mafb200_dwconv_conv1x1": (C.c_int32, [_P(MafTensor), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                            C.c_void_p, C.c_int32, _P(MafTensor), C.c_void_p]),
     "mafb200_bottleneck_supported": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "mafb200_bottleneck_trace": (C.c_int32, [C.c_void_p]),
     "mafb200_bottleneck": (C.c_int32, [_P(MafTensor), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                        C.c_void_p, C.c_void_p, _P(MafTensor), C.c_void_p]),
     "mafb200_maxpool2x2_conv1x1": (C.c_int32, [_P(MafTensor), C.c_void_p, C.c_void_p, C.c_int32, _P(MafTensor), C.c_void_p]),
@@ -92,6 +93,9 @@ _SIGNATURES = {
     "mafb200_detect_reset": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p]),
     "mafb200_head_pred": (C.c_int32, [_P(MafTensor), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                       C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mafb200_nms_select_packed": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32,
+                                              C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t,
+                                              C.c_void_p]),
     "mafb200_launch_count": (C.c_int64, []),
 }
 DETECT_CFG_BYTES = 16 + 256  # sizeof(maf_detect_cfg)

@@ -52,7 +52,15 @@ struct BneckParams {
   int32_t H, W, N, tile_n, mid_pad, nblk;
   int32_t tiles_x, tiles_y, tiles;  // tiles = n * tiles_y * tiles_x
   uint32_t idesc1, idesc2;
+  long long* trace;  // debug (mafb200_bottleneck_trace): clock64 stamps of CTA 0, [role][step][4]; nullptr = off
 };
+
+constexpr int kBnTraceSteps = 64;
+#define BN_TRACE(role, s, slot)                                                                              \
+  do {                                                                                                       \
+    if (p.trace != nullptr && blockIdx.x == 0 && (s) < kBnTraceSteps && lane == 0)                           \
+      p.trace[((role) * kBnTraceSteps + (s)) * 4 + (slot)] = clock64();                                      \
+  } while (0)
 
 __device__ __forceinline__ float silu_fast(float x) {
   const float h = 0.5f * x;
@@ -172,6 +180,7 @@ __global__ void __launch_bounds__(kBnThreads, 1) bneck_kernel(const __grid_const
         }
         tc_commit(&bar_acc1_full[buf]);
         if (cb == nblk - 1) tc_commit(bar_x_empty);  // the halo tile may be overwritten once these MMAs are done
+        BN_TRACE(0, s, 0);
       };
       auto mma2 = [&](int s) {
         const int it = s / nblk, cb = s - it * nblk;
@@ -191,12 +200,16 @@ __global__ void __launch_bounds__(kBnThreads, 1) bneck_kernel(const __grid_const
         }
         tc_commit(bar_a2_empty);
         if (cb == nblk - 1) tc_commit(bar_acc2_full);
+        BN_TRACE(0, s, 1);
       };
+      // MMA1 runs two steps ahead of MMA2: MMA1(s + 2) only needs epilogue 1 of step s (acc1[s & 1] drained), which
+      // precedes the end of the taps of step s that MMA2(s) waits for — so it is issued first and epilogue 1 never
+      // waits for the tensor core (measured with the clock64 trace: 3000 cycles of bubble per step the other way round)
       mma1(0);
       if (total_steps > 1) mma1(1);
       for (int s = 0; s < total_steps; ++s) {
-        mma2(s);
         if (s + 2 < total_steps) mma1(s + 2);
+        mma2(s);
       }
     }
   } else if (warp >= kBnTapWarps) {
@@ -208,32 +221,52 @@ __global__ void __launch_bounds__(kBnThreads, 1) bneck_kernel(const __grid_const
       const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
       mbar_wait(bar_acc2_full, it & 1);
       tc_fence_after_sync();
+      // 2 M tiles x tile_n columns per thread in 32-column groups; the TMEM load of the next group is in flight while
+      // this one is processed, bias in registers before the math (same reasons as epilogue 1)
+      const int groups_per_mt = (p.tile_n + 31) >> 5;  // 1 or 2
+      const int n_groups = 2 * groups_per_mt;
+      const uint32_t taddr0 = tmem_base + kBnAcc2Col0 + (static_cast<uint32_t>(q * 32) << 16);
+      uint32_t rr[2][32];
+      __syncwarp();
+      tmem_ld_32x32b_x32(taddr0, rr[0]);
 #pragma unroll 1
-      for (int mt = 0; mt < 2; ++mt) {
-        const int prow = mt * 128 + q * 32 + lane;
-        const int py = prow / kBnTX, px = prow - py * kBnTX;
-        const int gy = ty * kBnTY + py, gx = tx * kBnTX + px;
-        const bool ok = prow < kBnTX * kBnTY && gy < p.H && gx < p.W;
-        __half* orow = p.out + ((static_cast<size_t>(img) * p.H + (ok ? gy : 0)) * p.W + (ok ? gx : 0)) * p.out_ld;
-        const uint32_t taddr = tmem_base + kBnAcc2Col0 + mt * p.tile_n + (static_cast<uint32_t>(q * 32) << 16);
-#pragma unroll 1
-        for (int c = 0; c < p.tile_n; c += 16) {
-          uint32_t rr[16];
-          __syncwarp();
-          tmem_ld_32x32b_x16(taddr + c, rr);
-          tmem_ld_wait();
-          if (ok && c < p.N) {
-            uint32_t pk[8];
+      for (int gsel = 0; gsel < n_groups; gsel += 2) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              pk[j] = pack_half2(silu_fast(__uint_as_float(rr[2 * j]) + s_b2[c + 2 * j]),
-                                 silu_fast(__uint_as_float(rr[2 * j + 1]) + s_b2[c + 2 * j + 1]));
-            if (c + 16 <= p.N) {
-              asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(orow + c), "r"(pk[0]),
-                           "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
-                           : "memory");
-            } else {  // N % 16 == 8
-              *reinterpret_cast<uint4*>(orow + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        for (int u = 0; u < 2; ++u) {
+          const int gi = gsel + u;
+          if (gi >= n_groups) break;
+          const int mt = gi / groups_per_mt, c = (gi - mt * groups_per_mt) * 32;
+          float bias[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(&bias[j]) = *reinterpret_cast<const float4*>(s_b2 + c + j);
+          tmem_ld_wait();
+          if (gi + 1 < n_groups) {
+            const int mt2 = (gi + 1) / groups_per_mt, c2 = ((gi + 1) - mt2 * groups_per_mt) * 32;
+            __syncwarp();
+            tmem_ld_32x32b_x32(taddr0 + mt2 * p.tile_n + c2, rr[u ^ 1]);
+          }
+          const int prow = mt * 128 + q * 32 + lane;
+          const int py = prow / kBnTX, px = prow - py * kBnTX;
+          const int gy = ty * kBnTY + py, gx = tx * kBnTX + px;
+          const bool ok = prow < kBnTX * kBnTY && gy < p.H && gx < p.W;
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            pk[j] = pack_half2(silu_fast(__uint_as_float(rr[u][2 * j]) + bias[2 * j]),
+                               silu_fast(__uint_as_float(rr[u][2 * j + 1]) + bias[2 * j + 1]));
+          if (ok) {
+            __half* orow = p.out + ((static_cast<size_t>(img) * p.H + gy) * p.W + gx) * p.out_ld + c;
+#pragma unroll
+            for (int h16 = 0; h16 < 2; ++h16) {
+              const int cc = c + 16 * h16;
+              if (cc + 16 <= p.N) {
+                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(orow + 16 * h16),
+                             "r"(pk[8 * h16]), "r"(pk[8 * h16 + 1]), "r"(pk[8 * h16 + 2]), "r"(pk[8 * h16 + 3]),
+                             "r"(pk[8 * h16 + 4]), "r"(pk[8 * h16 + 5]), "r"(pk[8 * h16 + 6]), "r"(pk[8 * h16 + 7])
+                             : "memory");
+              } else if (cc + 8 <= p.N) {  // N % 16 == 8
+                *reinterpret_cast<uint4*>(orow + 16 * h16) = make_uint4(pk[8 * h16], pk[8 * h16 + 1], pk[8 * h16 + 2], pk[8 * h16 + 3]);
+              }
             }
           }
         }
@@ -249,41 +282,51 @@ __global__ void __launch_bounds__(kBnThreads, 1) bneck_kernel(const __grid_const
       const int img_r = t % tiles_per_img;
       const int ty = img_r / p.tiles_x, tx = img_r - ty * p.tiles_x;
       const int hy0 = ty * kBnTY - P, hx0 = tx * kBnTX - P;  // image coordinates of halo pixel (0, 0)
+      if (q == 0) BN_TRACE(1, s, 0);
       mbar_wait(&bar_acc1_full[buf], (s >> 1) & 1);
       tc_fence_after_sync();
+      if (q == 0) BN_TRACE(1, s, 1);
       mbar_wait(&bar_t1_empty[buf], ((s >> 1) & 1) ^ 1);
+      if (q == 0) BN_TRACE(1, s, 2);
       uint8_t* t1 = s_t1 + buf * kXBytes;
       const float* b1 = s_b1 + cb * kBnCB;
-#pragma unroll 1
-      for (int mt = 0; mt < 3; ++mt) {
+      // 6 half rows (3 M tiles x 2 x 32 columns) per thread.  The TMEM load of half h + 1 is in flight while half h is
+      // processed; the 32 bias values go to registers BEFORE the math so that the 32 SiLU chains are independent of the
+      // shared-memory stores (the compiler must assume the T1 stores alias the bias array: with the loads in between,
+      // the chains ran 8 at a time — 35 cycles per element in the clock64 trace).
+      uint32_t rr[2][32];
+      const uint32_t taddr0 = tmem_base + buf * kBnAcc1Cols + (static_cast<uint32_t>(q * 32) << 16);
+      __syncwarp();
+      tmem_ld_32x32b_x32(taddr0, rr[0]);
+#pragma unroll
+      for (int hh = 0; hh < 6; ++hh) {
+        const int mt = hh >> 1, half = hh & 1;
+        float bias[32];
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) *reinterpret_cast<float4*>(&bias[c]) = *reinterpret_cast<const float4*>(b1 + 32 * half + c);
+        tmem_ld_wait();
+        if (hh + 1 < 6) {
+          __syncwarp();
+          tmem_ld_32x32b_x32(taddr0 + ((hh + 1) >> 1) * kBnCB + 32 * ((hh + 1) & 1), rr[(hh + 1) & 1]);
+        }
         const int prow = mt * 128 + q * 32 + lane;  // halo pixel of this thread
         const int py = prow / TW, px = prow - py * TW;
         const int gy = hy0 + py, gx = hx0 + px;
         const bool row_ok = prow < kHaloRows;
         const bool inside = row_ok && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
-        uint8_t* trow = t1 + prow * 128;
-        const uint32_t taddr = tmem_base + buf * kBnAcc1Cols + mt * kBnCB + (static_cast<uint32_t>(q * 32) << 16);
+        uint32_t pk[16];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t rr[32];
-          __syncwarp();
-          tmem_ld_32x32b_x32(taddr + 32 * half, rr);
-          tmem_ld_wait();
-          if (row_ok) {
+        for (int j = 0; j < 16; ++j) {
+          const float a = silu_fast(__uint_as_float(rr[hh & 1][2 * j]) + bias[2 * j]);
+          const float b = silu_fast(__uint_as_float(rr[hh & 1][2 * j + 1]) + bias[2 * j + 1]);
+          pk[j] = inside ? pack_half2(a, b) : 0u;  // the depth-wise conv zero-pads t1 (common.py:915-923)
+        }
+        if (row_ok) {
+          uint8_t* trow = t1 + prow * 128;
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {  // 16-byte chunks (8 channels) of this half
-              uint32_t pk[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int c = 8 * ch + 2 * j;
-                const float a = silu_fast(__uint_as_float(rr[c]) + b1[32 * half + c]);
-                const float b = silu_fast(__uint_as_float(rr[c + 1]) + b1[32 * half + c + 1]);
-                pk[j] = inside ? pack_half2(a, b) : 0u;  // the depth-wise conv zero-pads t1 (common.py:915-923)
-              }
-              const int chunk = 4 * half + ch;
-              *reinterpret_cast<uint4*>(trow + ((chunk ^ (prow & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            }
-          }
+          for (int ch = 0; ch < 4; ++ch)
+            *reinterpret_cast<uint4*>(trow + (((4 * half + ch) ^ (prow & 7)) << 4)) =
+                make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
         }
       }
       tc_fence_before_sync();
@@ -292,6 +335,7 @@ __global__ void __launch_bounds__(kBnThreads, 1) bneck_kernel(const __grid_const
         mbar_arrive(&bar_acc1_empty[buf]);
         mbar_arrive(&bar_t1_full[buf]);
       }
+      if (q == 0) BN_TRACE(1, s, 3);
       // the output tile whose last block was step s - 1: its MMA2 completes while the taps of step s run
       if (s >= 1 && (s - 1) % nblk == nblk - 1) epilogue2((s - 1) / nblk);
     }
@@ -315,7 +359,9 @@ __global__ void __launch_bounds__(kBnThreads, 1) bneck_kernel(const __grid_const
 #pragma unroll
       for (int v = 0; v < 8; ++v) tb[v] = t1 + ((((p0 + v) & 7) ^ (lane >> 2)) << 4);
 
+      if (warp == 0) BN_TRACE(2, s, 0);
       mbar_wait(&bar_t1_full[buf], (s >> 1) & 1);
+      if (warp == 0) BN_TRACE(2, s, 1);
 
       float2 acc[5][5];
 #pragma unroll
@@ -340,6 +386,7 @@ __global__ void __launch_bounds__(kBnThreads, 1) bneck_kernel(const __grid_const
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_t1_empty[buf]);  // this warp's reads of T1[buf] are complete
+      if (warp == 0) BN_TRACE(2, s, 2);
 
       mbar_wait(bar_a2_empty, (s & 1) ^ 1);  // MMA2 of the previous step has read the A2 tile
 #pragma unroll
@@ -353,6 +400,7 @@ __global__ void __launch_bounds__(kBnThreads, 1) bneck_kernel(const __grid_const
       fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_a2_full);
+      if (warp == 0) BN_TRACE(2, s, 3);
     }
   }
 
@@ -393,6 +441,14 @@ extern "C" int32_t mafb200_bottleneck_supported(int32_t c_in, int32_t mid, int32
     return 0;
   const int mid_pad = round_up(mid, kBnCB), tile_n = round_up(c_out, 16);
   return bneck_smem_bytes(k, mid_pad, mid_pad / kBnCB, tile_n) <= 227 * 1024 ? 1 : 0;
+}
+
+static thread_local long long* g_bneck_trace = nullptr;
+// Debug hook (not part of the hot path): the next mafb200_bottleneck calls of this thread record clock64 stamps of CTA 0
+// into `trace` (device, 3 roles x 64 steps x 4 slots of int64; see BN_TRACE); NULL turns it off.
+extern "C" int32_t mafb200_bottleneck_trace(long long* trace) {
+  g_bneck_trace = trace;
+  return MAF_OK;
 }
 
 // dst = SiLU(W2 * SiLU(DW_k(SiLU(W1 * src + b1)) + dw_bias) + b2)     (DepthBottleneckUni, common.py:898-927)
@@ -472,6 +528,7 @@ extern "C" int32_t mafb200_bottleneck(const maf_tensor* src, int32_t mid, const 
   const long long tiles = static_cast<long long>(src->n) * p.tiles_x * p.tiles_y;
   if (tiles > 0x7fffffff) return fail(MAF_E_ARG, "bottleneck: too many tiles");
   p.tiles = static_cast<int32_t>(tiles);
+  p.trace = g_bneck_trace;
   p.idesc1 = umma_idesc_f16(128, kBnCB);
   p.idesc2 = umma_idesc_f16(128, tile_n);
   const size_t smem = bneck_smem_bytes(k, mid_pad, p.nblk, tile_n);

@@ -50,6 +50,8 @@ struct NmsParams {
   int32_t max_det, max_nms;
   float* det;
   int32_t* count;
+  long long det_stride;    // floats between the detections of consecutive images (0 -> max_det * 6)
+  long long count_stride;  // int32 elements between consecutive counts (0 -> 1)
   int32_t* ncand;       // [B]
   unsigned long long* keys;  // [B][cap_pow2]
   long long cap_pow2;
@@ -148,10 +150,11 @@ __global__ void __launch_bounds__(1024) nms_select_kernel(const NmsParams p) {
   const int no = 5 + p.nc;
   long long n = p.ncand[b];
   if (n > p.cap_pow2) n = p.cap_pow2;
-  float* det = p.det + static_cast<size_t>(b) * p.max_det * 6;
+  float* det = p.det + static_cast<size_t>(b) * (p.det_stride ? p.det_stride : static_cast<long long>(p.max_det) * 6);
+  int32_t* count_b = p.count + static_cast<size_t>(b) * (p.count_stride ? p.count_stride : 1);
   for (int i = threadIdx.x; i < p.max_det * 6; i += blockDim.x) det[i] = 0.0f;
   if (n == 0) {
-    if (threadIdx.x == 0) p.count[b] = 0;
+    if (threadIdx.x == 0) *count_b = 0;
     return;
   }
 
@@ -368,7 +371,7 @@ __global__ void __launch_bounds__(1024) nms_select_kernel(const NmsParams p) {
   if (n_run == n_eff || s_nk >= p.max_det) break;
   __syncthreads();
   }  // attempt
-  if (threadIdx.x == 0) p.count[b] = s_nk;
+  if (threadIdx.x == 0) *count_b = s_nk;
 }
 
 static long long pow2_ceil(long long v) {
@@ -464,9 +467,36 @@ extern "C" int32_t mafb200_nms(const float* pred, int32_t batch, int32_t anchors
 // mafb200_head_decode_detect, which fuses the decode with the threshold / compaction pass so that the
 // [B, A, 5+nc] prediction tensor is never materialised on the serving path).  `boxes`: fp32 (cx, cy, w, h) of
 // anchor a of image b at boxes[(b * anchors + a) * box_stride].
+static int32_t nms_select_impl(const float* boxes, int32_t box_stride, int32_t batch, int32_t anchors, int32_t nc,
+                               double iou_thres, int32_t agnostic, int32_t max_det, int32_t max_nms, float* det,
+                               long long det_stride, int32_t* count, long long count_stride, void* workspace,
+                               size_t workspace_bytes, void* stream);
+
 extern "C" int32_t mafb200_nms_select(const float* boxes, int32_t box_stride, int32_t batch, int32_t anchors, int32_t nc,
                                       double iou_thres, int32_t agnostic, int32_t max_det, int32_t max_nms, float* det,
                                       int32_t* count, void* workspace, size_t workspace_bytes, void* stream) {
+  return nms_select_impl(boxes, box_stride, batch, anchors, nc, iou_thres, agnostic, max_det, max_nms, det, 0, count, 0,
+                         workspace, workspace_bytes, stream);
+}
+
+// Same, writing the PACKED row layout of the detection all-gather (maf_yolo_b200/dist.py): image b's detections at
+// packed + b * row_floats (max_det * 6 floats) and its count, as int32 bits, in the float right behind them — so the
+// rank's slice of the gather buffer is written in place and ONE collective moves both, without any copy kernel.
+extern "C" int32_t mafb200_nms_select_packed(const float* boxes, int32_t box_stride, int32_t batch, int32_t anchors,
+                                             int32_t nc, double iou_thres, int32_t agnostic, int32_t max_det,
+                                             int32_t max_nms, float* packed, int32_t row_floats, void* workspace,
+                                             size_t workspace_bytes, void* stream) {
+  if (!packed || row_floats < max_det * 6 + 1 || max_det <= 0)
+    return fail(MAF_E_ARG, "nms_select_packed: row_floats=%d < max_det * 6 + 1", row_floats);
+  return nms_select_impl(boxes, box_stride, batch, anchors, nc, iou_thres, agnostic, max_det, max_nms, packed, row_floats,
+                         reinterpret_cast<int32_t*>(packed) + static_cast<size_t>(max_det) * 6, row_floats, workspace,
+                         workspace_bytes, stream);
+}
+
+static int32_t nms_select_impl(const float* boxes, int32_t box_stride, int32_t batch, int32_t anchors, int32_t nc,
+                               double iou_thres, int32_t agnostic, int32_t max_det, int32_t max_nms, float* det,
+                               long long det_stride, int32_t* count, long long count_stride, void* workspace,
+                               size_t workspace_bytes, void* stream) {
   if (!boxes || !det || !count || !workspace) return fail(MAF_E_ARG, "nms_select: null pointer");
   if (batch <= 0 || anchors <= 0 || nc <= 0 || box_stride < 4)
     return fail(MAF_E_ARG, "nms_select: bad shape B=%d A=%d nc=%d stride=%d", batch, anchors, nc, box_stride);
@@ -493,6 +523,8 @@ extern "C" int32_t mafb200_nms_select(const float* boxes, int32_t box_stride, in
   p.max_nms = max_nms;
   p.det = det;
   p.count = count;
+  p.det_stride = det_stride;
+  p.count_stride = count_stride;
   const size_t hdr = ((static_cast<size_t>(batch) * 4 + 255) / 256) * 256;
   p.ncand = static_cast<int32_t*>(workspace);
   p.keys = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(workspace) + hdr);

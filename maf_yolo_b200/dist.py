@@ -56,3 +56,39 @@ def all_gather_detections(det: torch.Tensor, count: torch.Tensor, global_batch: 
         keep.append(out[r * rows: r * rows + (re - rs)])
     full = torch.cat(keep, 0)
     return full[:, :-1].reshape(global_batch, max_det, 6), full[:, -1].to(torch.int32)
+
+
+class DetectionGather:
+    """The same single fixed-size collective WITHOUT staging copies: `copies` persistent buffers of
+    shape [world * batch, max_det * 6 + 2] fp32; mafb200_nms_select_packed writes this rank's rows in place (detections
+    + the count as int32 bits right behind them), `gather(i)` is one in-place `all_gather_into_tensor`, and `views(i)`
+    exposes the whole batch as (det [W*B, max_det, 6], count [W*B] int32) without moving anything.  Every rank owns the
+    same number of images (weak scaling / evenly divisible batches); uneven shards use all_gather_detections above."""
+
+    def __init__(self, batch: int, max_det: int, device, group: Optional[dist.ProcessGroup] = None, copies: int = 4):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.batch, self.max_det = batch, max_det
+        self.row = max_det * 6 + 2  # even: every row starts 8-byte aligned
+        self.bufs = [torch.zeros((self.world * batch, self.row), dtype=torch.float32, device=device) for _ in range(copies)]
+
+    def mine(self, i: int) -> torch.Tensor:
+        """This rank's rows of buffer i: the `packed` argument of ops.nms_select_packed."""
+        return self.bufs[i][self.rank * self.batch:(self.rank + 1) * self.batch]
+
+    def gather(self, i: int) -> None:
+        """Enqueues the collective on the current stream (CUDA) / runs it (gloo)."""
+        if self.world == 1:
+            return
+        buf = self.bufs[i]
+        if buf.is_cuda:
+            dist.all_gather_into_tensor(buf, self.mine(i), group=self.group)
+        else:  # gloo (CPU tests of the same logic)
+            dist.all_gather(list(buf.chunk(self.world, 0)), self.mine(i).clone(), group=self.group)
+
+    def views(self, i: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        buf = self.bufs[i]
+        det = buf[:, :self.max_det * 6].unflatten(1, (self.max_det, 6))
+        count = buf.view(torch.int32)[:, self.max_det * 6]
+        return det, count

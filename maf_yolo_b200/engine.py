@@ -182,9 +182,12 @@ class Plan:
 
     @staticmethod
     def _bneck_ok(c_: int, mid: int, k: int) -> bool:
-        """Can the whole DepthBottleneckUni run as ONE kernel (mafb200_bottleneck, K4)?  MAFB200_BNECK=0: round-1 form
-        (expand GEMM, then depth-wise + project)."""
-        if os.environ.get("MAFB200_BNECK", "1") == "0":
+        """Should the whole DepthBottleneckUni run as ONE kernel (mafb200_bottleneck, K4)?  Opt-in (MAFB200_BNECK=1):
+        the kernel is parity-green and removes the 3c_-wide buffer from the plan (160 -> 131.5 MB/img for N), but on B200
+        it measured 0.89x the speed of the two-kernel form it replaces (expand GEMM, then depth-wise + project:
+        profiles/r02_d_bneck_*.txt — its tap warps are issue/latency-bound at 2 warps per scheduler), so the default
+        plan keeps the two-kernel form."""
+        if os.environ.get("MAFB200_BNECK", "0") != "1":
             return False
         return ops.bottleneck_supported(c_, mid, (c_ + 15) // 16 * 16, k)
 

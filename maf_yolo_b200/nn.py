@@ -160,7 +160,7 @@ class B200DetectModel(torch.nn.Module):
     @torch.no_grad()
     def detect_async(self, x: torch.Tensor, conf_thres: float = 0.25, iou_thres: float = 0.45,
                      classes: Optional[Sequence[int]] = None, agnostic: bool = False, multi_label: bool = False,
-                     max_det: int = 300, max_nms: int = _MAX_NMS, after_nms=None) -> "DetectTicket":
+                     max_det: int = 300, max_nms: int = _MAX_NMS, after_nms=None, gather=None) -> "DetectTicket":
         """Serving form of `pred = model(x)[0]; non_max_suppression(pred, ...)` (evaler.py:168,178) that keeps
         several batches in flight instead of draining the GPU between them:
           * the NMS of a batch runs on a side stream and overlaps the forward of the next call (its 32 CTAs
@@ -171,7 +171,10 @@ class B200DetectModel(torch.nn.Module):
         Nothing is synchronised with the host.  Returns a DetectTicket: wait on `.done` (event) before reading
         `.det` [B,max_det,6] / `.count` [B] — the buffers are reused 2 * in_flight calls later; `.consumed` fires
         when `x` has been read.  `after_nms(det, count)` — optional — is invoked on the NMS stream right after
-        the NMS (e.g. to enqueue a D2H copy or the detection all-gather); its result is `.extra`."""
+        the NMS (e.g. to enqueue a D2H copy); its result is `.extra`.
+        `gather` — a maf_yolo_b200.dist.DetectionGather with 2 * in_flight copies — makes the NMS write this rank's rows
+        of the multi-GPU gather buffer in place and enqueues the ONE all-gather behind it; `.det` / `.count` are then
+        views of the whole job's batch ([world * B, max_det, 6], [world * B])."""
         if not x.is_cuda:
             raise RuntimeError("B200DetectModel needs a CUDA input tensor: there is no CPU fallback on this path")
         slot = self._rr % self.in_flight
@@ -212,15 +215,28 @@ class B200DetectModel(torch.nn.Module):
             side = st["stream"]
             side.wait_event(fwd_done)
             with torch.cuda.stream(side):
+                gi = 2 * slot + k  # buffer of the gatherer used by this call
+                if gather is not None and (gather.max_det != max_det or gather.batch != eng.batch or len(gather.bufs) < 2 * self.in_flight):
+                    raise ValueError("gather: DetectionGather(batch, max_det, copies=2 * in_flight) does not match this call")
                 if fused:
                     assert 0 <= conf_thres <= 1, f'conf_thresh must be in 0.0 to 1.0, however {conf_thres} is provided.'
                     assert 0 <= iou_thres <= 1, f'iou_thres must be in 0.0 to 1.0, however {iou_thres} is provided.'
-                    det, cnt = st["det"][k], st["cnt"][k]
-                    ops.nms_select(boxes, self.nc, iou_thres, agnostic, max_det, max_nms, det, cnt, eng.nms_ws[k])
+                    if gather is not None:
+                        ops.nms_select_packed(boxes, self.nc, iou_thres, agnostic, max_det, max_nms, gather.mine(gi), eng.nms_ws[k])
+                    else:
+                        det, cnt = st["det"][k], st["cnt"][k]
+                        ops.nms_select(boxes, self.nc, iou_thres, agnostic, max_det, max_nms, det, cnt, eng.nms_ws[k])
                 else:
                     det, cnt = non_max_suppression_padded(pred, conf_thres, iou_thres, classes, agnostic, multi_label,
                                                           max_det, max_nms, det=st["det"][k], count=st["cnt"][k],
                                                           workspace=st["ws"])
+                    if gather is not None:  # unfused path: stage through the private buffers, then into the gather rows
+                        mine = gather.mine(gi)
+                        mine[:, :max_det * 6].copy_(det.reshape(det.shape[0], -1))
+                        mine.view(torch.int32)[:, max_det * 6].copy_(cnt)
+                if gather is not None:
+                    gather.gather(gi)
+                    det, cnt = gather.views(gi)
                 extra = after_nms(det, cnt) if after_nms is not None else None
                 st["done"][k].record(side)
             eng.reader_done[k] = st["done"][k]

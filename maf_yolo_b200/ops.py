@@ -332,6 +332,16 @@ def nms_select(boxes: torch.Tensor, nc: int, iou_thres: float, agnostic: bool, m
                                    workspace.numel() * workspace.element_size(), _stream()))
 
 
+def nms_select_packed(boxes: torch.Tensor, nc: int, iou_thres: float, agnostic: bool, max_det: int, max_nms: int,
+                      packed: torch.Tensor, workspace: torch.Tensor) -> None:
+    """nms_select writing rows of the all-gather layout: packed [B, row_floats] fp32 (dist.DetectionGather)."""
+    b, a, stride = boxes.shape
+    assert packed.dtype == torch.float32 and packed.dim() == 2 and packed.shape[0] == b and packed.stride(1) == 1
+    check(lib().mafb200_nms_select_packed(boxes.data_ptr(), stride, b, a, nc, float(iou_thres), int(bool(agnostic)),
+                                          max_det, max_nms, packed.data_ptr(), packed.stride(0), workspace.data_ptr(),
+                                          workspace.numel() * workspace.element_size(), _stream()))
+
+
 def nms_workspace_bytes(batch: int, anchors: int, nc: int) -> int:
     return int(lib().mafb200_nms_workspace_bytes(batch, anchors, nc))
 

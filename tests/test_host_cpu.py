@@ -130,9 +130,11 @@ def test_weight_packing_layout():
     assert ws.shape == (24, 3, 3, 3)
 
 
-@pytest.mark.parametrize("variant", ["n", "m"])
-def test_plan_liveness_and_arena(variant):
-    """No two buffers that are live at the same launch overlap in the arena; slices stay in bounds."""
+@pytest.mark.parametrize("variant,bneck", [("n", "0"), ("m", "0"), ("n", "1"), ("s", "1")])
+def test_plan_liveness_and_arena(variant, bneck, monkeypatch):
+    """No two buffers that are live at the same launch overlap in the arena; slices stay in bounds.  bneck = "1": the
+    plan with the fused DepthBottleneckUni kernel (K4, opt-in)."""
+    monkeypatch.setenv("MAFB200_BNECK", bneck)
     g = topology.build_graph(variant)
     plan = engine.Plan(g, 640, 640)
     batch = 4
@@ -183,6 +185,15 @@ def test_plan_liveness_and_arena(variant):
     assert kinds.count("detect_reset") == 1 and kinds.index("detect_reset") < kinds.index("head_pred")
     old = engine.Plan(g, 640, 640, k7=False)
     assert not old.k7 and sum(op.kind == "decode" for op in old.ops) == 1 and len(old.ops) == len(plan.ops)
+    if bneck == "1":  # K4: every k <= 5, c_ <= 64 bottleneck is one kernel and its 3c_-wide buffer is gone
+        names = [op.name for op in plan.ops if op.kind == "bneck"]
+        assert names and not any(b.name.endswith(".expand") and b.name.split(".")[0] in {n.split(".")[0] for n in names}
+                                 for b in plan.bufs)
+        if variant == "n":
+            assert names == ["L2.m0.bottleneck(k3)", "L4.m0.bottleneck(k5)", "L20.m0.bottleneck(k5)", "L22.m0.bottleneck(k5)"]
+            assert plan.bytes_per_image() < 135e6
+    else:
+        assert not any(op.kind == "bneck" for op in plan.ops)
     # MAFPN fusion concats became multi-source GEMMs, upsample was fused away
     assert not any(op.kind == "upsample2x" for op in plan.ops)
     assert max(len(op.reads) for op in plan.ops if op.kind == "conv1x1") == 4
@@ -190,6 +201,7 @@ def test_plan_liveness_and_arena(variant):
 
 @pytest.mark.parametrize("variant", ["n", "s", "m"])
 def test_pad_fill_only_touches_unowned_padding(variant, monkeypatch):
+    monkeypatch.setenv("MAFB200_BNECK", "1")
     """Ops that end inside a 32-byte sector at the end of a padded buffer get zero filters for the padding channels
     (whole-sector stores).  Those channels must belong to no other view, the op must be the buffer's last-channel
     writer, and sigmoid outputs (act(0) != 0) are never extended."""

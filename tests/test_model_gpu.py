@@ -88,6 +88,27 @@ def test_forward_matches_oracle(cuda_device, variant, batch):
     _check_pred(pred, ref, f"MAF-YOLO-{variant} bs{batch} vs oracle")
 
 
+@pytest.mark.parametrize("variant", ["n", "s"])
+def test_forward_with_fused_bottleneck_matches_oracle(cuda_device, variant, monkeypatch):
+    """The opt-in plan with K4 (MAFB200_BNECK=1: every k <= 5, c_ <= 64 DepthBottleneckUni as one kernel) against the
+    oracle, on the seed-0 and on the conditioned weight family."""
+    import maf_yolo_b200 as mb
+    from oracle import model as om
+    from tests import _cond
+
+    monkeypatch.setenv("MAFB200_BNECK", "1")
+    g, sd, spec, x = _setup(variant, 1)
+    model = mb.from_state_dict(sd, variant)
+    pred = model(x.to(cuda_device))[0]
+    assert any(op.kind == "bneck" for op in model.engine_for(x.to(cuda_device)).plan.ops)
+    _check_pred(pred, om.forward_train_form(spec, sd, x), f"K4 plan MAF-YOLO-{variant} vs oracle")
+    g, sd, x = _cond.conditioned_inputs(variant, 2)
+    ref = om.forward_train_form(spec, sd, x)
+    eh = _reference_half_errors(spec, sd, x, ref)
+    _check_pred(mb.from_state_dict(sd, variant)(x.to(cuda_device))[0], ref, f"K4 plan, conditioned MAF-YOLO-{variant}",
+                score_tol=min(COND_SCORE_CAP, COND_SCORE_VS_HALF * eh["score"]), elem_tol=COND_ELEM_TOL, grid_tol=COND_GRID_TOL)
+
+
 def test_forward_matches_reference_golden(cuda_device):
     """Against the committed output of the unmodified reference (tests/golden/make_golden.py)."""
     import maf_yolo_b200 as mb
@@ -188,7 +209,8 @@ def test_end_to_end_detections(cuda_device):
 # stride-normalised.  Scores: an absolute 1e-3 is out of reach of ANY fp16 path on these inputs — the reference's own
 # `--half` mode deviates by 2e-3 .. 4e-3 from its fp32 result — so the gate is relative to that measured deviation
 # (<= COND_SCORE_VS_HALF x the reference-fp16 error of the same input, never above COND_SCORE_CAP), both printed.
-COND_ELEM_TOL, COND_GRID_TOL, COND_SCORE_VS_HALF, COND_SCORE_CAP = 1e-3, 1e-2, 3.0, 1e-2
+# Measured (profiles/r02_*parity*.txt): ours 1.1e-3 .. 1.0e-2, the reference's fp16 mode 1.9e-3 .. 1.3e-2 on the same inputs.
+COND_ELEM_TOL, COND_GRID_TOL, COND_SCORE_VS_HALF, COND_SCORE_CAP = 1e-3, 1e-2, 2.0, 2e-2
 
 
 def _reference_half_errors(spec, sd, x, ref):

@@ -144,3 +144,14 @@ def test_oracle_reproduces_conditioned_fixtures(variant, kind):
     st, opt = fx["cand_status"], fx["cand_optional"]
     r = _cond.check_against_fixture(fx["det0"], fx, f"{variant}/{kind} reference vs its own certification")
     assert r["strict"] == (kind == "strict") and r["n_must"] == int(((st == 1) & ~opt).sum())
+
+
+def test_torchvision_form_of_the_nms_oracle_equals_the_numpy_form():
+    """bench.py times `non_max_suppression_tv` (torchvision.ops.nms, the library call of nms.py:96) as the reference's
+    NMS; it must return exactly what the numpy restatement (the parity checker) returns."""
+    pred = synthetic_pred(2, 8400, 80, seed=1)
+    for kw in (dict(conf_thres=0.03, iou_thres=0.65, multi_label=True), dict(conf_thres=0.4, iou_thres=0.45, max_det=1000),
+               dict(conf_thres=0.03, iou_thres=0.65, multi_label=True, agnostic=True, classes=[1, 5, 7])):
+        a = onms.non_max_suppression(pred.numpy(), **kw)
+        b = onms.non_max_suppression_tv(pred.clone(), **kw)
+        assert all(np.array_equal(x, y.numpy()) for x, y in zip(a, b)), kw
