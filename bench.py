@@ -174,7 +174,9 @@ def run_reference_arm(a):
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons of this rank's GPU during the timed region."""
+    """Samples SM clocks / throttle reasons of this rank's GPU during the timed region — in process through NVML
+    (nvidia_ml_py), so that 8 ranks do not fork 8 x 50 nvidia-smi processes per second next to the enqueue threads
+    (round 1 did, and its host enqueue time tripled at N = 8); falls back to nvidia-smi if NVML is not importable."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -182,17 +184,41 @@ class ClockSampler(threading.Thread):
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        flag = lambda name: "Active" if r & getattr(n, name, 0) else "Not Active"  # noqa: E731
+        return [str(sm), str(mx), "0", flag("nvmlClocksThrottleReasonHwSlowdown"), flag("nvmlClocksThrottleReasonHwThermalSlowdown"),
+                flag("nvmlClocksThrottleReasonSwThermalSlowdown"), flag("nvmlClocksThrottleReasonSwPowerCap")]
 
     def run(self):
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                if self.nvml is not None:
+                    self.rows.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self._stop_evt.wait(0.02)
+            self._stop_evt.wait(0.004 if self.nvml is not None else 0.05)
 
     def stop(self):
         self._stop_evt.set()
@@ -205,7 +231,7 @@ class ClockSampler(threading.Thread):
                     reasons.add(name)
         mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+                "reasons": sorted(reasons), "samples": len(self.rows), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def measured_hbm_peak():
@@ -303,9 +329,14 @@ def run_ours(a):
     cnt = torch.empty((B,), dtype=torch.int32, device=dev)
     det_host = [torch.empty_like(det, device="cpu").pin_memory() for _ in range(n_in)]  # one per step in flight
     cnt_host = [torch.empty_like(cnt, device="cpu").pin_memory() for _ in range(n_in)]
+    packed_host = [torch.empty((B, EVAL_NMS["max_det"] * 6 + 2), dtype=torch.float32).pin_memory() for _ in range(n_in)]
 
     pipelined = not a.no_pipeline
     pending = []  # done-events of the last 2 * in_flight steps (side streams)
+
+    # multi-GPU: the NMS writes this rank's rows of a persistent gather buffer in place, ONE in-place NCCL all-gather
+    # follows on the NMS stream — no staging copies, no aten kernels (maf_yolo_b200.dist.DetectionGather)
+    gatherer = mdist.DetectionGather(B, EVAL_NMS["max_det"], dev, copies=2 * in_flight) if (world > 1 and pipelined) else None
 
     def gather(d, c):
         return mdist.all_gather_detections(d, c, B * world) if world > 1 else (d, c)
@@ -316,8 +347,7 @@ def run_ours(a):
         stream where it overlaps the NEXT step's forward; every step's work is still inside the timed region
         (the closing event waits for the last NMS)."""
         if pipelined:
-            fn = (lambda d, c: after(*gather(d, c))) if after is not None else gather
-            t = model.detect_async(x, **EVAL_NMS, after_nms=fn)
+            t = model.detect_async(x, **EVAL_NMS, after_nms=after, gather=gatherer)
             pending.append(t.done)
             del pending[:-2 * in_flight]
             return t
@@ -413,9 +443,12 @@ def run_ours(a):
 
     d2h_n = [0]
 
-    def d2h(d, c):  # runs on the stream the NMS ran on
+    def d2h(d, c, packed=None):  # runs on the stream the NMS ran on
         j = d2h_n[0] % n_in
         d2h_n[0] += 1
+        if packed is not None:  # gatherer: this rank's rows (detections + count bits) in one copy
+            packed_host[j].copy_(packed, non_blocking=True)
+            return
         det_host[j].copy_(d[:B] if world == 1 else d[rank * B:(rank + 1) * B], non_blocking=True)
         cnt_host[j].copy_(c[:B] if world == 1 else c[rank * B:(rank + 1) * B], non_blocking=True)
 
@@ -438,7 +471,32 @@ def run_ours(a):
     e2e_value = B * world * a.steps / (ms_e2e / 1e3)
     host_enqueue_e2e_ms = host_ms[0]
     h2d = host_u8[0].numel()
-    d2h_bytes = det_host[0].numel() * 4 + cnt_host[0].numel() * 4
+    d2h_bytes = packed_host[0].numel() * 4 if gatherer is not None else det_host[0].numel() * 4 + cnt_host[0].numel() * 4
+
+    # ---- multi-GPU: the gathered detections are what every rank computed locally -----------------
+    gather_check = None
+    if world > 1:
+        t = model.detect_async(x_f32[0], **EVAL_NMS)  # local results, no collective
+        t.done.synchronize()
+        local = (t.det.clone(), t.count.clone())
+        if gatherer is not None:
+            t = model.detect_async(x_f32[0], **EVAL_NMS, gather=gatherer)
+            t.done.synchronize()
+            gd, gc = t.det, t.count
+        else:
+            gd, gc = gather(*local)
+            torch.cuda.synchronize()
+        mine_ok = torch.equal(gd[rank * B:(rank + 1) * B], local[0]) and torch.equal(gc[rank * B:(rank + 1) * B], local[1])
+        # every rank holds the same gathered buffer: compare a checksum of checksums across ranks
+        chk = torch.stack([gd.double().sum(), gc.double().sum(), torch.tensor(float(mine_ok), device=dev, dtype=torch.float64)])
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        ok = bool(torch.equal(lo[:2], hi[:2])) and float(lo[2]) == 1.0 and int(gc.sum()) > 0
+        gather_check = {"ok": ok, "what": "rank r's rows of the NCCL-gathered [W*B, 300, 6] + counts equal its local NMS output "
+                                          "(all ranks), and all ranks hold the same gathered buffer (checksum min == max)"}
+        if not ok:
+            raise SystemExit(f"rank {rank}: gathered detections differ from the local ones")
 
     if rank != 0:
         if world > 1:
@@ -518,7 +576,7 @@ def run_ours(a):
         "latency_ms_per_batch": latency,
         "host_enqueue_ms_per_step": {"value_loop": round(host_enqueue_ms, 4), "e2e_loop": round(host_enqueue_e2e_ms, 4)},
         "clocks": clocks, "roofline": roofline, "whole_step": whole, "cpu_baseline": cpu,
-        "gpu_library_baseline": lib_base,
+        "gpu_library_baseline": lib_base, "gather_check": gather_check,
     }
     emit(line)
     if world > 1:

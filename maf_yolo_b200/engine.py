@@ -421,6 +421,9 @@ class Engine:
             self._calls: List[Callable[[], None]] = [self._bind(op, folded) for op in self.plan.ops]
         # captured graphs, keyed by (prediction-buffer index, detect configuration or None)
         self._graphs: Dict[Tuple[int, object], torch.cuda.CUDAGraph] = {}
+        # whole-forward graphs (stem included) per input address, and how often an address has been seen
+        self._full_graphs: Dict[object, torch.cuda.CUDAGraph] = {}
+        self._ptr_seen: Dict[object, int] = {}
         # detect mode (B200DetectModel.detect_async): the decode kernel also does the NMS threshold / compaction pass
         # and the prediction tensor is not materialised; buffers are allocated on first use
         self._detect: Optional[Tuple[float, bool, Optional[Tuple[int, ...]]]] = None
@@ -736,11 +739,19 @@ class Engine:
             torch.cuda.current_stream(self.device).wait_event(self.last_async_forward)
             self.last_async_forward = None
         self._upload_detect_cfg()
-        # The stem kernel reads the caller's tensor (its address changes per call), so it is launched
-        # eagerly; everything behind it only touches engine-owned memory and is replayed as one graph.
-        self._calls[0]()
+        # The stem kernel reads the caller's tensor.  Serving loops feed a few staging buffers over and over, so once an
+        # input ADDRESS has been seen twice the whole forward — stem included — is captured for that address and a step
+        # is ONE graph launch (bounded: the 8 most recent addresses).  For a new address the stem is launched eagerly
+        # and everything behind it, which only touches engine-owned memory, is replayed as one graph.
         gkey = self._graph_key(k, detect)
+        ptr = x.data_ptr()
+        fkey = (gkey, ptr, x.dtype)
+        full = self._full_graphs.get(fkey)
+        if full is not None:
+            full.replay()
+            return self.pred if detect is None else self.boxes[k]
         if gkey not in self._graphs:
+            self._calls[0]()
             for call in self._calls[1:]:  # warm-up outside capture (sets func attributes, loads modules)
                 call()
             torch.cuda.synchronize(self.device)
@@ -752,7 +763,26 @@ class Engine:
                     for call in self._calls[1:]:
                         call()
             self._graphs[gkey] = g
-            self._calls[0]()
+        seen = self._ptr_seen.get(fkey, 0) + 1
+        self._ptr_seen[fkey] = seen
+        if seen >= 2 and os.environ.get("MAFB200_FULL_GRAPH", "1") != "0":
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._calls[0]()
+                if self._schedule is not None:
+                    self._launch_scheduled(1)
+                else:
+                    for call in self._calls[1:]:
+                        call()
+            if len(self._full_graphs) >= 8:
+                self._full_graphs.pop(next(iter(self._full_graphs)))
+            if len(self._ptr_seen) > 64:
+                self._ptr_seen.clear()
+            self._full_graphs[fkey] = g
+            g.replay()
+            return self.pred if detect is None else self.boxes[k]
+        self._calls[0]()
         self._graphs[gkey].replay()
         return self.pred if detect is None else self.boxes[k]
 

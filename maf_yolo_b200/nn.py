@@ -237,7 +237,11 @@ class B200DetectModel(torch.nn.Module):
                 if gather is not None:
                     gather.gather(gi)
                     det, cnt = gather.views(gi)
-                extra = after_nms(det, cnt) if after_nms is not None else None
+                    # with a gatherer the callback also gets this rank's packed rows (contiguous [B, max_det*6+2]:
+                    # detections + count bits), so that a D2H of the local results is ONE copy
+                    extra = after_nms(det, cnt, gather.mine(gi)) if after_nms is not None else None
+                else:
+                    extra = after_nms(det, cnt) if after_nms is not None else None
                 st["done"][k].record(side)
             eng.reader_done[k] = st["done"][k]
         return DetectTicket(det, cnt, st["done"][k], fwd_done, extra)

@@ -371,3 +371,17 @@ def test_api_contract(cuda_device):
         model.train()
     with pytest.raises(AssertionError, match="conf_thresh must be in 0.0 to 1.0"):
         mb.non_max_suppression(torch.zeros(1, 10, 85, device=cuda_device), conf_thres=1.5)
+
+
+def test_second_device_in_the_same_process(cuda_device):
+    """the >48 KB dynamic shared-memory opt-in is per device — a model on cuda:1 after one on cuda:0 in the
+    same process (skipped on single-GPU boxes)."""
+    import maf_yolo_b200 as mb
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    g, sd, spec, x = _setup("n", 1)
+    a = mb.from_state_dict(sd, "n")(x.to("cuda:0"))[0].cpu()
+    b = mb.from_state_dict(sd, "n")(x.to("cuda:1"))[0].cpu()
+    d = mb.non_max_suppression(mb.from_state_dict(sd, "n")(x.to("cuda:1"))[0], 0.03, 0.65, multi_label=True)
+    assert torch.equal(a, b) and d[0].device.index == 1
