@@ -214,7 +214,7 @@ def detect_eval(head_outs, strides=(8, 16, 32), reg_max=16, nc=80):
     anchor_points, stride_tensor = generate_anchors_eval([o[0].shape[2:] for o in head_outs], strides)
     # yolo.py:328-330; a parameter of the model, so `model.half()` (evaler.py:112) casts it with the convs while the
     # anchor points stay fp32 (anchor_generator.py:18) and promote the boxes back to fp32
-    proj = torch.linspace(0, reg_max, reg_max + 1).view(1, reg_max + 1, 1, 1).to(head_outs[0][2].dtype)
+    proj = torch.linspace(0, reg_max, reg_max + 1).view(1, reg_max + 1, 1, 1).to(head_outs[0][2])
     cls_l, reg_l = [], []
     for stem, cls, reg in head_outs:
         b, _, h, w = stem.shape

@@ -443,11 +443,11 @@ def test_head_pred_epilogues(cuda_device, c_in, sizes):
         torch.cuda.synchronize()
         assert int(want_c.sum()) > 0 and torch.equal(cnt, want_c) and torch.equal(det, want_d), kw
         # the same selection written as rows of the multi-GPU gather buffer (detections + count bits per row)
-        packed = torch.full((n, 300 * 6 + 2), float("nan"), device=cuda_device)
-        ops.nms_select_packed(boxes, nc, 0.65, False, 300, 30000, packed, ws)
+        rows = torch.full((n, 300 * 6 + 2), float("nan"), device=cuda_device)
+        ops.nms_select_packed(boxes, nc, 0.65, False, 300, 30000, rows, ws)
         torch.cuda.synchronize()
-        assert torch.equal(packed[:, :1800].reshape(n, 300, 6), want_d)
-        assert torch.equal(packed.view(torch.int32)[:, 1800], want_c)
+        assert torch.equal(rows[:, :1800].reshape(n, 300, 6), want_d)
+        assert torch.equal(rows.view(torch.int32)[:, 1800], want_c)
     assert torch.equal(boxes, pred[..., :4])
 
 
