@@ -227,7 +227,7 @@ def detect_eval(head_outs, strides=(8, 16, 32), reg_max=16, nc=80):
     reg_all = torch.cat(reg_l, -1).permute(0, 2, 1)
     boxes = dist2bbox_xywh(reg_all, anchor_points)
     boxes = boxes * stride_tensor
-    return torch.cat([boxes, torch.ones((boxes.shape[0], boxes.shape[1], 1), dtype=boxes.dtype), cls_all], -1)
+    return torch.cat([boxes, torch.ones((boxes.shape[0], boxes.shape[1], 1), dtype=boxes.dtype, device=boxes.device), cls_all], -1)
 
 
 # ------------------------------------------------------------------------------------------------
