@@ -381,6 +381,7 @@ __device__ __forceinline__ void head_epilogue_loop(const GemmParams& p, const Ge
         }
         tmem_ld_wait();
         const int valid = min(32, p.N - c);
+        uint32_t bits = 0;  // multi-label: columns of this chunk that are candidates of this thread's row
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           if (j >= valid) break;
@@ -389,16 +390,44 @@ __device__ __forceinline__ void head_epilogue_loop(const GemmParams& p, const Ge
           if (emit && v > skip_below) {
             const float s = sigmoid_fast(v);  // score = cls * obj, obj == 1 (nms.py:69)
             if (multi_label) {
-              if (s > conf && (filt == nullptr || filt[c + j] != 0)) {
-                const long long slot = atomicAdd(&p.ncand[b], 1);
-                if (slot < p.cap_pow2)
-                  p.keys[static_cast<size_t>(b) * p.cap_pow2 + slot] =
-                      (static_cast<unsigned long long>(~__float_as_uint(s)) << 32) |
-                      static_cast<unsigned long long>(static_cast<unsigned>(a) * p.nc + (c + j));
-              }
+              if (s > conf && (filt == nullptr || filt[c + j] != 0)) bits |= 1u << j;
             } else if (s > best) {
               best = s;
               best_c = c + j;
+            }
+          }
+        }
+        // Emission, warp-aggregated: one atomicAdd per warp and chunk instead of one per candidate (random-weight S / M
+        // heads put 10-50 k candidates on an image; the per-candidate atomics on the image's single counter made this
+        // kernel 5x slower than the GEMM itself).  The common case — no candidate in the chunk — is one vote.
+        if (__any_sync(0xffffffffu, bits != 0)) {
+          const int cnt = __popc(bits);
+          int incl = cnt;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+          }
+          const int total = __shfl_sync(0xffffffffu, incl, 31);
+          long long base;
+          if (__all_sync(0xffffffffu, !row_ok || b == __shfl_sync(0xffffffffu, b, 0)) && __shfl_sync(0xffffffffu, row_ok ? 1 : 0, 0)) {
+            int b0 = 0;
+            if (lane == 0) b0 = atomicAdd(&p.ncand[b], total);  // every candidate row of the warp belongs to image b
+            base = static_cast<long long>(__shfl_sync(0xffffffffu, b0, 0)) + (incl - cnt);
+          } else {  // the 32 rows straddle two images (or lane 0 is past the end): per-lane reservation
+            base = cnt > 0 ? atomicAdd(&p.ncand[b], cnt) : 0;
+          }
+          if (bits != 0) {
+            unsigned long long* kb = p.keys + static_cast<size_t>(b) * p.cap_pow2;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (bits & (1u << j)) {
+                const float s = sigmoid_fast(__fadd_rn(__uint_as_float(r[j]), s_bias[c + j]));  // the same value as above
+                if (base < p.cap_pow2)
+                  kb[base] = (static_cast<unsigned long long>(~__float_as_uint(s)) << 32) |
+                             static_cast<unsigned long long>(static_cast<unsigned>(a) * p.nc + (c + j));
+                ++base;
+              }
             }
           }
         }
