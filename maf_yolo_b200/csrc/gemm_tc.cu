@@ -410,7 +410,11 @@ __device__ __forceinline__ void head_epilogue_loop(const GemmParams& p, const Ge
           }
           const int total = __shfl_sync(0xffffffffu, incl, 31);
           long long base;
-          if (__all_sync(0xffffffffu, !row_ok || b == __shfl_sync(0xffffffffu, b, 0)) && __shfl_sync(0xffffffffu, row_ok ? 1 : 0, 0)) {
+          // (every lane must execute the shuffles: no short-circuit evaluation around them)
+          const int b_lane0 = __shfl_sync(0xffffffffu, b, 0);
+          const int lane0_ok = __shfl_sync(0xffffffffu, row_ok ? 1 : 0, 0);
+          const bool same_image = __all_sync(0xffffffffu, !row_ok || b == b_lane0) != 0;
+          if (same_image && lane0_ok) {
             int b0 = 0;
             if (lane == 0) b0 = atomicAdd(&p.ncand[b], total);  // every candidate row of the warp belongs to image b
             base = static_cast<long long>(__shfl_sync(0xffffffffu, b0, 0)) + (incl - cnt);
