@@ -42,6 +42,7 @@ constexpr int kBnA2Bytes = kBnTX * kBnTY * 128;  // 25600: 200 pixel rows (the M
 struct BneckParams {
   CUtensorMap tm_x;    // x as {c_, W, H, N}, box {64, TW, TH, 1}, SWIZZLE_128B
   CUtensorMap tm_w1;   // W1 packed fp16 [mid_pad][64], box {64, mid_pad}, SWIZZLE_128B
+  CUtensorMap tm_w1b;  // the same W1, box {64, 64}: one 64-channel block (2-CTA shape)
   CUtensorMap tm_w2;   // W2 packed fp16 [tile_n][mid_pad], box {64, tile_n}, SWIZZLE_128B
   const float* b1;     // [mid_pad]
   const float* dw_w;   // [k*k][mid_pad] fp32
@@ -409,6 +410,281 @@ __global__ void __launch_bounds__(kBnThreads, 1) bneck_kernel(const __grid_const
   if (warp == kBnTapWarps + kBnEpiWarps) tmem_dealloc(tmem_base, 512);
 }
 
+// ================================================================================================================
+// K4, second shape — two CTAs per SM, every warp does every phase (the structure of dwpw_kernel, which measured
+// faster than the warp-specialised persistent shape above because 16 tap warps per SM hide each other's latencies):
+//   one CTA = one 8 x 16 output tile of one image; halo (8+k-1) x (16+k-1) <= 240 pixels = 2 M tiles of the expand GEMM;
+//   per 64-channel block cb of the mid channels:
+//     thread 0: MMA1(cb) = Xhalo[256 x 64] * W1[cb]^T -> acc1 (128 TMEM columns); W1 / W2 blocks stream through one
+//               shared-memory slot each (TMA), so shared memory does not grow with `mid`
+//     all 8 warps: epilogue 1 (warp = (M tile, lane quarter), one halo pixel per thread): +b1, SiLU, 0 outside the image,
+//               fp16 -> T1 (chunk-swizzled);  __syncthreads;  thread 0 issues MMA1(cb+1) — it overlaps the taps
+//     all 8 warps: taps, warp = 4 x 4 pixel unit, lane = channel pair (16 x k*k FFMA2), +bd, SiLU -> A2 (SW128 by hand)
+//     thread 0: MMA2(cb): acc2[128 x c_] += A2 * W2[cb]^T
+//   final epilogue: acc2 -> +b2 -> SiLU -> global (warps 0-3 / 4-7 take the two 32-column halves).
+// ~105 KB of shared memory and 256 TMEM columns per CTA.
+constexpr int kB2TX = 16, kB2TY = 8;
+constexpr int kB2Threads = 256;
+
+template <int K>
+__global__ void __launch_bounds__(kB2Threads, 2) bneck2_kernel(const __grid_constant__ BneckParams p) {
+  constexpr int P = K / 2;
+  constexpr int TW = kB2TX + K - 1, TH = kB2TY + K - 1;
+  constexpr int kHaloRows = TH * TW;               // 240 (k = 5) / 180 (k = 3)
+  constexpr uint32_t kXBytes = kHaloRows * 128;
+  constexpr int U = 4;                             // unit = 4 x 4 output pixels per warp
+  static_assert(kHaloRows <= 256, "halo must fit two M tiles");
+
+  extern __shared__ uint8_t smem_b2_raw[];
+  uint8_t* smem = smem_b2_raw + ((1024u - (smem_u32(smem_b2_raw) & 1023u)) & 1023u);
+  constexpr uint32_t kXAlloc = ((kXBytes + 1023) / 1024) * 1024;
+  uint8_t* s_x = smem;                              // [kHaloRows][128 B]; MMA1 reads 256 rows (the tail = rows of A2: unused)
+  uint8_t* s_a2 = s_x + kXAlloc;                    // [128 rows][128 B]
+  uint8_t* s_w1 = s_a2 + 16384;                     // 2 slots x [64 rows][128 B]
+  uint8_t* s_w2 = s_w1 + 2 * 8192;                  // 2 slots x [tile_n rows][128 B] (8 KB apart)
+  uint8_t* s_t1 = s_w2 + 2 * 8192;                  // [kHaloRows][128 B], chunk-swizzled by hand
+  float* s_b2 = reinterpret_cast<float*>(s_t1 + ((kXBytes + 127) / 128) * 128);  // [64]
+  float* s_b1 = s_b2 + 64;                          // [mid_pad]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_b1 + p.mid_pad);
+  uint64_t* bar_x = bars;
+  uint64_t* bar_w1 = bars + 1;   // [2] per slot
+  uint64_t* bar_w2 = bars + 3;   // [2] per slot
+  uint64_t* bar_mma1 = bars + 5;
+  uint64_t* bar_mma2 = bars + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile_x = blockIdx.x % p.tiles_x, tile_y = blockIdx.x / p.tiles_x;
+  const int img = blockIdx.y;
+  const int x0 = tile_x * kB2TX, y0 = tile_y * kB2TY;
+  const int nblk = p.nblk, mid_pad = p.mid_pad;
+  const int w2_bytes = p.tile_n * 128;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.tm_x);
+    tma_prefetch_desc(&p.tm_w1b);
+    tma_prefetch_desc(&p.tm_w2);
+    mbar_init(bar_x, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_w1[i], 1);
+      mbar_init(&bar_w2[i], 1);
+    }
+    mbar_init(bar_mma1, 1);
+    mbar_init(bar_mma2, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < p.tile_n; i += kB2Threads) s_b2[i] = __ldg(p.b2 + i);
+  for (int i = threadIdx.x; i < p.mid_pad; i += kB2Threads) s_b1[i] = __ldg(p.b1 + i);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t acc2_col = 128;
+
+  auto issue_mma1 = [&](int cb) {  // thread 0 only
+    if (cb == 0) mbar_wait(bar_x, 0);
+    mbar_wait(&bar_w1[cb & 1], (cb >> 1) & 1);
+    tc_fence_after_sync();
+    const uint64_t db = umma_smem_desc_sw128(smem_u32(s_w1 + (cb & 1) * 8192));
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const uint64_t da = umma_smem_desc_sw128(smem_u32(s_x + mt * 16384));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) tc_mma_f16(tmem_base + mt * kBnCB, da + 2 * k, db + 2 * k, p.idesc1, k != 0 ? 1u : 0u);
+    }
+    tc_commit(bar_mma1);
+  };
+
+  if (threadIdx.x == 0) {
+    pdl_launch_dependents();
+    for (int i = 0; i < 2 && i < nblk; ++i) {  // weights are constants: may start before the previous kernel ends
+      mbar_arrive_expect_tx(&bar_w1[i], 8192);
+      tma_load_2d(s_w1 + i * 8192, &p.tm_w1b, &bar_w1[i], 0, i * kBnCB);
+      mbar_arrive_expect_tx(&bar_w2[i], w2_bytes);
+      tma_load_2d(s_w2 + i * 8192, &p.tm_w2, &bar_w2[i], i * kBnCB, 0);
+    }
+    pdl_wait();  // x (and, causally, every output store) follows the previous kernels
+    mbar_arrive_expect_tx(bar_x, kXBytes);
+    tma_load_tile_4d(s_x, &p.tm_x, bar_x, 0, x0 - P, y0 - P, img);
+    issue_mma1(0);
+  }
+
+  // epilogue-1 role of this thread: one halo pixel
+  const int e_mt = warp >> 2, e_q = warp & 3;
+  const int e_row = e_mt * 128 + e_q * 32 + lane;
+  const int e_py = e_row / TW, e_px = e_row - e_py * TW;
+  const bool e_row_ok = e_row < kHaloRows;
+  const bool e_inside = e_row_ok && y0 - P + e_py >= 0 && y0 - P + e_py < p.H && x0 - P + e_px >= 0 && x0 - P + e_px < p.W;
+  const uint32_t e_taddr = tmem_base + e_mt * kBnCB + (static_cast<uint32_t>(e_q * 32) << 16);
+  // tap role: 4 x 4 unit
+  const int uy = warp >> 2, ux = warp & 3;
+  const int oy0 = uy * U, ox0 = ux * U;
+  const int p0 = oy0 * TW + ox0;
+
+  for (int cb = 0; cb < nblk; ++cb) {
+    const int c0 = cb * kBnCB;
+    // ---- epilogue 1: acc1 -> T1 ------------------------------------------------------------------------------------
+    mbar_wait(bar_mma1, cb & 1);
+    tc_fence_after_sync();
+    if (threadIdx.x == 0 && cb + 2 < nblk) {  // MMA1(cb) is complete: its W1 slot takes the panel of block cb + 2
+      mbar_arrive_expect_tx(&bar_w1[cb & 1], 8192);
+      tma_load_2d(s_w1 + (cb & 1) * 8192, &p.tm_w1b, &bar_w1[cb & 1], 0, c0 + 2 * kBnCB);
+    }
+    {
+      uint32_t rr[2][32];
+      __syncwarp();
+      tmem_ld_32x32b_x32(e_taddr, rr[0]);
+      tmem_ld_32x32b_x32(e_taddr + 32, rr[1]);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        // bias to registers BEFORE the math: the T1 stores below may alias s_b1 as far as the compiler knows
+        float bias[32];
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) *reinterpret_cast<float4*>(&bias[c]) = *reinterpret_cast<const float4*>(s_b1 + c0 + 32 * h + c);
+        if (h == 0) tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float a = silu_fast(__uint_as_float(rr[h][2 * j]) + bias[2 * j]);
+          const float b = silu_fast(__uint_as_float(rr[h][2 * j + 1]) + bias[2 * j + 1]);
+          pk[j] = e_inside ? pack_half2(a, b) : 0u;  // the depth-wise conv zero-pads t1 (common.py:915-923)
+        }
+        if (e_row_ok) {
+          uint8_t* trow = s_t1 + e_row * 128;
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch)
+            *reinterpret_cast<uint4*>(trow + (((4 * h + ch) ^ (e_row & 7)) << 4)) =
+                make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+        }
+      }
+    }
+    // depth-wise weights of this thread's two channels (L2-resident, coalesced): in flight across the barrier
+    float2 wreg[K * K];
+#pragma unroll
+    for (int t = 0; t < K * K; ++t) wreg[t] = __ldg(reinterpret_cast<const float2*>(p.dw_w + static_cast<size_t>(t) * mid_pad + c0 + 2 * lane));
+    const float2 bv = __ldg(reinterpret_cast<const float2*>(p.dw_b + c0 + 2 * lane));
+    tc_fence_before_sync();
+    __syncthreads();  // T1 complete, acc1 drained
+    tc_fence_after_sync();
+    if (threadIdx.x == 0 && cb + 1 < nblk) issue_mma1(cb + 1);  // overlaps the taps below
+
+    // ---- taps: T1 -> registers --------------------------------------------------------------------------------------
+    const uint8_t* t1 = s_t1 + p0 * 128 + ((lane & 3) << 2);
+    const uint8_t* tb[8];
+#pragma unroll
+    for (int v = 0; v < 8; ++v) tb[v] = t1 + ((((p0 + v) & 7) ^ (lane >> 2)) << 4);
+    float2 acc[U][U];
+#pragma unroll
+    for (int i = 0; i < U; ++i)
+#pragma unroll
+      for (int r = 0; r < U; ++r) acc[i][r] = bv;
+#pragma unroll
+    for (int d = 0; d < U + K - 1; ++d) {
+      float2 win[U + K - 1];
+#pragma unroll
+      for (int j = 0; j < U + K - 1; ++j)
+        win[j] = __half22float2(*reinterpret_cast<const __half2*>(tb[(d * TW + j) & 7] + (d * TW + j) * 128));
+#pragma unroll
+      for (int i = 0; i < U; ++i) {
+        const int ky = d - i;
+        if (ky < 0 || ky >= K) continue;
+#pragma unroll
+        for (int r = 0; r < U; ++r)
+#pragma unroll
+          for (int kx = 0; kx < K; ++kx) acc[i][r] = ffma2(win[r + kx], wreg[ky * K + kx], acc[i][r]);
+      }
+    }
+    // ---- A2 tile + MMA2 -----------------------------------------------------------------------------------------------
+    if (cb > 0) mbar_wait(bar_mma2, (cb - 1) & 1);  // MMA2 of the previous block has read A2 (and its W2 slot)
+    if (threadIdx.x == 0 && cb > 0 && cb + 1 < nblk) {  // the freed W2 slot takes the panel of block cb + 1
+      mbar_arrive_expect_tx(&bar_w2[(cb + 1) & 1], w2_bytes);
+      tma_load_2d(s_w2 + ((cb + 1) & 1) * 8192, &p.tm_w2, &bar_w2[(cb + 1) & 1], c0 + kBnCB, 0);
+    }
+#pragma unroll
+    for (int i = 0; i < U; ++i)
+#pragma unroll
+      for (int r = 0; r < U; ++r) {
+        const int prow = (oy0 + i) * kB2TX + ox0 + r;
+        *reinterpret_cast<uint32_t*>(s_a2 + prow * 128 + ((((lane >> 2) ^ (prow & 7)) << 4) | ((lane & 3) << 2))) =
+            pack_half2(silu_fast(acc[i][r].x), silu_fast(acc[i][r].y));
+      }
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();  // A2 complete; every warp is done reading T1
+    tc_fence_after_sync();
+    if (threadIdx.x == 0) {
+      mbar_wait(&bar_w2[cb & 1], (cb >> 1) & 1);
+      tc_fence_after_sync();
+      const uint64_t da = umma_smem_desc_sw128(smem_u32(s_a2));
+      const uint64_t db = umma_smem_desc_sw128(smem_u32(s_w2 + (cb & 1) * 8192));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) tc_mma_f16(tmem_base + acc2_col, da + 2 * k, db + 2 * k, p.idesc2, (cb | k) != 0 ? 1u : 0u);
+      tc_commit(bar_mma2);
+    }
+  }
+
+  // ---- final epilogue: acc2 row = tile pixel; warps 0-3 columns 0..31, warps 4-7 columns 32..63 ---------------------
+  mbar_wait(bar_mma2, (nblk - 1) & 1);
+  tc_fence_after_sync();
+  {
+    const int q = warp & 3, c = (warp >> 2) * 32;
+    const int prow = q * 32 + lane;
+    const int py = prow / kB2TX, px = prow - py * kB2TX;
+    const int gy = y0 + py, gx = x0 + px;
+    const bool ok = gy < p.H && gx < p.W;
+    uint32_t rr[32];
+    __syncwarp();
+    if (c < p.tile_n) {  // warp-uniform
+      tmem_ld_32x32b_x32(tmem_base + acc2_col + c + (static_cast<uint32_t>(q * 32) << 16), rr);
+      tmem_ld_wait();
+      if (ok) {
+        __half* orow = p.out + ((static_cast<size_t>(img) * p.H + gy) * p.W + gx) * p.out_ld + c;
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          pk[j] = pack_half2(silu_fast(__uint_as_float(rr[2 * j]) + s_b2[c + 2 * j]),
+                             silu_fast(__uint_as_float(rr[2 * j + 1]) + s_b2[c + 2 * j + 1]));
+#pragma unroll
+        for (int h16 = 0; h16 < 2; ++h16) {
+          const int cc = c + 16 * h16;
+          if (cc + 16 <= p.N) {
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(orow + 16 * h16), "r"(pk[8 * h16]),
+                         "r"(pk[8 * h16 + 1]), "r"(pk[8 * h16 + 2]), "r"(pk[8 * h16 + 3]), "r"(pk[8 * h16 + 4]),
+                         "r"(pk[8 * h16 + 5]), "r"(pk[8 * h16 + 6]), "r"(pk[8 * h16 + 7])
+                         : "memory");
+          } else if (cc + 8 <= p.N) {
+            *reinterpret_cast<uint4*>(orow + 16 * h16) = make_uint4(pk[8 * h16], pk[8 * h16 + 1], pk[8 * h16 + 2], pk[8 * h16 + 3]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
+static size_t bneck2_smem_bytes(int k) {
+  const size_t halo = static_cast<size_t>(kB2TX + k - 1) * (kB2TY + k - 1) * 128;
+  return 1024 + ((halo + 1023) / 1024) * 1024 + 16384 + 4 * 8192 + ((halo + 127) / 128) * 128 + 64 * 4 + 7 * 8 + 16;  // + 4 * mid_pad (biases)
+}
+
+template <int K>
+static int32_t launch_bneck2(BneckParams& p, int n, cudaStream_t st) {
+  const size_t smem = bneck2_smem_bytes(K) + static_cast<size_t>(p.mid_pad) * 4;
+  {
+    static SmemOptIn opt_in;
+    const int32_t rc = smem_opt_in(opt_in, bneck2_kernel<K>, 113 * 1024, "bottleneck(2-CTA shape)");
+    if (rc) return rc;
+  }
+  launch_pdl(bneck2_kernel<K>, dim3(p.tiles_x * p.tiles_y, n), dim3(kB2Threads), smem, st, p);
+  return check_launch("bottleneck kernel launch");
+}
+
 static size_t bneck_smem_bytes(int k, int mid_pad, int nblk, int tile_n) {
   const size_t halo = static_cast<size_t>(kBnTX + k - 1) * (kBnTY + k - 1) * 128;
   return 1024 + static_cast<size_t>(mid_pad) * 128 + static_cast<size_t>(nblk) * tile_n * 128 + halo + kBnA2Bytes + 2 * halo +
@@ -435,10 +711,22 @@ static int32_t launch_bneck(BneckParams& p, size_t smem, cudaStream_t st) {
 using namespace mafb200;
 
 // Can mafb200_bottleneck run this shape?  (pure host arithmetic; the engine asks before planning the fused op)
+// MAFB200_BNECK_SHAPE: 2 (default) = two CTAs per SM, every warp does every phase, weight panels streamed (any mid <= 512);
+// 1 = the persistent warp-specialised CTA per SM with resident panels (mid <= 192).
+static int bneck_shape() {
+  static const int shape = [] {
+    const char* e = getenv("MAFB200_BNECK_SHAPE");
+    return (e && e[0] == '1') ? 1 : 2;
+  }();
+  return shape;
+}
+
 extern "C" int32_t mafb200_bottleneck_supported(int32_t c_in, int32_t mid, int32_t c_out, int32_t k) {
-  if ((k != 3 && k != 5) || c_in < 8 || c_in > kBnMaxCin || c_in % 8 || mid < 8 || mid > kBnMaxMid || mid % 8 ||
+  const int max_mid = bneck_shape() == 1 ? kBnMaxMid : 512;
+  if ((k != 3 && k != 5) || c_in < 8 || c_in > kBnMaxCin || c_in % 8 || mid < 8 || mid > max_mid || mid % 8 ||
       c_out < 8 || c_out > 64 || c_out % 8)
     return 0;
+  if (bneck_shape() == 2) return 1;
   const int mid_pad = round_up(mid, kBnCB), tile_n = round_up(c_out, 16);
   return bneck_smem_bytes(k, mid_pad, mid_pad / kBnCB, tile_n) <= 227 * 1024 ? 1 : 0;
 }
@@ -478,8 +766,10 @@ extern "C" int32_t mafb200_bottleneck(const maf_tensor* src, int32_t mid, const 
   BneckParams p;
   memset(&p, 0, sizeof(p));
   const int mid_pad = round_up(mid, kBnCB), tile_n = round_up(dst->c, 16);
+  const int shape = bneck_shape();
+  const int tx = shape == 1 ? kBnTX : kB2TX, ty = shape == 1 ? kBnTY : kB2TY;
   {
-    const int TW = kBnTX + k - 1, TH = kBnTY + k - 1;
+    const int TW = tx + k - 1, TH = ty + k - 1;
     const cuuint64_t px = static_cast<cuuint64_t>(src->c_stride) * 2;
     cuuint64_t dims[4] = {static_cast<cuuint64_t>(src->c), static_cast<cuuint64_t>(src->w),
                           static_cast<cuuint64_t>(src->h), static_cast<cuuint64_t>(src->n)};
@@ -494,12 +784,17 @@ extern "C" int32_t mafb200_bottleneck(const maf_tensor* src, int32_t mid, const 
   {
     cuuint64_t dims[2] = {kBnCB, static_cast<cuuint64_t>(mid_pad)};
     cuuint64_t strides[1] = {kBnCB * 2};
-    cuuint32_t box[2] = {kBnCB, static_cast<cuuint32_t>(mid_pad)};
+    cuuint32_t box[2] = {kBnCB, static_cast<cuuint32_t>(mid_pad <= 256 ? mid_pad : 256)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&p.tm_w1, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(w1_packed), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(MAF_E_CUDA, "bottleneck: cuTensorMapEncodeTiled(W1) failed: %d", (int)r);
+    box[1] = kBnCB;  // one 64-channel block per load (2-CTA shape)
+    r = enc(&p.tm_w1b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(w1_packed), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(MAF_E_CUDA, "bottleneck: cuTensorMapEncodeTiled(W1 block) failed: %d", (int)r);
   }
   {
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(mid_pad), static_cast<cuuint64_t>(tile_n)};
@@ -523,15 +818,19 @@ extern "C" int32_t mafb200_bottleneck(const maf_tensor* src, int32_t mid, const 
   p.tile_n = tile_n;
   p.mid_pad = mid_pad;
   p.nblk = mid_pad / kBnCB;
-  p.tiles_x = ceil_div(src->w, kBnTX);
-  p.tiles_y = ceil_div(src->h, kBnTY);
+  p.tiles_x = ceil_div(src->w, tx);
+  p.tiles_y = ceil_div(src->h, ty);
   const long long tiles = static_cast<long long>(src->n) * p.tiles_x * p.tiles_y;
   if (tiles > 0x7fffffff) return fail(MAF_E_ARG, "bottleneck: too many tiles");
   p.tiles = static_cast<int32_t>(tiles);
   p.trace = g_bneck_trace;
   p.idesc1 = umma_idesc_f16(128, kBnCB);
   p.idesc2 = umma_idesc_f16(128, tile_n);
-  const size_t smem = bneck_smem_bytes(k, mid_pad, p.nblk, tile_n);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (shape == 2) {
+    if (src->n > 65535) return fail(MAF_E_ARG, "bottleneck: batch %d > 65535", src->n);
+    return k == 3 ? launch_bneck2<3>(p, src->n, st) : launch_bneck2<5>(p, src->n, st);
+  }
+  const size_t smem = bneck_smem_bytes(k, mid_pad, p.nblk, tile_n);
   return k == 3 ? launch_bneck<3>(p, smem, st) : launch_bneck<5>(p, smem, st);
 }

@@ -47,7 +47,7 @@ for name, c_, k, h, w in SHAPES:
     steps = n * ((h + 9) // 10) * ((w + 19) // 20) * ((mid + 63) // 64) / 148
     print(f"{name}: c_={c_} mid={mid} k={k} {h}x{w} bs{n}: fused {fused:.1f} us, two kernels {unfused:.1f} us; "
           f"{steps:.1f} steps/SM -> {fused * 1.9e3 / steps:.0f} clk/step (at 1.9 GHz)")
-    if name == "L20":
+    if name == "L20" and os.environ.get("MAFB200_BNECK_SHAPE") == "1":
         tr = torch.zeros(3 * 64 * 4, dtype=torch.int64, device=dev)
         _lib.check(_lib.lib().mafb200_bottleneck_trace(tr.data_ptr()))
         ops.bottleneck(src, packed, dst)
