@@ -130,16 +130,6 @@ MAFB200_API int32_t mafb200_stem_conv3x3s2(const void* x_nchw, int32_t x_dtype, 
 MAFB200_API int32_t mafb200_dwconv(const maf_tensor* src, const float* weight, const float* bias, int32_t k, int32_t act,
                        const maf_tensor* dst, void* stream);
 
-/* ---- the same depth-wise conv on the tensor cores (mma.sync, Toeplitz formulation; c % 8 == 0) ---------
- * The k*k fp32 weights of each channel are packed ON THE HOST (pure CPU, no GPU needed) into fp16 B
- * fragments: `table` = mafb200_dw_tc_table_bytes(c, k) bytes; weight fp32 [c][k][k] (PyTorch's [C,1,k,k]).
- * mafb200_dwconv_tc takes the table as DEVICE memory; dst must be 32-B aligned with c_stride % 16 == 0.
- * Replaces the same reference lines as mafb200_dwconv (common.py:2948-3100, 915-923, 1328-1334). */
-MAFB200_API size_t mafb200_dw_tc_table_bytes(int32_t c, int32_t k);
-MAFB200_API int32_t mafb200_dw_tc_pack(const float* weight_host, int32_t c, int32_t k, void* table_host);
-MAFB200_API int32_t mafb200_dwconv_tc(const maf_tensor* src, const void* table, const float* bias, int32_t k,
-                          int32_t act, const maf_tensor* dst, void* stream);
-
 /* ---- depth-wise k x k fused with the 1x1 conv that consumes it (k in 3,5; cout <= 128) -------------------
  * dst = act2(W2 * act1(DW_k(src) + dw_bias) + pw_bias): DepthBottleneckUni's conv2 -> SiLU -> one_conv
  * (common.py:915-926) and Head_DepthUni's cls_conv -> cls_conv_s / reg_conv -> reg_conv_s (common.py:1328-1336);

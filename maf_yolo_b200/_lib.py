@@ -58,10 +58,6 @@ _SIGNATURES = {
                                            C.c_void_p, C.c_int32, _P(MafTensor), C.c_void_p]),
     "mafb200_dwconv": (C.c_int32, [_P(MafTensor), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, _P(MafTensor),
                                    C.c_void_p]),
-    "mafb200_dw_tc_table_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
-    "mafb200_dw_tc_pack": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
-    "mafb200_dwconv_tc": (C.c_int32, [_P(MafTensor), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, _P(MafTensor),
-                                      C.c_void_p]),
     "mafb200_dwconv_conv1x1": (C.c_int32, [_P(MafTensor), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                            C.c_void_p, C.c_int32, _P(MafTensor), C.c_void_p]),
     "mafb200_bottleneck_supported": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),

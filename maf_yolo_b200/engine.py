@@ -72,7 +72,6 @@ class _Op:
     weight3: Optional[str] = None             # fused bottleneck ("bneck"): weight = expand 1x1, weight3 = depth-wise, weight2 = project 1x1
     act2: str = "none"
     wslice: Optional[Tuple[int, int]] = None  # channel range of the folded weight this op uses (split depth-wise convs)
-    impl: str = ""                            # "" = default kernel, "tc" = tensor-core depth-wise kernel
     level: int = -1                           # head_pred: pyramid level; anchor_off = first anchor of the level
     anchor_off: int = 0
     # dependencies through memory outside the arena (pred / boxes / NMS workspace), by name
@@ -153,22 +152,7 @@ class Plan:
         return op
 
     def _emit_dw(self, name: str, src: _View, dst: _View, weight: str, act: str, k: int):
-        """One depth-wise conv, or — experiment knob MAFB200_DW_SPLIT=<fraction>, default off — two launches over
-        disjoint channel ranges: the first on the FFMA kernel (FMA pipe 60 % busy, LSU 18 %), the rest on the
-        tensor-core kernel (LSU 85 %, FMA 8 %; profiles/r01_ncu_full_summaries.md), on different streams of the
-        captured graph so that the complementary pipes overlap.  Measured: 17.15k images/s at 0.34 / 0.5 / 0.67
-        against 17.96k unsplit — the two grids mostly run one after the other and 16 launches are added."""
-        c = src.c
-        frac = float(os.environ.get("MAFB200_DW_SPLIT", "0"))
-        c_tc = int(c * frac) // 32 * 32 if frac > 0 else 0
-        if c_tc <= 0 or c - c_tc < 32 or (c - c_tc) % 16 != 0 or dst.buf.ld % 16 != 0 or (dst.c_off + c - c_tc) % 16 != 0:
-            self._emit("dwconv", name, [src], [dst], weight=weight, act=act, k=k)
-            return
-        c_a = c - c_tc
-        self._emit("dwconv", name + ".ffma", [src.slice(0, c_a)], [dst.slice(0, c_a)], weight=weight, act=act, k=k,
-                   wslice=(0, c_a))
-        self._emit("dwconv", name + ".tc", [src.slice(c_a, c_tc)], [dst.slice(c_a, c_tc)], weight=weight, act=act, k=k,
-                   wslice=(c_a, c), impl="tc")
+        self._emit("dwconv", name, [src], [dst], weight=weight, act=act, k=k)
 
     @staticmethod
     def _dwpw_ok(c: int, cout: int, k: int) -> bool:
@@ -510,11 +494,6 @@ class Engine:
             wt, bs = folded[op.weight]
             if op.wslice is not None:
                 wt, bs = wt[op.wslice[0]:op.wslice[1]], bs[op.wslice[0]:op.wslice[1]]
-            use_tc = op.impl == "tc" or os.environ.get("MAFB200_DW_TC", "0") != "0"
-            if use_tc and reads[0].c % 8 == 0 and writes[0].ld % 16 == 0 and writes[0].c_off % 16 == 0:
-                w, b = ops.pack_dw_tc(wt, bs, device=dev)  # tensor-core (Toeplitz HMMA) kernel
-                self._weights[op.name] = (w, b)
-                return lambda: ops.dwconv_tc(reads[0], w, b, op.k, op.act, writes[0])
             w, b = ops.pack_dw(wt, bs, device=dev)
             self._weights[op.name] = (w, b)
             return lambda: ops.dwconv(reads[0], w, b, op.k, op.act, writes[0])

@@ -140,20 +140,6 @@ def pack_dw(weight: torch.Tensor, bias: torch.Tensor, device="cuda"):
             bias.to(torch.float32).contiguous().to(device))
 
 
-def pack_dw_tc(weight: torch.Tensor, bias: torch.Tensor, device="cuda"):
-    """weight [C, 1, k, k] -> (uint8 table of Toeplitz B fragments for mafb200_dwconv_tc, fp32 bias [C]).
-    The packing itself is the library's host-side mafb200_dw_tc_pack (pure CPU)."""
-    c, one, k, k2 = weight.shape
-    assert one == 1 and k == k2
-    w = weight.reshape(c, k, k).to(torch.float32).contiguous().cpu()
-    nbytes = int(lib().mafb200_dw_tc_table_bytes(c, k))
-    if nbytes == 0:
-        raise ValueError(f"dw_tc: unsupported (c={c}, k={k})")
-    table = torch.empty(nbytes, dtype=torch.uint8)
-    check(lib().mafb200_dw_tc_pack(w.data_ptr(), c, k, table.data_ptr()))
-    return table.to(device), bias.to(torch.float32).contiguous().to(device)
-
-
 def bottleneck_supported(c_in: int, mid: int, c_out: int, k: int) -> bool:
     return bool(lib().mafb200_bottleneck_supported(c_in, mid, c_out, k))
 
@@ -257,10 +243,6 @@ def stem_conv3x3s2(x_nchw: torch.Tensor, weight: torch.Tensor, bias: torch.Tenso
 
 def dwconv(src: NHWC, weight: torch.Tensor, bias: torch.Tensor, k: int, act, dst: NHWC) -> None:
     check(lib().mafb200_dwconv(src.ref(), weight.data_ptr(), bias.data_ptr(), k, _act(act), dst.ref(), _stream()))
-
-
-def dwconv_tc(src: NHWC, table: torch.Tensor, bias: torch.Tensor, k: int, act, dst: NHWC) -> None:
-    check(lib().mafb200_dwconv_tc(src.ref(), table.data_ptr(), bias.data_ptr(), k, _act(act), dst.ref(), _stream()))
 
 
 def dwconv_conv1x1(src: NHWC, dw_w: torch.Tensor, dw_b: torch.Tensor, k: int, act1, pw_w: torch.Tensor,

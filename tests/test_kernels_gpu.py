@@ -200,32 +200,6 @@ def test_dwconv(cuda_device, c, k, h, w, n, act):
     _close(dst.to_nchw(), ref, f"dwconv c={c} k={k}")
 
 
-DW_TC_CASES = DW_CASES + [(72, 3, 160, 160, 1, "silu"), (40, 5, 33, 47, 2, "silu"), (8, 9, 16, 16, 1, "none"),
-                          (192, 5, 80, 80, 2, "silu"), (32, 7, 5, 3, 1, "silu")]
-
-
-@pytest.mark.parametrize("c,k,h,w,n,act", DW_TC_CASES)
-def test_dwconv_tc(cuda_device, c, k, h, w, n, act):
-    """Tensor-core (Toeplitz HMMA) depth-wise kernel: fp16 inputs AND fp16 weights, fp32 accumulate."""
-    from maf_yolo_b200 import ops
-
-    g = torch.Generator().manual_seed(77 + c + k)
-    x = torch.randn(n, c, h, w, generator=g).half().float()
-    wgt = (torch.randn(c, 1, k, k, generator=g) / k).half().float()
-    bias = torch.randn(c, generator=g)
-    ref = _act_ref(F.conv2d(x, wgt, bias, padding=k // 2, groups=c), act)
-    wide = ops.NHWC.from_nchw(torch.cat([torch.zeros(n, 8, h, w), x], 1).to(cuda_device))
-    src = wide.slice(8, c)
-    tab, bp = ops.pack_dw_tc(wgt, bias, cuda_device)
-    dst = ops.NHWC.empty(n, h, w, c, cuda_device, ld=(c + 15) // 16 * 16)
-    dst.buf.fill_(7.0)  # padding channels must stay untouched
-    ops.dwconv_tc(src, tab, bp, k, act, dst)
-    torch.cuda.synchronize()
-    _close(dst.to_nchw(), ref, f"dwconv_tc c={c} k={k}")
-    if dst.ld > c:
-        assert (dst.buf[..., c:] == 7.0).all(), "dwconv_tc wrote outside its channels"
-
-
 @pytest.mark.parametrize("c,cout,k,h,w,n,act1,act2", [(192, 64, 5, 40, 40, 2, "silu", "silu"), (128, 128, 5, 24, 30, 1, "none", "silu"),
                                                       (72, 24, 3, 40, 40, 1, "silu", "silu"), (64, 32, 3, 7, 9, 2, "relu", "none"),
                                                       (144, 48, 5, 20, 20, 2, "silu", "silu"), (192, 64, 5, 80, 80, 1, "silu", "silu"),
