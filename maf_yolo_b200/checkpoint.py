@@ -193,3 +193,80 @@ def from_checkpoint(weights, variant_or_yaml=None, nc=None, bn_eps: float = 1e-3
     if meta.get("names") is not None and "names" not in kw:
         kw["names"] = meta["names"]
     return from_state_dict(sd, topo, ncls, bn_eps, **kw)
+
+
+# ------------------------------------------------------------------------------------------------
+# export (second half): folded weights back to the reference / to a packed file
+# ------------------------------------------------------------------------------------------------
+def export_deploy_state_dict(graph, folded, dtype=torch.float32) -> "OrderedDict[str, torch.Tensor]":
+    """The folded (weight, bias) pairs as a DEPLOY-form `state_dict` under the reference's own keys — what its model
+    holds after `fuse_model` + `switch_to_deploy` + `reparameterize` (yolov6/core/evaler.py:93-109): `rbr_reparam.*` for
+    RepVGGBlocks, `conv.weight` / `conv.bias` for every fused `Conv`, `dwconv.lk_origin.*` for the merged depth-wise
+    kernels, `cls_pred` / `reg_pred`, and the DFL projection.  It loads into a reference deploy model with
+    `load_state_dict(strict=True)` and into this package again (`from_state_dict` detects the form by key presence)."""
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+
+    def put(prefix, key, names=("weight", "bias")):
+        w, b = folded[key]
+        sd[f"{prefix}.{names[0]}"] = w.to(dtype).contiguous()
+        sd[f"{prefix}.{names[1]}"] = b.to(dtype).contiguous()
+
+    for l in graph.layers:
+        p, i = f"backbone.{l.i}", str(l.i)
+        if l.kind == "repvgg":
+            put(p + ".rbr_reparam", i)
+        elif l.kind == "rephdw":
+            put(p + ".conv1.conv", i + ".conv1")
+            for j in range(l.depth):
+                put(f"{p}.m.{j}.conv1.conv", f"{i}.m.{j}.conv1")
+                put(f"{p}.m.{j}.conv2.dwconv.lk_origin", f"{i}.m.{j}.dw")
+                put(f"{p}.m.{j}.one_conv.conv", f"{i}.m.{j}.one_conv")
+            put(p + ".conv2.conv", i + ".conv2")
+        elif l.kind == "mprep":
+            put(p + ".conv1.conv", i + ".conv1")
+            put(p + ".conv2.rbr_reparam", i + ".conv2")
+        elif l.kind == "sppf":
+            put(p + ".cv1.conv", i + ".cv1")
+            put(p + ".cv2.conv", i + ".cv2")
+        elif l.kind == "convw":
+            put(p + ".block.conv", i + ".block")
+        elif l.kind == "head":
+            put(p + ".stem.conv", i + ".stem")
+            for br in ("cls", "reg"):
+                put(f"{p}.{br}_conv.dwconv.lk_origin", f"{i}.{br}_dw")
+                put(f"{p}.{br}_conv_s.conv", f"{i}.{br}_s")
+                put(f"{p}.{br}_pred", f"{i}.{br}_pred")
+    reg_max = graph.layers[graph.head_layers[0]].reg_max
+    sd["detect.proj"] = torch.linspace(0, reg_max, reg_max + 1).to(dtype)
+    sd["detect.proj_conv.weight"] = sd["detect.proj"].view(1, reg_max + 1, 1, 1).clone()
+    return sd
+
+
+def save_packed(path, variant_or_yaml, folded, names=None, nc: int = 80, dtype=torch.float16) -> None:
+    """Packed weight file: the folded deploy-form tensors (fp16 by default — released checkpoints carry fp16 precision,
+    yolov6/utils/checkpoint.py:119) keyed as `fold_state_dict` keys them + the topology.  Plain tensors / containers
+    only: `load_packed` reads it with `torch.load(weights_only=True)`."""
+    from .topology import variant_rows
+
+    rows = variant_rows(variant_or_yaml) if isinstance(variant_or_yaml, str) and variant_or_yaml in ("n", "s", "m") else variant_or_yaml
+    blob = {"format": "mafb200-packed-1", "yaml": rows, "nc": int(nc), "names": list(names) if names is not None else None,
+            "weights": {k: (w.to(dtype).contiguous(), b.to(torch.float32).contiguous()) for k, (w, b) in folded.items()}}
+    torch.save(blob, path)
+
+
+def load_packed(path):
+    """-> (folded, yaml rows, nc, names) of a `save_packed` file."""
+    blob = torch.load(path, map_location="cpu", weights_only=True)
+    if not isinstance(blob, dict) or blob.get("format") != "mafb200-packed-1":
+        raise TypeError(f"{path}: not a mafb200 packed weight file")
+    folded = {k: (w.to(torch.float64), b.to(torch.float64)) for k, (w, b) in blob["weights"].items()}
+    return folded, blob["yaml"], blob["nc"], blob["names"]
+
+
+def from_packed(path, **kw):
+    """Packed weight file -> B200DetectModel (no folding at load time)."""
+    from .nn import B200DetectModel
+    from .topology import build_graph
+
+    folded, rows, nc, names = load_packed(path)
+    return B200DetectModel(build_graph(rows, nc), folded, names=names, **kw)

@@ -169,3 +169,50 @@ def test_allow_list_is_explicit():
     assert up.find_class("torch", "float16") is torch.float16
     assert up.find_class("collections", "OrderedDict") is __import__("collections").OrderedDict
     assert up.find_class("torch._utils", "_rebuild_tensor_v2") is torch._utils._rebuild_tensor_v2
+
+
+def test_export_deploy_state_dict_round_trip(tmp_path):
+    """SURVEY 8 f4, second half: folded weights -> deploy-form state_dict under the reference's keys -> folded again
+    (bit-identical in fp64), and the packed weight file round trip (loaded with weights_only=True)."""
+    from maf_yolo_b200 import fold, synth, topology
+
+    for variant in ("n", "m"):
+        g = topology.build_graph(variant)
+        folded = fold.fold_state_dict(g, synth.random_state_dict(g, seed=2))
+        sd = ck.export_deploy_state_dict(g, folded, dtype=torch.float64)
+        assert "backbone.0.rbr_reparam.weight" in sd and "backbone.2.m.0.conv2.dwconv.lk_origin.bias" in sd
+        assert not any(".bn." in k or "origin_bn" in k or ".norm." in k for k in sd)
+        again = fold.fold_state_dict(g, sd)
+        assert again.keys() == folded.keys()
+        assert all(torch.equal(again[k][0], folded[k][0]) and torch.equal(again[k][1], folded[k][1]) for k in folded)
+    path = tmp_path / "n.mafb200"
+    ck.save_packed(path, "n", folded if variant == "n" else fold.fold_state_dict(topology.build_graph("n"), synth.random_state_dict(topology.build_graph("n"), seed=2)),
+                   names=[f"c{i}" for i in range(80)])
+    f2, rows, nc, names = ck.load_packed(path)
+    assert nc == 80 and names[3] == "c3" and rows["backbone"][0][2] == "RepVGGBlock"
+    gn = topology.build_graph(rows, nc)
+    assert [l.kind for l in gn.layers] == [l.kind for l in topology.build_graph("n").layers]
+    ref = fold.fold_state_dict(gn, synth.random_state_dict(gn, seed=2))
+    assert all(torch.equal(f2[k][0], ref[k][0].half().double()) and torch.equal(f2[k][1], ref[k][1].float().double()) for k in ref)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present")
+def test_exported_state_dict_loads_into_the_reference_deploy_model():
+    """The exported state_dict loads strictly into the reference's own deploy-form model, whose forward then equals
+    the train-form forward of the original weights (the reference does the same folding in fp32)."""
+    from maf_yolo_b200 import fold, synth, topology
+
+    g = topology.build_graph("n")
+    sd_train = synth.random_state_dict(g, seed=4)
+    m = ref_loader.build_model("n")
+    m.load_state_dict(sd_train, strict=True)
+    x = torch.rand(1, 3, 320, 320, generator=torch.Generator().manual_seed(9))
+    with torch.no_grad():
+        want = m(x)[0]
+    dep = ref_loader.to_deploy(ref_loader.build_model("n"))
+    exported = ck.export_deploy_state_dict(g, fold.fold_state_dict(g, sd_train))
+    missing = dep.load_state_dict(exported, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    with torch.no_grad():
+        got = dep(x)[0]
+    assert (got[..., :4] - want[..., :4]).abs().max() < 2e-3 and (got[..., 5:] - want[..., 5:]).abs().max() < 1e-5
