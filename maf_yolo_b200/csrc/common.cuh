@@ -9,7 +9,19 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 namespace mafb200 {
+
+// Compile-time loop: f(std::integral_constant<int, I>) for I in [I0, N).  Used where `#pragma unroll` gives up on a
+// large body (depth-wise k = 7 / 9 taps) and the trip index must be a constant expression.
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, N>(static_cast<F&&>(f));
+  }
+}
 
 // ----------------------------------------------------------------------------------------------
 // Activation codes shared by the C ABI (include/mafb200.h) and every epilogue.

@@ -29,13 +29,36 @@
 
 namespace mafb200 {
 
+// k = 9 at 4 CTAs/SM (128 registers) spills ~80 values; at 3 CTAs/SM ptxas keeps 152 registers and caches weight rows
+// across the (d, i) pairs (251 instead of 587 LDS per unit).  A/B knob for the measurement.
+#ifndef MAFB200_DW9_MINB
+#define MAFB200_DW9_MINB 3
+#endif
+
 constexpr int kDwR = 5;     // output columns per thread
 constexpr int kDwTY = 5;    // output rows per thread
 constexpr int kDwTXB = 20;  // output tile per CTA
 constexpr int kDwTYB = 10;
 
+template <int ACT>
+__device__ __forceinline__ void dw_store_unit(const float2 (&acc)[kDwTY][kDwR], __half* obase, int row_ld, int out_ld,
+                                              int ny, int nx) {
+#pragma unroll
+  for (int i = 0; i < kDwTY; ++i) {
+    if (i < ny) {
+      __half* orow = obase + i * row_ld;
+#pragma unroll
+      for (int r = 0; r < kDwR; ++r) {
+        if (r < nx)
+          *reinterpret_cast<__half2*>(orow + r * out_ld) =
+              __floats2half2_rn(apply_act_fast(acc[i][r].x, ACT), apply_act_fast(acc[i][r].y, ACT));
+      }
+    }
+  }
+}
+
 template <int K, int CB, bool kTma>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, (CB == 32 && K == 7) ? 4 : (CB == 32 && K == 9) ? MAFB200_DW9_MINB : 1)
     dwconv_kernel(const __grid_constant__ CUtensorMap tm_in, const __half* __restrict__ in, int in_ld,
                   __half* __restrict__ out, int out_ld, const float* __restrict__ wgt,
                   const float* __restrict__ bias, int H, int W, int C, int act, int tiles_x) {
@@ -163,45 +186,43 @@ __global__ void __launch_bounds__(128)
 #pragma unroll
       for (int r = 0; r < kDwR; ++r) acc[i][r] = bv;
 
-#pragma unroll
-    for (int d = 0; d < kDwTY + K - 1; ++d) {
+    // The (input row d, output row i) nest is expanded by template recursion: `#pragma unroll` left the k = 7 / 9
+    // bodies (1225 / 2025 FFMA2) ROLLED over d, with the `ky` range tests, the weight addresses and the window
+    // addresses evaluated at run time — 62 % of the executed instructions were not taps (ncu prof33).
+    static_for<0, kDwTY + K - 1>([&](auto dc) {
+      constexpr int d = decltype(dc)::value;
       float2 win[kDwR + K - 1];
 #pragma unroll
       for (int j = 0; j < kDwR + K - 1; ++j)
         win[j] = __half22float2(*reinterpret_cast<const __half2*>(ibase + (d * TW + j) * CB));
+      static_for<0, kDwTY>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        constexpr int ky = d - i;
+        if constexpr (ky >= 0 && ky < K) {
+          float2 wv[K];
 #pragma unroll
-      for (int i = 0; i < kDwTY; ++i) {
-        const int ky = d - i;  // compile-time after unrolling
-        if (ky < 0 || ky >= K) continue;
-        float2 wv[K];
+          for (int kx = 0; kx < K; ++kx)
+            wv[kx] = kRegW ? wreg[ky * K + kx] : *reinterpret_cast<const float2*>(wbase + (ky * K + kx) * CB);
 #pragma unroll
-        for (int kx = 0; kx < K; ++kx)
-          wv[kx] = kRegW ? wreg[ky * K + kx] : *reinterpret_cast<const float2*>(wbase + (ky * K + kx) * CB);
+          for (int r = 0; r < kDwR; ++r) {
 #pragma unroll
-        for (int r = 0; r < kDwR; ++r) {
-#pragma unroll
-          for (int kx = 0; kx < K; ++kx) {
-            acc[i][r] = ffma2(win[r + kx], wv[kx], acc[i][r]);
+            for (int kx = 0; kx < K; ++kx) acc[i][r] = ffma2(win[r + kx], wv[kx], acc[i][r]);
           }
         }
-      }
-    }
+      });
+    });
 
     if (ch_ok) {
-      __half* obase = out + (static_cast<size_t>(img) * H * W) * out_ld + c0 + 2 * pair;
-#pragma unroll
-      for (int i = 0; i < kDwTY; ++i) {
-        const int y = y0 + oy0 + i;
-        if (y >= H) continue;
-#pragma unroll
-        for (int r = 0; r < kDwR; ++r) {
-          const int x = x0 + ox0 + r;
-          if (x >= W) continue;
-          const float a = apply_act_fast(acc[i][r].x, act);
-          const float c = apply_act_fast(acc[i][r].y, act);
-          *reinterpret_cast<__half2*>(obase + (static_cast<size_t>(y) * W + x) * out_ld) = __floats2half2_rn(a, c);
-        }
-      }
+      // one 64-bit base per unit, then (row, column) offsets that are small multiples of two run-time strides
+      __half* obase = out + ((static_cast<size_t>(img) * H + (y0 + oy0)) * W + (x0 + ox0)) * out_ld + c0 + 2 * pair;
+      const int row_ld = W * out_ld;
+      const int ny = H - (y0 + oy0), nx = W - (x0 + ox0);  // rows / columns of this unit inside the image
+      if (act == ACT_SILU)
+        dw_store_unit<ACT_SILU>(acc, obase, row_ld, out_ld, ny, nx);
+      else if (act == ACT_RELU)
+        dw_store_unit<ACT_RELU>(acc, obase, row_ld, out_ld, ny, nx);
+      else
+        dw_store_unit<ACT_NONE>(acc, obase, row_ld, out_ld, ny, nx);
     }
   }
 }

@@ -25,10 +25,26 @@
 
 namespace mafb200 {
 
-constexpr int kFwTX = 20, kFwTY = 10;   // output tile
 constexpr int kFwCB = 64;               // channels per block = one 128-byte swizzle row
-constexpr int kFwThreads = 256;
-constexpr int kFwRows = 256;            // A tile rows (2 M tiles); 200 used
+
+// Tile shapes: a CTA is (TX/5) x (TY/5) warps, each one 5 x 5 pixel unit.  10 x 20 = 8 warps, 2 M tiles (round 1);
+// 10 x 10 = 4 warps, 1 M tile (round 2): half the work per CTA and twice the CTAs per SM, i.e. FOUR instead of two
+// independently progressing agents per SM for the same 16 warps.  The kernel alternates an FMA-pipe phase (taps) with
+// phases that leave the pipe idle (A-tile write, MMA wait, epilogue, start-up), all CTA-wide in lock step, so the pipe
+// is only busy while at least one resident CTA is in its taps: ablation builds (tools/bench_dwpw.py,
+// profiles/r02_j_dwpw_ablation.md) showed the halo TMA and the weight loads off the critical path, the taps ~50 % of the
+// run time and the FMA pipe 54 % busy (ncu).
+template <int TX, int TY>
+struct FwTile {
+  static constexpr int kWarps = (TX / 5) * (TY / 5);
+  static constexpr int kThreads = kWarps * 32;
+  static constexpr int kPixels = TX * TY;
+  static constexpr int kMTiles = (kPixels + 127) / 128;
+  // A tile: one 128-byte row per pixel.  The MMA reads whole 128-row M tiles; rows >= kPixels alias whatever follows the
+  // A tile in shared memory (their accumulator rows are never read).
+  static constexpr uint32_t kABytes = kMTiles == 2 ? 256 * 128 : ((kPixels * 128 + 1023) / 1024) * 1024;
+  static_assert(TX % 5 == 0 && TY % 5 == 0 && kWarps == 4 * kMTiles, "one epilogue warp per 32 accumulator rows");
+};
 
 struct DwPwParams {
   CUtensorMap tm_in;   // x as {C, W, H, N}, box {64, TW, TH, 1}, no swizzle
@@ -44,16 +60,18 @@ struct DwPwParams {
   uint32_t idesc;
 };
 
-template <int K, int kCtas>
-__global__ void __launch_bounds__(kFwThreads, kCtas) dwpw_kernel(const __grid_constant__ DwPwParams p) {
+template <int K, int kCtas, int kFwTX, int kFwTY>
+__global__ void __launch_bounds__(FwTile<kFwTX, kFwTY>::kThreads, kCtas) dwpw_kernel(const __grid_constant__ DwPwParams p) {
+  using Tile = FwTile<kFwTX, kFwTY>;
+  constexpr int kFwThreads = Tile::kThreads;
   constexpr int P = K / 2;
   constexpr int TW = kFwTX + K - 1, TH = kFwTY + K - 1;
   constexpr uint32_t kHaloBytes = TH * TW * kFwCB * 2;
-  constexpr uint32_t kABytes = kFwRows * 128;  // 32 KB
+  constexpr uint32_t kABytes = Tile::kABytes;
 
   extern __shared__ uint8_t smem_fw_raw[];
   uint8_t* smem = smem_fw_raw + ((1024u - (smem_u32(smem_fw_raw) & 1023u)) & 1023u);
-  uint8_t* s_a = smem;                                    // [256 rows][128 B], SWIZZLE_128B K-major
+  uint8_t* s_a = smem;                                    // [rows][128 B], SWIZZLE_128B K-major
   uint8_t* s_w = s_a + kABytes;                           // W2: two slots of one k block [tile_n rows][128 B]
   const int kblocks = (p.C + kFwCB - 1) / kFwCB;
   const int b_bytes = p.tile_n * 128;
@@ -95,7 +113,7 @@ __global__ void __launch_bounds__(kFwThreads, kCtas) dwpw_kernel(const __grid_co
   }
 
   // this warp's 5 x 5 unit of the tile; lane = channel pair of the block
-  const int uy = warp >> 2, ux = warp & 3;  // 2 x 4 units
+  const int uy = warp / (kFwTX / 5), ux = warp % (kFwTX / 5);
   const int oy0 = uy * 5, ox0 = ux * 5;
   const __half* ibase = s_in + (oy0 * TW + ox0) * kFwCB + 2 * lane;
 
@@ -160,7 +178,7 @@ __global__ void __launch_bounds__(kFwThreads, kCtas) dwpw_kernel(const __grid_co
     if (threadIdx.x == 0) {
       const uint64_t db = umma_smem_desc_sw128(smem_u32(s_w + (cb & 1) * b_bytes));  // landed with this block's halo tile
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
+      for (int mt = 0; mt < Tile::kMTiles; ++mt) {
         const uint64_t da = umma_smem_desc_sw128(smem_u32(s_a + mt * 16384));
 #pragma unroll
         for (int k = 0; k < 4; ++k)
@@ -170,7 +188,7 @@ __global__ void __launch_bounds__(kFwThreads, kCtas) dwpw_kernel(const __grid_co
     }
   }
 
-  // ---- epilogue: accumulator row = tile pixel; warps 0-3 -> rows 0..127, warps 4-7 -> rows 128..255 ----------------
+  // ---- epilogue: accumulator row = tile pixel; warps 0-3 -> rows 0..127, warps 4-7 (if any) -> rows 128..255 ------
   mbar_wait(bar_mma, (kblocks - 1) & 1);
   tc_fence_after_sync();
   {
@@ -208,35 +226,86 @@ __global__ void __launch_bounds__(kFwThreads, kCtas) dwpw_kernel(const __grid_co
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
-template <int K, int kCtas>
+template <int K, int kCtas, int TX, int TY>
 static int32_t launch_dwpw_as(DwPwParams& p, int n, int tiles, size_t smem, cudaStream_t st) {
   {
     static SmemOptIn opt_in;  // per device (a process-wide flag skipped the opt-in on a second GPU)
-    const int32_t rc_attr = smem_opt_in(opt_in, dwpw_kernel<K, kCtas>, 113 * 1024, "dwpw");
+    const int32_t rc_attr = smem_opt_in(opt_in, dwpw_kernel<K, kCtas, TX, TY>, 113 * 1024, "dwpw");
     if (rc_attr) return rc_attr;
   }
-  launch_pdl(dwpw_kernel<K, kCtas>, dim3(tiles, n), dim3(kFwThreads), smem, st, p);
+  launch_pdl(dwpw_kernel<K, kCtas, TX, TY>, dim3(tiles, n), dim3(FwTile<TX, TY>::kThreads), smem, st, p);
   return check_launch("dwpw kernel launch");
 }
 
-template <int K>
-static int32_t launch_dwpw(DwPwParams& p, int n, int tiles, cudaStream_t st) {
-  constexpr int TW = kFwTX + K - 1, TH = kFwTY + K - 1;
-  const size_t smem = 1024 + static_cast<size_t>(kFwRows) * 128 + static_cast<size_t>(2) * p.tile_n * 128 +
-                      ((static_cast<size_t>(TH) * TW * kFwCB * 2 + 127) / 128) * 128 + 64 + static_cast<size_t>(p.tile_n) * 4;
-  if (smem > 113 * 1024) return fail(MAF_E_ARG, "dwpw: %zu B of shared memory needed (C=%d N=%d)", smem, p.C, p.N);
-  if constexpr (K == 3) {
-    // k = 3 needs 18 weight + 14 window registers beside the 50 accumulators: it fits 80 registers (4 bytes of spill),
-    // and with cout <= 32 three CTAs fit the SM's shared memory and TMEM -> 24 instead of 16 warps to cover the TMA /
-    // barrier / epilogue gaps of its short tap loop.  Measured: dwpw family 459 -> 449 us, 19.7k -> 19.9k images/s,
-    // latency 1.948 -> 1.937 ms.  MAFB200_DWPW_3CTA=0 selects the 2-CTA build.
-    static const bool three = [] {
-      const char* e = getenv("MAFB200_DWPW_3CTA");
-      return !(e && e[0] == '0');
-    }();
-    if (three && 3 * (smem + 1024) <= 228 * 1024 && 3 * p.tmem_cols <= 512) return launch_dwpw_as<K, 3>(p, n, tiles, smem, st);
+// Shared memory of one CTA: alignment slack + A tile + two W2 slots + halo tile + barriers + bias.
+template <int K, int TX, int TY>
+static size_t dwpw_smem(int tile_n) {
+  constexpr int TW = TX + K - 1, TH = TY + K - 1;
+  return 1024 + FwTile<TX, TY>::kABytes + static_cast<size_t>(2) * tile_n * 128 +
+         ((static_cast<size_t>(TH) * TW * kFwCB * 2 + 127) / 128) * 128 + 64 + static_cast<size_t>(tile_n) * 4;
+}
+
+static int dwpw_tmem_cols(int m_tiles, int tile_n) {
+  int cols = 32;
+  while (cols < m_tiles * tile_n) cols <<= 1;
+  return cols;
+}
+
+// 0: 10 x 20 tiles, 256 threads (round 1).  1 (default): 10 x 10 tiles, 128 threads, twice the CTAs per SM.
+static int dwpw_small_tiles() {
+  static const int v = [] {
+    const char* e = getenv("MAFB200_DWPW_SMALL");
+    return (e && e[0] == '0') ? 0 : 1;
+  }();
+  return v;
+}
+
+template <int K, int TX, int TY>
+static int32_t launch_dwpw(DwPwParams& p, const maf_tensor* src, cudaStream_t st) {
+  using Tile = FwTile<TX, TY>;
+  EncodeTiledFn enc = encode_tiled_fn();
+  {
+    constexpr int TW = TX + K - 1, TH = TY + K - 1;
+    const cuuint64_t px = static_cast<cuuint64_t>(src->c_stride) * 2;
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(src->c), static_cast<cuuint64_t>(src->w),
+                          static_cast<cuuint64_t>(src->h), static_cast<cuuint64_t>(src->n)};
+    cuuint64_t strides[3] = {px, px * src->w, px * src->w * src->h};
+    cuuint32_t box[4] = {kFwCB, static_cast<cuuint32_t>(TW), static_cast<cuuint32_t>(TH), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&p.tm_in, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, src->ptr, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(MAF_E_CUDA, "dwconv_conv1x1: cuTensorMapEncodeTiled(src) failed: %d", (int)r);
   }
-  return launch_dwpw_as<K, 2>(p, n, tiles, smem, st);
+  p.tiles_x = ceil_div(src->w, TX);
+  p.tmem_cols = dwpw_tmem_cols(Tile::kMTiles, p.tile_n);
+  const int tiles = p.tiles_x * ceil_div(src->h, TY);
+  const size_t smem = dwpw_smem<K, TX, TY>(p.tile_n);
+  if (smem > 113 * 1024) return fail(MAF_E_ARG, "dwpw: %zu B of shared memory needed (C=%d N=%d)", smem, p.C, p.N);
+  // resident CTAs per SM: shared memory (228 KB, 1 KB reserved per CTA), TMEM columns (512), registers (launch bounds)
+  const int by_smem = static_cast<int>((228 * 1024) / (smem + 1024)), by_tmem = 512 / p.tmem_cols;
+  const int fit = by_smem < by_tmem ? by_smem : by_tmem;
+  const int n = src->n;
+  if constexpr (Tile::kThreads == 128) {
+    // k = 5: 124 registers -> 4 CTAs of 128 threads; k = 3: 96 registers -> 5 CTAs
+    if constexpr (K == 3) {
+      if (fit >= 5) return launch_dwpw_as<K, 5, TX, TY>(p, n, tiles, smem, st);
+    }
+    if (fit >= 4) return launch_dwpw_as<K, 4, TX, TY>(p, n, tiles, smem, st);
+    return launch_dwpw_as<K, 2, TX, TY>(p, n, tiles, smem, st);
+  } else {
+    if constexpr (K == 3) {
+      // k = 3 needs 18 weight + 14 window registers beside the 50 accumulators: it fits 80 registers, and with
+      // cout <= 32 three CTAs fit the SM's shared memory and TMEM -> 24 instead of 16 warps to cover the gaps of its
+      // short tap loop (round 1: dwpw family 459 -> 449 us).  MAFB200_DWPW_3CTA=0 selects the 2-CTA build.
+      static const bool three = [] {
+        const char* e = getenv("MAFB200_DWPW_3CTA");
+        return !(e && e[0] == '0');
+      }();
+      if (three && fit >= 3) return launch_dwpw_as<K, 3, TX, TY>(p, n, tiles, smem, st);
+    }
+    return launch_dwpw_as<K, 2, TX, TY>(p, n, tiles, smem, st);
+  }
 }
 
 }  // namespace mafb200
@@ -274,19 +343,6 @@ extern "C" int32_t mafb200_dwconv_conv1x1(const maf_tensor* src, const float* dw
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return fail(MAF_E_ARCH, "cuTensorMapEncodeTiled entry point not available");
   {
-    const int TW = kFwTX + k - 1, TH = kFwTY + k - 1;
-    const cuuint64_t px = static_cast<cuuint64_t>(src->c_stride) * 2;
-    cuuint64_t dims[4] = {static_cast<cuuint64_t>(src->c), static_cast<cuuint64_t>(src->w),
-                          static_cast<cuuint64_t>(src->h), static_cast<cuuint64_t>(src->n)};
-    cuuint64_t strides[3] = {px, px * src->w, px * src->w * src->h};
-    cuuint32_t box[4] = {kFwCB, static_cast<cuuint32_t>(TW), static_cast<cuuint32_t>(TH), 1};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = enc(&p.tm_in, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, src->ptr, dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(MAF_E_CUDA, "dwconv_conv1x1: cuTensorMapEncodeTiled(src) failed: %d", (int)r);
-  }
-  {
     const int chans[1] = {src->c};
     const int k_packed = mafb200_packed_k_1x1(chans, 1);
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(k_packed), static_cast<cuuint64_t>(tile_n)};
@@ -308,14 +364,11 @@ extern "C" int32_t mafb200_dwconv_conv1x1(const maf_tensor* src, const float* dw
   p.C = src->c;
   p.N = dst->c;
   p.tile_n = tile_n;
-  p.tiles_x = ceil_div(src->w, kFwTX);
   p.act1 = act1;
   p.act2 = act2;
-  int cols = 32;
-  while (cols < 2 * tile_n) cols <<= 1;
-  p.tmem_cols = cols;
   p.idesc = umma_idesc_f16(128, tile_n);
-  const int tiles = p.tiles_x * ceil_div(src->h, kFwTY);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return k == 3 ? launch_dwpw<3>(p, src->n, tiles, st) : launch_dwpw<5>(p, src->n, tiles, st);
+  if (dwpw_small_tiles())
+    return k == 3 ? launch_dwpw<3, 10, 10>(p, src, st) : launch_dwpw<5, 10, 10>(p, src, st);
+  return k == 3 ? launch_dwpw<3, 20, 10>(p, src, st) : launch_dwpw<5, 20, 10>(p, src, st);
 }

@@ -205,7 +205,9 @@ def test_dwconv(cuda_device, c, k, h, w, n, act):
                                                       (144, 48, 5, 20, 20, 2, "silu", "silu"), (192, 64, 5, 80, 80, 1, "silu", "silu"),
                                                       # k = 3 with 2, 3 and 4 channel blocks (the halo buffer and both W2 slots are reused)
                                                       (144, 24, 3, 33, 41, 2, "silu", "silu"), (256, 32, 3, 20, 20, 1, "silu", "none"),
-                                                      (96, 32, 3, 160, 160, 1, "silu", "silu"), (72, 64, 3, 20, 20, 1, "silu", "silu")])
+                                                      (96, 32, 3, 160, 160, 1, "silu", "silu"), (72, 64, 3, 20, 20, 1, "silu", "silu"),
+                                                      # 16- and 8-channel tail blocks (fetched by cp.async) on ragged maps
+                                                      (80, 32, 3, 23, 37, 2, "silu", "silu"), (136, 40, 5, 17, 26, 1, "none", "silu")])
 def test_dwconv_conv1x1_fused(cuda_device, c, cout, k, h, w, n, act1, act2):
     """Fused depth-wise -> 1x1 kernel against the two reference ops in fp32 (the intermediate is rounded to fp16 once,
     exactly as the two separate kernels do)."""
