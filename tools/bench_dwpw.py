@@ -38,3 +38,4 @@ for name, c, cout, k, h, w, act1 in SHAPES:
     t = timeit(lambda: ops.dwconv_conv1x1(src, *pdw, k, act1, *pw2, "silu", dst))
     out.append(f"{name} {t:.1f}")
 print(os.environ.get("MAFB200_LIB", "default"), " | ".join(out), "us")
+
