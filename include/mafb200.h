@@ -278,6 +278,31 @@ MAFB200_API int32_t mafb200_scale_detections(const float* det, const int32_t* co
                                  int32_t recip_mul, float* out, int32_t* out_cat, void* stream);
 
 /* number of kernel launches issued by this library in the calling process (bench.py gpu_launches) */
+/* ---- training-side kernels -------------------------------------------------------------------------
+ * Task-aligned label assignment + detection loss of the reference's ComputeLoss.__call__ for epoch >= warm-up
+ * (yolov6/models/loss.py:56-162; TaskAlignedAssigner(topk=13, alpha=1, beta=6), yolov6/assigners/tal_assigner.py:22-151,
+ * assigner_utils.py:25-89; VarifocalLoss loss.py:181-192; BboxLoss GIoU + DFL loss.py:195-254, figure_iou.py:27-65),
+ * forward value and the gradients w.r.t. the head's train-form outputs.  Replaces the numpy / python target loop of
+ * loss.py:164-172 and ~40 torch ops on [B,G,8400] float64 tensors.
+ *   pred_scores  [B,A,nc] fp32 class probabilities, pred_distri [B,A,68] fp32 DFL logits (Detect_yaml train branch,
+ *                yolov6/models/yolo.py:333-354); A = (s/8)^2 + (s/16)^2 + (s/32)^2 anchors for image size s
+ *   targets      [T,6] fp32 rows (image index, class, cx, cy, w, h normalised), as the dataloader collates them
+ *   gt_cap       capacity G of boxes per image (>= the largest count; rows beyond it are counted in scalars[6])
+ *   boxes_override  optional [B,A,4] fp32 xyxy in stride units used instead of decoding pred_distri (tests)
+ *   scalars_out  device double[8]: loss, 2.5*loss_iou, 0.5*loss_dfl, 1.0*loss_cls (the reference's return values),
+ *                target_scores_sum, number of foreground anchors, dropped target rows, 0
+ *   grad_scores / grad_distri  optional fp32 [B,A,nc] / [B,A,68]: d loss / d pred_scores, d loss / d pred_distri
+ *   out_gt_idx / out_fg / out_target_score  optional [B,A] int32 / uint8 / double: the assignment (target_gt_idx,
+ *                fg_mask, and the one non-zero entry of each row of target_scores)
+ * Nothing allocates or synchronises; all kernels are enqueued on `stream`. */
+MAFB200_API size_t mafb200_loss_workspace_bytes(int32_t batch, int32_t anchors, int32_t gt_cap);
+MAFB200_API int32_t mafb200_detect_loss(const float* pred_scores, const float* pred_distri, const float* targets,
+                                        int32_t num_targets, int32_t batch, int32_t img_size, int32_t num_classes,
+                                        int32_t gt_cap, const float* boxes_override, void* workspace,
+                                        size_t workspace_bytes, double* scalars_out, float* grad_scores,
+                                        float* grad_distri, int32_t* out_gt_idx, uint8_t* out_fg,
+                                        double* out_target_score, void* stream);
+
 MAFB200_API int64_t mafb200_launch_count(void);
 
 #ifdef __cplusplus

@@ -19,7 +19,7 @@ CSRC = PKG_DIR / "csrc"
 # libmafb200_<name>.so, loaded with MAFB200_LIB=<path> (maf_yolo_b200/_lib.py).  Same sources, same CUDA path.
 SUFFIX = os.environ.get("MAFB200_BUILD_SUFFIX", "")
 LIB_PATH = PKG_DIR / (f"libmafb200_{SUFFIX}.so" if SUFFIX else "libmafb200.so")
-SOURCES = ["host.cu", "gemm_tc.cu", "stem_conv.cu", "dwconv.cu", "dwpw.cu", "bneck.cu", "poolpw.cu", "pool.cu", "decode.cu", "nms.cu", "postprocess.cu", "preprocess.cu"]
+SOURCES = ["host.cu", "gemm_tc.cu", "stem_conv.cu", "dwconv.cu", "dwpw.cu", "bneck.cu", "poolpw.cu", "pool.cu", "decode.cu", "nms.cu", "postprocess.cu", "preprocess.cu", "loss.cu"]
 EXTRA = os.environ.get("MAFB200_NVCC_EXTRA", "").split()
 NVCC_FLAGS = EXTRA + [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -1,0 +1,693 @@
+// K10 — training-side kernels: task-aligned label assignment + varifocal / GIoU / DFL loss, forward
+// value AND the gradients w.r.t. the head outputs, for the reference's `ComputeLoss.__call__` after its warm-up epochs
+// (yolov6/models/loss.py:56-162 with formal_assigner = TaskAlignedAssigner(topk=13, alpha=1, beta=6),
+// yolov6/assigners/tal_assigner.py:22-151, assigner_utils.py:25-89, figure_iou.py:27-65, general.py:29-49).
+//
+// The reference materialises [B, G, 8400] float64 tensors five times over (IoU, metric, in-box mask, top-k one-hot with
+// 8400 classes, ...: the "OOM RuntimeError ... CPU mode" branch of loss.py:95-133) and loops over the targets in
+// python / numpy on the host.  Here nothing of size B x G x A exists except one byte map:
+//
+//   targets_kernel   [T,6] fp32 rows -> padded [B,G,5] float64 (class, xyxy pixels), original order kept
+//   decode_kernel    DFL softmax-expectation -> boxes [B,A,4] fp32 in stride units      (4 lanes per anchor)
+//   topk_kernel      one CTA per (image, box): IoU / in-box test / alignment metric of all A anchors into shared memory,
+//                    13 rounds of block arg-max -> byte map pos[B,G,A]
+//   resolve_kernel   one thread per anchor: boxes that claim it; more than one -> the box with the highest IoU over ALL
+//                    boxes; atomicMax of the per-box normalisers (non-negative float64 as uint64)
+//   norm_kernel      target score of every foreground anchor + deterministic partial sums
+//   vfl_kernel       varifocal loss over B x A x nc + d/d pred_scores
+//   box_kernel       GIoU (forward-mode dual numbers) + DFL of the foreground anchors + d/d pred_distri
+//   final_kernel     fixed-order reduction of the partial sums, loss = 1.0 cls + 2.5 iou + 0.5 dfl
+//
+// Arithmetic follows the reference's dtypes: its target tensor is FLOAT64 (built with numpy, never cast), so the IoUs, the
+// metric, the normalised target scores and the loss sums are float64; the predictions, BCE and cross-entropy are fp32.
+// Comparison-deciding float64 expressions use round-to-nearest intrinsics in the reference's operation order (no FMA
+// contraction).  pow(iou, 6), exp and log are the CUDA library's (<= 2 ulp from torch's), which can move a top-13 cut
+// only between metrics that are equal to ~1e-16 relative.
+#include <math.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "host.h"
+
+namespace mafb200 {
+
+constexpr int kRegBins = 17;   // reg_max + 1
+constexpr int kTopK = 13;
+constexpr double kTalEps = 1e-9;
+constexpr double kIouLossEps = 1e-10;
+
+struct LossParams {
+  const float* pred_scores;  // [B,A,nc] probabilities
+  const float* pred_distri;  // [B,A,68] logits
+  const float* targets;      // [T,6]
+  const float* boxes_in;     // optional [B,A,4] stride units (skips decode_kernel)
+  int32_t T, B, A, nc, G, img;
+  int32_t n0, n1, n2;        // cells per side of the three levels (strides 8, 16, 32)
+  // workspace
+  double* gt;                // [B,G,5]
+  uint8_t* mask_gt;          // [B,G]
+  uint8_t* pos;              // [B,G,A]
+  float* boxes;              // [B,A,4] stride units
+  int32_t* gt_idx;           // [B,A]
+  uint8_t* fg;               // [B,A]
+  double* align_a;           // [B,A]
+  double* ovl_a;             // [B,A]
+  double* norm;              // [B,A]
+  unsigned long long* pos_align;  // [B,G] float64 bits
+  unsigned long long* pos_ovl;    // [B,G]
+  double* partial;           // [4][kMaxPartials]: tss, cls, iou, dfl
+  double* scalars;           // [8]: loss, 2.5 iou, 0.5 dfl, cls, tss, num_fg, target overflow, (spare)
+  int32_t* counters;         // [2]: num_fg, target overflow
+  float* grad_scores;        // optional [B,A,nc]
+  float* grad_distri;        // optional [B,A,68]
+};
+constexpr int kMaxPartials = 16384;  // blocks per reduction stage (the box kernel is one thread per (anchor, side): B x A <= 1M)
+
+// ---- anchors: level-major, row-major inside a level (anchor_generator.py:29-52) ----------------------------------
+struct Anchor {
+  float px, py, stride;  // pixel centre, stride
+};
+__device__ __forceinline__ Anchor anchor_of(const LossParams& p, int a) {
+  int n = p.n0, s = 8;
+  if (a >= p.n0 * p.n0) {
+    a -= p.n0 * p.n0;
+    n = p.n1;
+    s = 16;
+    if (a >= p.n1 * p.n1) {
+      a -= p.n1 * p.n1;
+      n = p.n2;
+      s = 32;
+    }
+  }
+  const int y = a / n, x = a - y * n;
+  Anchor r;
+  r.stride = static_cast<float>(s);
+  r.px = __fmul_rn(static_cast<float>(x) + 0.5f, r.stride);
+  r.py = __fmul_rn(static_cast<float>(y) + 0.5f, r.stride);
+  return r;
+}
+
+// ---- float64 helpers in the reference's operation order ------------------------------------------------------------
+__device__ __forceinline__ double clip0(double v) { return v < 0.0 ? 0.0 : v; }
+
+// assigner_utils.py:72-89: box1 = ground truth, box2 = prediction (pixels)
+// The prediction's own area is an expression of fp32 tensors only and therefore fp32 in the reference; everything that
+// touches the float64 ground truth is float64.
+__device__ __forceinline__ double iou_gt_pred(const double* g, float fx1, float fy1, float fx2, float fy2) {
+  const double px1 = fx1, py1 = fy1, px2 = fx2, py2 = fy2;
+  const double x1 = fmax(g[0], px1), y1 = fmax(g[1], py1), x2 = fmin(g[2], px2), y2 = fmin(g[3], py2);
+  const double overlap = __dmul_rn(clip0(__dsub_rn(x2, x1)), clip0(__dsub_rn(y2, y1)));
+  const double area1 = __dmul_rn(clip0(__dsub_rn(g[2], g[0])), clip0(__dsub_rn(g[3], g[1])));
+  const double area2 = __fmul_rn(fmaxf(__fsub_rn(fx2, fx1), 0.0f), fmaxf(__fsub_rn(fy2, fy1), 0.0f));
+  const double uni = __dadd_rn(__dsub_rn(__dadd_rn(area1, area2), overlap), kTalEps);
+  return __ddiv_rn(overlap, uni);
+}
+
+// prediction box of anchor a in pixels: fp32 (stride units) x fp32 stride, as `pred_bboxes.detach() * stride_tensor`
+__device__ __forceinline__ void pred_box_px(const LossParams& p, int b, int a, float stride, float* o) {
+  const float4 v = *reinterpret_cast<const float4*>(p.boxes + (static_cast<size_t>(b) * p.A + a) * 4);
+  o[0] = __fmul_rn(v.x, stride);
+  o[1] = __fmul_rn(v.y, stride);
+  o[2] = __fmul_rn(v.z, stride);
+  o[3] = __fmul_rn(v.w, stride);
+}
+
+// ---- 1. targets ------------------------------------------------------------------------------------------------------
+// loss.py:164-172.  Row order inside an image = order in `targets` (the assigner's tie-breaks depend on it): the slot of
+// a row is the number of earlier rows of the same image (T is a few hundred at most).
+__global__ void __launch_bounds__(256) loss_targets_kernel(const LossParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (int i = threadIdx.x; i < p.B * p.G; i += blockDim.x) {
+    double* g = p.gt + static_cast<size_t>(i) * 5;
+    g[0] = -1.0;
+    g[1] = g[2] = g[3] = g[4] = 0.0;
+    p.mask_gt[i] = 0;
+    p.pos_align[i] = 0ull;
+    p.pos_ovl[i] = 0ull;
+  }
+  if (threadIdx.x < 2) p.counters[threadIdx.x] = 0;
+  __syncthreads();
+  const double scale = static_cast<double>(p.img);
+  for (int t = threadIdx.x; t < p.T; t += blockDim.x) {
+    const float* r = p.targets + static_cast<size_t>(t) * 6;
+    const int b = static_cast<int>(r[0]);
+    if (b < 0 || b >= p.B) {
+      atomicAdd(p.counters + 1, 1);
+      continue;
+    }
+    int slot = 0;
+    for (int u = 0; u < t; ++u) slot += static_cast<int>(p.targets[static_cast<size_t>(u) * 6]) == b;
+    if (slot >= p.G) {
+      atomicAdd(p.counters + 1, 1);
+      continue;
+    }
+    const double cx = __dmul_rn(static_cast<double>(r[2]), scale), cy = __dmul_rn(static_cast<double>(r[3]), scale);
+    const double w = __dmul_rn(static_cast<double>(r[4]), scale), h = __dmul_rn(static_cast<double>(r[5]), scale);
+    const double x1 = __dsub_rn(cx, __dmul_rn(w, 0.5)), y1 = __dsub_rn(cy, __dmul_rn(h, 0.5));  // general.py:52-58
+    const double x2 = __dadd_rn(x1, w), y2 = __dadd_rn(y1, h);
+    double* g = p.gt + (static_cast<size_t>(b) * p.G + slot) * 5;
+    g[0] = static_cast<double>(r[1]);
+    g[1] = x1;
+    g[2] = y1;
+    g[3] = x2;
+    g[4] = y2;
+    p.mask_gt[b * p.G + slot] = __dadd_rn(__dadd_rn(__dadd_rn(x1, y1), x2), y2) > 0.0;  // loss.py:76
+  }
+}
+
+// ---- 2. box decode ----------------------------------------------------------------------------------------------------
+// loss.py:174-178: one lane per (anchor, side): softmax over 17 logits, expectation, point -/+ distance (stride units)
+__device__ __forceinline__ float dfl_expect(const float* logit, float* prob /* [17] or nullptr */, float* lse_out) {
+  float v[kRegBins];
+  float m = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < kRegBins; ++k) {
+    v[k] = logit[k];
+    m = fmaxf(m, v[k]);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < kRegBins; ++k) {
+    v[k] = expf(v[k] - m);
+    s += v[k];
+  }
+  float e = 0.f;
+#pragma unroll
+  for (int k = 0; k < kRegBins; ++k) {
+    const float q = v[k] / s;
+    if (prob) prob[k] = q;
+    e += q * static_cast<float>(k);
+  }
+  if (lse_out) *lse_out = m + logf(s);
+  return e;
+}
+
+__global__ void __launch_bounds__(256) loss_decode_kernel(const LossParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // (b, a, side)
+  if (i >= static_cast<size_t>(p.B) * p.A * 4) return;
+  const int side = static_cast<int>(i & 3);
+  const int a = static_cast<int>((i >> 2) % p.A);
+  const float e = dfl_expect(p.pred_distri + i * kRegBins, nullptr, nullptr);
+  const Anchor an = anchor_of(p, a);
+  const float c = (side & 1) ? an.py / an.stride : an.px / an.stride;  // anchor_points / stride_tensor (exact)
+  p.boxes[i] = side < 2 ? c - e : c + e;
+}
+
+// ---- 3. top-13 anchors per box ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tal_topk_kernel(const LossParams p) {
+  extern __shared__ double s_metric[];  // [A]
+  __shared__ double s_val[8];
+  __shared__ int s_idx[8];
+  __shared__ int s_win;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int g = blockIdx.x, b = blockIdx.y;
+  if (!p.mask_gt[b * p.G + g]) return;  // padding rows vote for anchor 0 thirteen times and are dropped (tal_assigner.py:121-127)
+  const double* gt = p.gt + (static_cast<size_t>(b) * p.G + g) * 5;
+  const double gb[4] = {gt[1], gt[2], gt[3], gt[4]};
+  int label = static_cast<int>(static_cast<long long>(gt[0]));
+  label = label < 0 ? 0 : (label >= p.nc ? p.nc - 1 : label);  // memory safety only: real boxes carry valid classes
+  const float* score = p.pred_scores + static_cast<size_t>(b) * p.A * p.nc + label;
+  for (int a = threadIdx.x; a < p.A; a += blockDim.x) {
+    const Anchor an = anchor_of(p, a);
+    const double ax = an.px, ay = an.py;
+    // centre strictly inside the box (assigner_utils.py:25-45)
+    const double dmin = fmin(fmin(__dsub_rn(ax, gb[0]), __dsub_rn(ay, gb[1])), fmin(__dsub_rn(gb[2], ax), __dsub_rn(gb[3], ay)));
+    double m = 0.0;
+    if (dmin > kTalEps) {
+      float pb[4];
+      pred_box_px(p, b, a, an.stride, pb);
+      const double iou = iou_gt_pred(gb, pb[0], pb[1], pb[2], pb[3]);
+      m = __dmul_rn(static_cast<double>(score[static_cast<size_t>(a) * p.nc]), pow(iou, 6.0));  // tal_assigner.py:107
+    }
+    s_metric[a] = m;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* pos = p.pos + (static_cast<size_t>(b) * p.G + g) * p.A;
+  for (int round = 0; round < kTopK; ++round) {
+    double best = -1.0;
+    int bi = 0x7fffffff;
+    for (int a = threadIdx.x; a < p.A; a += blockDim.x) {
+      const double v = s_metric[a];
+      if (v > best) {  // strictly greater: the smallest index wins among equals (indices ascend per thread)
+        best = v;
+        bi = a;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) {
+        best = ov;
+        bi = oi;
+      }
+    }
+    if (lane == 0) {
+      s_val[warp] = best;
+      s_idx[warp] = bi;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double v = s_val[0];
+      int wi = s_idx[0];
+      for (int w = 1; w < 8; ++w)
+        if (s_val[w] > v || (s_val[w] == v && s_idx[w] < wi)) {
+          v = s_val[w];
+          wi = s_idx[w];
+        }
+      // a metric of exactly 0 is an anchor outside the box (or a zero score): mask_in_gts drops it whichever of the
+      // tied zeros torch.topk would have returned
+      if (v > 0.0) {
+        pos[wi] = 1;
+        s_metric[wi] = -1.0;
+        s_win = 1;
+      } else {
+        s_win = 0;
+      }
+    }
+    __syncthreads();
+    if (!s_win) break;
+  }
+}
+
+// ---- 4. one box per anchor ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tal_resolve_kernel(const LossParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int a = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (a >= p.A) return;
+  const size_t ba = static_cast<size_t>(b) * p.A + a;
+  int count = 0, first = 0;
+  for (int g = 0; g < p.G; ++g) {
+    const int v = p.pos[(static_cast<size_t>(b) * p.G + g) * p.A + a];
+    if (v && count == 0) first = g;
+    count += v;
+  }
+  if (count == 0) {
+    p.gt_idx[ba] = 0;
+    p.fg[ba] = 0;
+    p.align_a[ba] = 0.0;
+    p.ovl_a[ba] = 0.0;
+    return;
+  }
+  const Anchor an = anchor_of(p, a);
+  float pb[4];
+  pred_box_px(p, b, a, an.stride, pb);
+  int gs = first;
+  double iou;
+  if (count > 1) {  // assigner_utils.py:60-66: arg-max of the IoU over ALL boxes of the image (first maximum)
+    double best = -1.0;
+    for (int g = 0; g < p.G; ++g) {
+      const double* gt = p.gt + (static_cast<size_t>(b) * p.G + g) * 5;
+      const double v = iou_gt_pred(gt + 1, pb[0], pb[1], pb[2], pb[3]);
+      if (v > best) {
+        best = v;
+        gs = g;
+      }
+    }
+    iou = best;
+  } else {
+    iou = iou_gt_pred(p.gt + (static_cast<size_t>(b) * p.G + gs) * 5 + 1, pb[0], pb[1], pb[2], pb[3]);
+  }
+  const double* gt = p.gt + (static_cast<size_t>(b) * p.G + gs) * 5;
+  long long lab = static_cast<long long>(gt[0]);
+  if (lab < 0) lab += p.nc;  // pd_scores[..., -1] of a padding row (tal_assigner.py:101-104); cannot win with IoU 0
+  if (lab < 0 || lab >= p.nc) lab = 0;
+  const double sc = p.pred_scores[ba * p.nc + lab];
+  const double align = __dmul_rn(sc, pow(iou, 6.0));
+  p.gt_idx[ba] = gs;
+  p.fg[ba] = 1;
+  p.align_a[ba] = align;
+  p.ovl_a[ba] = iou;
+  atomicMax(p.pos_align + b * p.G + gs, static_cast<unsigned long long>(__double_as_longlong(align)));
+  atomicMax(p.pos_ovl + b * p.G + gs, static_cast<unsigned long long>(__double_as_longlong(iou)));
+  atomicAdd(p.counters, 1);
+}
+
+// fixed-order block sum of one double per thread (256 threads) -> thread 0
+__device__ __forceinline__ double block_sum_256(double v, double* s_red /* [8] */) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.x == 0)
+    for (int w = 0; w < 8; ++w) t += s_red[w];
+  __syncthreads();
+  return t;
+}
+
+// ---- 5. normalised target scores (tal_assigner.py:66-72) + sum ---------------------------------------------------------------
+__global__ void __launch_bounds__(256) tal_norm_kernel(const LossParams p) {
+  __shared__ double s_red[8];
+  pdl_launch_dependents();
+  pdl_wait();
+  const size_t n = static_cast<size_t>(p.B) * p.A;
+  double acc = 0.0;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    double v = 0.0;
+    if (p.fg[i]) {
+      const int b = static_cast<int>(i / p.A);
+      const int gs = p.gt_idx[i];
+      const double pa = __longlong_as_double(static_cast<long long>(p.pos_align[b * p.G + gs]));
+      const double po = __longlong_as_double(static_cast<long long>(p.pos_ovl[b * p.G + gs]));
+      v = __ddiv_rn(__dmul_rn(p.align_a[i], po), __dadd_rn(pa, kTalEps));
+    }
+    p.norm[i] = v;
+    acc += v;
+  }
+  const double t = block_sum_256(acc, s_red);
+  if (threadIdx.x == 0) p.partial[blockIdx.x] = t;
+}
+
+// sums partial[which][0..n) in a fixed order into scalars[dst]
+__device__ __forceinline__ double reduce_partials(const double* part, int n, double* s_red) {
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) acc += part[i];
+  return block_sum_256(acc, s_red);
+}
+
+__global__ void __launch_bounds__(256) loss_tss_kernel(const LossParams p, int n_part) {
+  __shared__ double s_red[8];
+  pdl_launch_dependents();
+  pdl_wait();
+  const double t = reduce_partials(p.partial, n_part, s_red);
+  if (threadIdx.x == 0) p.scalars[4] = t;
+}
+
+// ---- 6. varifocal loss (loss.py:181-192) + gradient ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) loss_vfl_kernel(const LossParams p) {
+  __shared__ double s_red[8];
+  pdl_launch_dependents();
+  pdl_wait();
+  const double tss = p.scalars[4];
+  const size_t n = static_cast<size_t>(p.B) * p.A * p.nc;
+  double acc = 0.0;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t row = i / p.nc;
+    const int c = static_cast<int>(i - row * p.nc);
+    const float pr = p.pred_scores[i];
+    bool is_t = false;
+    double t = 0.0;
+    if (p.fg[row]) {
+      const int b = static_cast<int>(row / p.A);
+      const double* gt = p.gt + (static_cast<size_t>(b) * p.G + p.gt_idx[row]) * 5;
+      long long lab = static_cast<long long>(gt[0]);
+      if (lab < 0) lab = 0;  // tal_assigner.py:143
+      if (lab == c) {
+        is_t = true;
+        t = p.norm[row];
+      }
+    }
+    const float l1 = fmaxf(log1pf(-pr), -100.0f), l2 = fmaxf(logf(pr), -100.0f);  // BCE's clamp
+    const float den = fmaxf((1.0f - pr) * pr, 1e-12f);                            // BCE backward's clamp
+    double term, grad;
+    if (is_t) {
+      const float t32 = static_cast<float>(t);
+      const float bce = (t32 - 1.0f) * l1 - t32 * l2;
+      term = static_cast<double>(bce) * t;
+      grad = t * static_cast<double>((pr - t32) / den);
+    } else {
+      const float w = 0.75f * (pr * pr);
+      const float bce = -l1 - 0.0f * l2;
+      term = static_cast<double>(bce) * static_cast<double>(w);
+      grad = static_cast<double>(w) * static_cast<double>(pr / den) + static_cast<double>(bce) * static_cast<double>(1.5f * pr);
+    }
+    acc += term;
+    if (p.grad_scores) p.grad_scores[i] = static_cast<float>(grad / tss);  // loss weight 'class' = 1.0
+  }
+  const double t = block_sum_256(acc, s_red);
+  if (threadIdx.x == 0) p.partial[kMaxPartials + blockIdx.x] = t;
+}
+
+// ---- 7. GIoU + DFL of the foreground anchors (loss.py:195-254) + gradient -----------------------------------------------------
+// forward-mode dual number: value + derivative w.r.t. ONE chosen coordinate of the predicted box
+struct Dual {
+  double v, d;
+};
+__device__ __forceinline__ Dual dk(double v) { return {v, 0.0}; }
+__device__ __forceinline__ Dual operator+(Dual a, Dual b) { return {a.v + b.v, a.d + b.d}; }
+__device__ __forceinline__ Dual operator-(Dual a, Dual b) { return {a.v - b.v, a.d - b.d}; }
+__device__ __forceinline__ Dual operator*(Dual a, Dual b) { return {a.v * b.v, a.d * b.v + a.v * b.d}; }
+__device__ __forceinline__ Dual operator/(Dual a, Dual b) { return {a.v / b.v, (a.d * b.v - a.v * b.d) / (b.v * b.v)}; }
+__device__ __forceinline__ Dual dmin(Dual a, Dual b) { return a.v <= b.v ? a : b; }
+__device__ __forceinline__ Dual dmax(Dual a, Dual b) { return a.v >= b.v ? a : b; }
+__device__ __forceinline__ Dual dclamp0(Dual a) { return a.v >= 0.0 ? a : Dual{0.0, 0.0}; }
+
+__global__ void __launch_bounds__(256) loss_box_kernel(const LossParams p) {
+  __shared__ double s_red[8];
+  pdl_launch_dependents();
+  pdl_wait();
+  const double tss = p.scalars[4];
+  const size_t n = static_cast<size_t>(p.B) * p.A * 4;
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // (b, a, side); a quad = one anchor
+  double iou_term = 0.0, dfl_term = 0.0;
+  const bool in_range = i < n;
+  const size_t row = in_range ? (i >> 2) : 0;
+  const int side = static_cast<int>(i & 3);
+  const bool fg = in_range && p.fg[row];
+  // quads never straddle a warp and n % 4 == 0, so the shuffles below see whole anchors; lanes of background anchors run
+  // the arithmetic on zeros and store nothing but zero gradients
+  float prob[kRegBins];
+  float lse = 0.f, e = 0.f;
+  const float* logit = p.pred_distri + (in_range ? i : 0) * kRegBins;
+  if (fg) e = dfl_expect(logit, prob, &lse);
+  const int b = static_cast<int>(row / p.A), a = static_cast<int>(row - static_cast<size_t>(b) * p.A);
+  const Anchor an = anchor_of(p, a);
+  const float cs = (side & 1) ? an.py / an.stride : an.px / an.stride;
+  double my_coord = 0.0, tgt_coord = 0.0, bw = 0.0;
+  if (fg) {
+    my_coord = p.boxes[i];  // the box the assigner saw (decode_kernel, or the caller's)
+    const double* gt = p.gt + (static_cast<size_t>(b) * p.G + p.gt_idx[row]) * 5;
+    tgt_coord = __ddiv_rn(gt[1 + side], static_cast<double>(an.stride));  // target_bboxes /= stride_tensor (loss.py:141)
+    bw = p.norm[row];                                                     // target_scores.sum(-1)
+  }
+  const unsigned quad_base = (threadIdx.x & 31) & ~3u;
+  double pbx[4], tbx[4];
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    pbx[s] = __shfl_sync(0xffffffffu, my_coord, quad_base + s);
+    tbx[s] = __shfl_sync(0xffffffffu, tgt_coord, quad_base + s);
+  }
+  double g_coord = 0.0;  // d giou_loss / d (this lane's coordinate)
+  double dfl_ce = 0.0;   // this side's left/right cross-entropy
+  double wl = 0.0, wr = 0.0;
+  int tl = 0;
+  if (fg) {
+    // figure_iou.py:37-65, box1 = prediction, box2 = target; the derivative is taken w.r.t. coordinate `side` of box1
+    Dual x1 = dk(pbx[0]), y1 = dk(pbx[1]), x2 = dk(pbx[2]), y2 = dk(pbx[3]);
+    (side == 0 ? x1 : side == 1 ? y1 : side == 2 ? x2 : y2).d = 1.0;
+    const Dual u1 = dk(tbx[0]), v1 = dk(tbx[1]), u2 = dk(tbx[2]), v2 = dk(tbx[3]);
+    const Dual eps = dk(kIouLossEps);
+    const Dual inter = dclamp0(dmin(x2, u2) - dmax(x1, u1)) * dclamp0(dmin(y2, v2) - dmax(y1, v1));
+    // w1, h1 (+ eps) and w1 * h1 are expressions of the fp32 prediction only: fp32 in the reference (the derivatives are
+    // taken of the exact expression)
+    const float fx1 = static_cast<float>(pbx[0]), fy1 = static_cast<float>(pbx[1]), fx2 = static_cast<float>(pbx[2]), fy2 = static_cast<float>(pbx[3]);
+    const float w1f = __fsub_rn(fx2, fx1), h1f = __fadd_rn(__fsub_rn(fy2, fy1), 1e-10f);
+    const Dual w1 = {static_cast<double>(w1f), (x2 - x1).d}, h1 = {static_cast<double>(h1f), (y2 - y1).d};
+    Dual a1 = w1 * h1;
+    a1.v = static_cast<double>(__fmul_rn(w1f, h1f));
+    const Dual w2 = u2 - u1, h2 = v2 - v1 + eps;
+    const Dual uni = a1 + w2 * h2 - inter + eps;
+    const Dual iou = inter / uni;
+    const Dual cw = dmax(x2, u2) - dmin(x1, u1), ch = dmax(y2, v2) - dmin(y1, v1);
+    const Dual hull = cw * ch + eps;
+    const Dual loss = dk(1.0) - (iou - (hull - uni) / hull);
+    g_coord = loss.d;
+    if (side == 0) iou_term = loss.v * bw;  // one lane per anchor contributes the value
+    // DFL (loss.py:243-254): target distance of this side, clipped to [0, reg_max - 0.01] (general.py:43-49)
+    const double csd = static_cast<double>(cs);
+    double tgt = side < 2 ? csd - tbx[side] : tbx[side] - csd;
+    tgt = fmin(fmax(tgt, 0.0), 16.0 - 0.01);
+    tl = static_cast<int>(tgt);
+    wl = static_cast<double>(static_cast<float>(tl + 1)) - tgt;
+    wr = 1.0 - wl;
+    const float ce_l = lse - logit[tl], ce_r = lse - logit[tl + 1];  // F.cross_entropy, fp32
+    dfl_ce = static_cast<double>(ce_l) * wl + static_cast<double>(ce_r) * wr;
+  }
+  // mean over the four sides
+  double ce4 = dfl_ce;
+  ce4 += __shfl_xor_sync(0xffffffffu, ce4, 1);
+  ce4 += __shfl_xor_sync(0xffffffffu, ce4, 2);
+  if (fg && side == 0) dfl_term = (ce4 / 4.0) * bw;
+  if (p.grad_distri && in_range) {
+    float* go = p.grad_distri + i * kRegBins;
+    if (fg) {
+      // coordinate = point -/+ expectation; d expectation / d logit_j = p_j (j - E)
+      const double g_dist = (side < 2 ? -g_coord : g_coord) * bw * 2.5 / tss;
+      const double g_dfl = 0.25 * bw * 0.5 / tss;
+#pragma unroll
+      for (int j = 0; j < kRegBins; ++j) {
+        const double pj = prob[j];
+        double gj = g_dist * pj * (static_cast<double>(j) - static_cast<double>(e));
+        gj += g_dfl * (pj - (j == tl ? wl : 0.0) - (j == tl + 1 ? wr : 0.0));
+        go[j] = static_cast<float>(gj);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < kRegBins; ++j) go[j] = 0.0f;
+    }
+  }
+  const double ti = block_sum_256(iou_term, s_red);
+  const double td = block_sum_256(dfl_term, s_red);
+  if (threadIdx.x == 0) {
+    p.partial[2 * kMaxPartials + blockIdx.x] = ti;
+    p.partial[3 * kMaxPartials + blockIdx.x] = td;
+  }
+}
+
+// ---- 8. totals (loss.py:145-162) --------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) loss_final_kernel(const LossParams p, int n_vfl, int n_box) {
+  __shared__ double s_red[8];
+  pdl_launch_dependents();
+  pdl_wait();
+  const double cls = reduce_partials(p.partial + kMaxPartials, n_vfl, s_red);
+  const double iou = reduce_partials(p.partial + 2 * kMaxPartials, n_box, s_red);
+  const double dfl = reduce_partials(p.partial + 3 * kMaxPartials, n_box, s_red);
+  if (threadIdx.x == 0) {
+    const double tss = p.scalars[4];
+    const int num_fg = p.counters[0];
+    const double l_cls = cls / tss;                      // inf / nan without a single foreground anchor, as the reference
+    const double l_iou = num_fg > 0 ? iou / tss : 0.0;   // loss.py:205,238-240
+    const double l_dfl = num_fg > 0 ? dfl / tss : 0.0;
+    p.scalars[0] = 1.0 * l_cls + 2.5 * l_iou + 0.5 * l_dfl;
+    p.scalars[1] = 2.5 * l_iou;
+    p.scalars[2] = 0.5 * l_dfl;
+    p.scalars[3] = 1.0 * l_cls;
+    p.scalars[5] = static_cast<double>(num_fg);
+    p.scalars[6] = static_cast<double>(p.counters[1]);
+    p.scalars[7] = 0.0;
+  }
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct LossLayout {
+  size_t gt, mask_gt, pos, boxes, gt_idx, fg, align_a, ovl_a, norm, pos_align, pos_ovl, partial, scalars, counters, total;
+};
+static LossLayout loss_layout(size_t B, size_t A, size_t G) {
+  LossLayout l;
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    const size_t at = o;
+    o = align_up(o + bytes, 256);
+    return at;
+  };
+  l.gt = take(B * G * 5 * 8);
+  l.mask_gt = take(B * G);
+  l.pos = take(B * G * A);
+  l.boxes = take(B * A * 4 * 4);
+  l.gt_idx = take(B * A * 4);
+  l.fg = take(B * A);
+  l.align_a = take(B * A * 8);
+  l.ovl_a = take(B * A * 8);
+  l.norm = take(B * A * 8);
+  l.pos_align = take(B * G * 8);
+  l.pos_ovl = take(B * G * 8);
+  l.partial = take(static_cast<size_t>(4) * kMaxPartials * 8);
+  l.scalars = take(8 * 8);
+  l.counters = take(2 * 4);
+  l.total = o;
+  return l;
+}
+
+}  // namespace mafb200
+
+using namespace mafb200;
+
+extern "C" size_t mafb200_loss_workspace_bytes(int32_t batch, int32_t anchors, int32_t gt_cap) {
+  if (batch <= 0 || anchors <= 0 || gt_cap < 0) return 0;
+  return loss_layout(batch, anchors, gt_cap > 0 ? gt_cap : 1).total;
+}
+
+extern "C" int32_t mafb200_detect_loss(const float* pred_scores, const float* pred_distri, const float* targets,
+                                       int32_t num_targets, int32_t batch, int32_t img_size, int32_t num_classes,
+                                       int32_t gt_cap, const float* boxes_override, void* workspace, size_t workspace_bytes,
+                                       double* scalars_out, float* grad_scores, float* grad_distri, int32_t* out_gt_idx,
+                                       uint8_t* out_fg, double* out_target_score, void* stream) {
+  if (!pred_scores || !pred_distri || !workspace || !scalars_out) return fail(MAF_E_ARG, "detect_loss: null pointer");
+  if (num_targets < 0 || (num_targets > 0 && !targets)) return fail(MAF_E_ARG, "detect_loss: bad targets");
+  if (batch <= 0 || batch > 65535 || num_classes <= 0 || img_size <= 0 || img_size % 32 != 0)
+    return fail(MAF_E_ARG, "detect_loss: batch %d / classes %d / image size %d (must be a multiple of 32)", batch, num_classes, img_size);
+  if (gt_cap < 0 || gt_cap > 65535) return fail(MAF_E_ARG, "detect_loss: gt_cap %d", gt_cap);
+  const int n0 = img_size / 8, n1 = img_size / 16, n2 = img_size / 32;
+  const int A = n0 * n0 + n1 * n1 + n2 * n2;
+  const int G = gt_cap > 0 ? gt_cap : 1;  // gt_cap 0: one padding row per image (no foreground; the reference's early return)
+  const size_t topk_smem = static_cast<size_t>(A) * 8;
+  if (topk_smem > 200 * 1024) return fail(MAF_E_ARG, "detect_loss: %d anchors need %zu B of shared memory", A, topk_smem);
+  if ((reinterpret_cast<uintptr_t>(pred_scores) | reinterpret_cast<uintptr_t>(pred_distri) | reinterpret_cast<uintptr_t>(workspace)) & 15)
+    return fail(MAF_E_ALIGN, "detect_loss: predictions / workspace must be 16-B aligned");
+  const LossLayout l = loss_layout(batch, A, G);
+  if (workspace_bytes < l.total) return fail(MAF_E_WORKSPACE, "detect_loss: workspace %zu B < %zu B", workspace_bytes, l.total);
+  int32_t rc = require_sm100();
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+
+  LossParams p;
+  memset(&p, 0, sizeof(p));
+  p.pred_scores = pred_scores;
+  p.pred_distri = pred_distri;
+  p.targets = targets;
+  p.boxes_in = boxes_override;
+  p.T = num_targets;
+  p.B = batch;
+  p.A = A;
+  p.nc = num_classes;
+  p.G = G;
+  p.img = img_size;
+  p.n0 = n0;
+  p.n1 = n1;
+  p.n2 = n2;
+  p.gt = reinterpret_cast<double*>(ws + l.gt);
+  p.mask_gt = ws + l.mask_gt;
+  p.pos = ws + l.pos;
+  p.boxes = boxes_override ? const_cast<float*>(boxes_override) : reinterpret_cast<float*>(ws + l.boxes);
+  p.gt_idx = out_gt_idx ? out_gt_idx : reinterpret_cast<int32_t*>(ws + l.gt_idx);
+  p.fg = out_fg ? out_fg : ws + l.fg;
+  p.align_a = reinterpret_cast<double*>(ws + l.align_a);
+  p.ovl_a = reinterpret_cast<double*>(ws + l.ovl_a);
+  p.norm = out_target_score ? out_target_score : reinterpret_cast<double*>(ws + l.norm);
+  p.pos_align = reinterpret_cast<unsigned long long*>(ws + l.pos_align);
+  p.pos_ovl = reinterpret_cast<unsigned long long*>(ws + l.pos_ovl);
+  p.partial = reinterpret_cast<double*>(ws + l.partial);
+  p.scalars = scalars_out;
+  p.counters = reinterpret_cast<int32_t*>(ws + l.counters);
+  p.grad_scores = grad_scores;
+  p.grad_distri = grad_distri;
+  if (boxes_override && (reinterpret_cast<uintptr_t>(boxes_override) & 15)) return fail(MAF_E_ALIGN, "detect_loss: boxes must be 16-B aligned");
+
+  if (cudaMemsetAsync(p.pos, 0, static_cast<size_t>(batch) * G * A, st) != cudaSuccess)
+    return fail(MAF_E_CUDA, "detect_loss: cudaMemsetAsync failed");
+  {
+    static SmemOptIn opt_in;
+    rc = smem_opt_in(opt_in, tal_topk_kernel, 200 * 1024, "tal_topk");
+    if (rc) return rc;
+  }
+  const size_t rows = static_cast<size_t>(batch) * A;
+  auto blocks_for = [](size_t n, int per_thread) {
+    size_t b = (n + 256ull * per_thread - 1) / (256ull * per_thread);
+    if (b < 1) b = 1;
+    if (b > kMaxPartials) b = kMaxPartials;
+    return static_cast<int>(b);
+  };
+  const int n_norm = blocks_for(rows, 4), n_vfl = blocks_for(rows * num_classes, 8);
+  const size_t box_blocks = (rows * 4 + 255) / 256;  // one thread per (anchor, side), no grid stride
+  if (box_blocks > static_cast<size_t>(kMaxPartials))
+    return fail(MAF_E_ARG, "detect_loss: batch x anchors = %zu too large (%zu box blocks > %d)", rows, box_blocks, kMaxPartials);
+  launch_pdl(loss_targets_kernel, dim3(1), dim3(256), 0, st, p);
+  if (!boxes_override) launch_pdl(loss_decode_kernel, dim3(static_cast<unsigned>((rows * 4 + 255) / 256)), dim3(256), 0, st, p);
+  launch_pdl(tal_topk_kernel, dim3(G, batch), dim3(256), topk_smem, st, p);
+  launch_pdl(tal_resolve_kernel, dim3((A + 255) / 256, batch), dim3(256), 0, st, p);
+  launch_pdl(tal_norm_kernel, dim3(n_norm), dim3(256), 0, st, p);
+  launch_pdl(loss_tss_kernel, dim3(1), dim3(256), 0, st, p, n_norm);
+  launch_pdl(loss_vfl_kernel, dim3(n_vfl), dim3(256), 0, st, p);
+  launch_pdl(loss_box_kernel, dim3(static_cast<unsigned>(box_blocks)), dim3(256), 0, st, p);
+  launch_pdl(loss_final_kernel, dim3(1), dim3(256), 0, st, p, n_vfl, static_cast<int>(box_blocks));
+  return check_launch("detect_loss kernels");
+}
