@@ -94,6 +94,85 @@ FUSED_MB_PER_IMAGE = {"n": 58.2, "s": 78.9, "m": 121.3}
 GFLOP_PER_IMAGE = {"n": 10.508, "s": 25.448, "m": 76.650}
 
 
+
+def training_side_leg(dev, batch: int = 16, boxes_per_image: int = 20, steps: int = 50, cpu_steps: int = 2):
+    """SURVEY 8 f3 (config #5's non-conv part): the detection loss of one training step — task-aligned assignment +
+    varifocal / GIoU / DFL + gradients w.r.t. the head outputs — at the reference's per-GPU batch (16, 8400 anchors, 80
+    classes), outside the timed region.  `us_per_call`: mafb200_detect_loss, CUDA events.  `torch_same_gpu_us`: the same
+    arithmetic as ~60 torch ops on this GPU (the oracle's restatement of ComputeLoss, forward + autograd backward);
+    `cpu_ms`: the same on the host cores.  Algorithmic bytes: both prediction tensors read, both gradients written."""
+    from maf_yolo_b200.loss import ComputeLoss
+    from oracle import loss as ol
+
+    try:
+        g = torch.Generator().manual_seed(3)
+        a = 8400
+        scores = torch.sigmoid(torch.randn(batch, a, 80, generator=g) * 1.5 - 3.0)
+        distri = torch.randn(batch, a, 68, generator=g)
+        rows = []
+        for b in range(batch):
+            for _ in range(boxes_per_image):
+                cx, cy = torch.rand(2, generator=g).tolist()
+                w, h = (0.04 + 0.45 * torch.rand(2, generator=g)).tolist()
+                rows.append([float(b), float(int(torch.randint(0, 80, (1,), generator=g))), cx, cy, w, h])
+        targets = torch.tensor(rows, dtype=torch.float32)
+        ps, pd, tg = scores.to(dev).requires_grad_(), distri.to(dev).requires_grad_(), targets.to(dev)
+        crit = ComputeLoss(warmup_epoch=0)
+
+        def ours():
+            return crit((None, ps, pd), tg, 0, 0, gt_cap=boxes_per_image)[0]
+
+        def timed(fn, n):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s_ev.record()
+            for _ in range(n):
+                fn()
+            e_ev.record()
+            torch.cuda.synchronize()
+            return 1e3 * s_ev.elapsed_time(e_ev) / n
+
+        us = timed(ours, steps)
+        loss_ours = ours().item()
+
+        def torch_ref(device):
+            p1, p2, tt = scores.to(device).requires_grad_(), distri.to(device).requires_grad_(), targets.to(device)
+
+            def step():
+                p1.grad = p2.grad = None
+                loss, _ = ol.compute_loss(p1, p2, tt)
+                loss.backward()
+                return loss
+            return step
+
+        torch_us, loss_ref = None, None
+        try:
+            step = torch_ref(dev)
+            torch_us = timed(step, 5)
+            loss_ref = step().item()
+        except Exception as e:  # noqa: BLE001 (a torch op without a CUDA kernel must not cost the bench line)
+            torch_us = f"unavailable: {type(e).__name__}: {e}"[:200]
+        step_cpu = torch_ref(torch.device("cpu"))
+        step_cpu()
+        t0 = time.perf_counter()
+        for _ in range(cpu_steps):
+            l_cpu = step_cpu()
+        cpu_ms = 1e3 * (time.perf_counter() - t0) / cpu_steps
+        loss_ref = loss_ref if loss_ref is not None else l_cpu.item()
+        alg = batch * a * (80 + 68) * 4 * 2
+        return {"what": "detection loss of one training step (task-aligned assignment + VFL/GIoU/DFL + gradients), SURVEY 8 f3",
+                "batch": batch, "anchors": a, "boxes_per_image": boxes_per_image, "us_per_call": round(us, 1),
+                "kernels_per_call": 9, "algorithmic_bytes": alg, "GB/s": round(alg / us / 1e3, 1),
+                "hbm_frac_of_peak": round(alg / us / 1e3 / measured_hbm_peak()[0], 4),
+                "torch_same_gpu_us": round(torch_us, 1) if isinstance(torch_us, float) else torch_us,
+                "cpu_ms": round(cpu_ms, 1) if cpu_ms is not None else None, "cpu_cores": torch.get_num_threads(),
+                "loss": loss_ours, "loss_reference_arithmetic": loss_ref,
+                "rel_diff": abs(loss_ours - loss_ref) / abs(loss_ref) if loss_ref else None}
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+
 def gpu_library_baseline(variant: str, batch: int, dev, steps: int = 10):
     """The bar on the same box: the reference's deploy-form forward as plain
     torch-eager library calls on this GPU — cuDNN / cuBLAS convs in fp16, channels_last — + the reference's NMS with
@@ -561,6 +640,7 @@ def run_ours(a):
         del x_u8, det_host
         torch.cuda.empty_cache()
         lib_base = gpu_library_baseline(a.variant, B, dev)
+    train_leg = training_side_leg(dev) if world == 1 and not a.no_cpu_baseline else None
 
     line = {
         "metric": "images/sec @ 640x640 (forward + decode + NMS)", "value": round(value, 1), "unit": "images/s",
@@ -583,7 +663,7 @@ def run_ours(a):
         "latency_ms_per_batch": latency,
         "host_enqueue_ms_per_step": {"value_loop": round(host_enqueue_ms, 4), "e2e_loop": round(host_enqueue_e2e_ms, 4)},
         "clocks": clocks, "roofline": roofline, "whole_step": whole, "cpu_baseline": cpu,
-        "gpu_library_baseline": lib_base, "gather_check": gather_check,
+        "gpu_library_baseline": lib_base, "gather_check": gather_check, "training_side": train_leg,
     }
     emit(line)
     if world > 1:
