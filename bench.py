@@ -164,7 +164,7 @@ def training_side_leg(dev, batch: int = 16, boxes_per_image: int = 20, steps: in
         alg = batch * a * (80 + 68) * 4 * 2
         return {"what": "detection loss of one training step (task-aligned assignment + VFL/GIoU/DFL + gradients), SURVEY 8 f3",
                 "batch": batch, "anchors": a, "boxes_per_image": boxes_per_image, "us_per_call": round(us, 1),
-                "kernels_per_call": 9, "algorithmic_bytes": alg, "GB/s": round(alg / us / 1e3, 1),
+                "kernels_per_call": 7, "algorithmic_bytes": alg, "GB/s": round(alg / us / 1e3, 1),
                 "hbm_frac_of_peak": round(alg / us / 1e3 / measured_hbm_peak()[0], 4),
                 "torch_same_gpu_us": round(torch_us, 1) if isinstance(torch_us, float) else torch_us,
                 "cpu_ms": round(cpu_ms, 1) if cpu_ms is not None else None, "cpu_cores": torch.get_num_threads(),

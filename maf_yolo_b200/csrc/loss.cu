@@ -13,16 +13,17 @@
 //                    13 rounds of block arg-max -> byte map pos[B,G,A]
 //   resolve_kernel   one thread per anchor: boxes that claim it; more than one -> the box with the highest IoU over ALL
 //                    boxes; atomicMax of the per-box normalisers (non-negative float64 as uint64)
-//   norm_kernel      target score of every foreground anchor + deterministic partial sums
-//   vfl_kernel       varifocal loss over B x A x nc + d/d pred_scores
-//   box_kernel       GIoU (forward-mode dual numbers) + DFL of the foreground anchors + d/d pred_distri
-//   final_kernel     fixed-order reduction of the partial sums, loss = 1.0 cls + 2.5 iou + 0.5 dfl
+//   norm_kernel      target score + class of every anchor; the last block to finish folds target_scores_sum
+//   vfl_kernel       varifocal loss over B x A x nc + d/d pred_scores (4 classes per thread)
+//   box_kernel       GIoU (forward-mode dual numbers) + DFL of the foreground anchors + d/d pred_distri; the last block to
+//                    finish folds the partial sums in a fixed order: loss = 1.0 cls + 2.5 iou + 0.5 dfl
+// Seven launches + one memset per call; sums are deterministic (fixed-order folds, no floating-point atomics).
 //
 // Arithmetic follows the reference's dtypes: its target tensor is FLOAT64 (built with numpy, never cast), so the IoUs, the
 // metric, the normalised target scores and the loss sums are float64; the predictions, BCE and cross-entropy are fp32.
 // Comparison-deciding float64 expressions use round-to-nearest intrinsics in the reference's operation order (no FMA
-// contraction).  pow(iou, 6), exp and log are the CUDA library's (<= 2 ulp from torch's), which can move a top-13 cut
-// only between metrics that are equal to ~1e-16 relative.
+// contraction).  iou^6 (three multiplications), exp and log are within 2 ulp of torch's, which can move a top-13 cut only
+// between metrics that are equal to ~1e-16 relative.
 #include <math.h>
 #include <string.h>
 
@@ -57,7 +58,9 @@ struct LossParams {
   unsigned long long* pos_ovl;    // [B,G]
   double* partial;           // [4][kMaxPartials]: tss, cls, iou, dfl
   double* scalars;           // [8]: loss, 2.5 iou, 0.5 dfl, cls, tss, num_fg, target overflow, (spare)
-  int32_t* counters;         // [2]: num_fg, target overflow
+  int32_t* counters;         // [4]: num_fg, target overflow, blocks done (norm stage), blocks done (box stage)
+  int32_t* tlabel;           // [B,A] class of the assigned box, -1 on background anchors
+  int32_t n_vfl;             // blocks of the varifocal kernel (its partial sums are folded by the box kernel's last block)
   float* grad_scores;        // optional [B,A,nc]
   float* grad_distri;        // optional [B,A,68]
 };
@@ -103,6 +106,13 @@ __device__ __forceinline__ double iou_gt_pred(const double* g, float fx1, float 
   return __ddiv_rn(overlap, uni);
 }
 
+// overlaps.pow(6.0) (tal_assigner.py:107) as three float64 multiplications: <= 2 ulp from a correctly rounded pow, which is
+// what CUDA's pow() guarantees too, at a hundredth of its cost (pow was 45 of the top-k kernel's 57 us)
+__device__ __forceinline__ double pow6(double x) {
+  const double x2 = __dmul_rn(x, x);
+  return __dmul_rn(__dmul_rn(x2, x2), x2);
+}
+
 // prediction box of anchor a in pixels: fp32 (stride units) x fp32 stride, as `pred_bboxes.detach() * stride_tensor`
 __device__ __forceinline__ void pred_box_px(const LossParams& p, int b, int a, float stride, float* o) {
   const float4 v = *reinterpret_cast<const float4*>(p.boxes + (static_cast<size_t>(b) * p.A + a) * 4);
@@ -126,9 +136,17 @@ __global__ void __launch_bounds__(256) loss_targets_kernel(const LossParams p) {
     p.pos_align[i] = 0ull;
     p.pos_ovl[i] = 0ull;
   }
-  if (threadIdx.x < 2) p.counters[threadIdx.x] = 0;
+  if (threadIdx.x < 4) p.counters[threadIdx.x] = 0;
   __syncthreads();
   const double scale = static_cast<double>(p.img);
+  __shared__ int16_t s_img[4096];  // image index of every row (the slot count below is O(T^2) reads)
+  const bool staged = p.T <= 4096;
+  if (staged)
+    for (int t = threadIdx.x; t < p.T; t += blockDim.x) {
+      const int b = static_cast<int>(p.targets[static_cast<size_t>(t) * 6]);
+      s_img[t] = static_cast<int16_t>(b < 0 || b >= p.B ? -1 : b);
+    }
+  __syncthreads();
   for (int t = threadIdx.x; t < p.T; t += blockDim.x) {
     const float* r = p.targets + static_cast<size_t>(t) * 6;
     const int b = static_cast<int>(r[0]);
@@ -137,7 +155,11 @@ __global__ void __launch_bounds__(256) loss_targets_kernel(const LossParams p) {
       continue;
     }
     int slot = 0;
-    for (int u = 0; u < t; ++u) slot += static_cast<int>(p.targets[static_cast<size_t>(u) * 6]) == b;
+    if (staged) {
+      for (int u = 0; u < t; ++u) slot += s_img[u] == b;
+    } else {
+      for (int u = 0; u < t; ++u) slot += static_cast<int>(p.targets[static_cast<size_t>(u) * 6]) == b;
+    }
     if (slot >= p.G) {
       atomicAdd(p.counters + 1, 1);
       continue;
@@ -194,14 +216,17 @@ __global__ void __launch_bounds__(256) loss_decode_kernel(const LossParams p) {
   const Anchor an = anchor_of(p, a);
   const float c = (side & 1) ? an.py / an.stride : an.px / an.stride;  // anchor_points / stride_tensor (exact)
   p.boxes[i] = side < 2 ? c - e : c + e;
+  if (p.grad_distri) {
+    // zero d loss / d pred_distri here (68 floats = 17 float4 per anchor, spread over its four lanes): the box kernel
+    // then stores foreground rows only, ~1 % of the anchors
+    float4* g4 = reinterpret_cast<float4*>(p.grad_distri + (i >> 2) * (4 * kRegBins));
+    for (int q = side; q < kRegBins; q += 4) g4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
 }
 
 // ---- 3. top-13 anchors per box ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) tal_topk_kernel(const LossParams p) {
-  extern __shared__ double s_metric[];  // [A]
-  __shared__ double s_val[8];
-  __shared__ int s_idx[8];
-  __shared__ int s_win;
+  extern __shared__ double s_metric[];  // [A] candidate metrics (67 KB at 8400 anchors: three CTAs per SM, one wave for 16 x 20 boxes)
   pdl_launch_dependents();
   pdl_wait();
   const int g = blockIdx.x, b = blockIdx.y;
@@ -211,31 +236,88 @@ __global__ void __launch_bounds__(256) tal_topk_kernel(const LossParams p) {
   int label = static_cast<int>(static_cast<long long>(gt[0]));
   label = label < 0 ? 0 : (label >= p.nc ? p.nc - 1 : label);  // memory safety only: real boxes carry valid classes
   const float* score = p.pred_scores + static_cast<size_t>(b) * p.A * p.nc + label;
-  for (int a = threadIdx.x; a < p.A; a += blockDim.x) {
-    const Anchor an = anchor_of(p, a);
-    const double ax = an.px, ay = an.py;
-    // centre strictly inside the box (assigner_utils.py:25-45)
-    const double dmin = fmin(fmin(__dsub_rn(ax, gb[0]), __dsub_rn(ay, gb[1])), fmin(__dsub_rn(gb[2], ax), __dsub_rn(gb[3], ay)));
-    double m = 0.0;
-    if (dmin > kTalEps) {
-      float pb[4];
-      pred_box_px(p, b, a, an.stride, pb);
-      const double iou = iou_gt_pred(gb, pb[0], pb[1], pb[2], pb[3]);
-      m = __dmul_rn(static_cast<double>(score[static_cast<size_t>(a) * p.nc]), pow(iou, 6.0));  // tal_assigner.py:107
+  // Anchors whose centre can lie inside the box form one rectangle of cells per level: enumerate those (one cell of
+  // margin; the exact float64 test of assigner_utils.py:25-45 decides) instead of all A anchors — ~300 instead of 8400
+  // for a 100-pixel box, for the metric pass AND for each of the 13 selection rounds.
+  int n_l[3] = {p.n0, p.n1, p.n2}, x_lo[3], y_lo[3], nx[3], cnt[4];
+  cnt[0] = 0;
+#pragma unroll
+  for (int l = 0; l < 3; ++l) {
+    const double st = static_cast<double>(8 << l);
+    int xl = static_cast<int>(floor(gb[0] / st - 0.5)) - 1, xh = static_cast<int>(ceil(gb[2] / st - 0.5)) + 1;
+    int yl = static_cast<int>(floor(gb[1] / st - 0.5)) - 1, yh = static_cast<int>(ceil(gb[3] / st - 0.5)) + 1;
+    xl = xl < 0 ? 0 : xl;
+    yl = yl < 0 ? 0 : yl;
+    xh = xh > n_l[l] - 1 ? n_l[l] - 1 : xh;
+    yh = yh > n_l[l] - 1 ? n_l[l] - 1 : yh;
+    x_lo[l] = xl;
+    y_lo[l] = yl;
+    nx[l] = xh >= xl ? xh - xl + 1 : 0;
+    const int ny = yh >= yl ? yh - yl + 1 : 0;
+    cnt[l + 1] = cnt[l] + nx[l] * ny;
+  }
+  const int n_cand = cnt[3];
+  auto cand_anchor = [&](int i) {  // candidate number -> anchor index (level-major, row-major)
+    const int l = i < cnt[1] ? 0 : (i < cnt[2] ? 1 : 2);
+    const int local = i - cnt[l];
+    const int cy = y_lo[l] + local / nx[l], cx = x_lo[l] + local % nx[l];
+    return (l > 0 ? p.n0 * p.n0 : 0) + (l > 1 ? p.n1 * p.n1 : 0) + cy * n_l[l] + cx;
+  };
+  // four candidates per thread and pass: all global loads (box, score) of the four are issued before the first float64
+  // division consumes one (the pass is bound by cold L2 / DRAM round trips, not by arithmetic)
+  for (int i0 = threadIdx.x; i0 < n_cand; i0 += 4 * blockDim.x) {
+    bool inside[4];
+    float4 box4[4];
+    float sc4[4], stride4[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * blockDim.x;
+      inside[u] = false;
+      if (i < n_cand) {
+        const int a = cand_anchor(i);
+        const Anchor an = anchor_of(p, a);
+        const double ax = an.px, ay = an.py;
+        // centre strictly inside the box (assigner_utils.py:25-45)
+        const double dmin = fmin(fmin(__dsub_rn(ax, gb[0]), __dsub_rn(ay, gb[1])), fmin(__dsub_rn(gb[2], ax), __dsub_rn(gb[3], ay)));
+        stride4[u] = an.stride;
+        inside[u] = dmin > kTalEps;
+        if (inside[u]) {
+          box4[u] = *reinterpret_cast<const float4*>(p.boxes + (static_cast<size_t>(b) * p.A + a) * 4);
+          sc4[u] = score[static_cast<size_t>(a) * p.nc];
+        }
+      }
     }
-    s_metric[a] = m;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i < n_cand) {
+        double m = 0.0;
+        if (inside[u]) {  // pred_bboxes.detach() * stride_tensor in fp32, then the float64 IoU
+          const double iou = iou_gt_pred(gb, __fmul_rn(box4[u].x, stride4[u]), __fmul_rn(box4[u].y, stride4[u]),
+                                         __fmul_rn(box4[u].z, stride4[u]), __fmul_rn(box4[u].w, stride4[u]));
+          m = __dmul_rn(static_cast<double>(sc4[u]), pow6(iou));  // tal_assigner.py:107
+        }
+        s_metric[i] = m;
+      }
+    }
   }
   __syncthreads();
+  // 13 rounds of block-wide arg-max over the candidates (ties go to the earlier candidate).  A variant in which every warp
+  // first extracts the top 13 of its own slice with shuffles only and warp 0 merges the 8 short lists measured slower
+  // (37 vs 33 us for 16 x 20 boxes): the rounds are short, the kernel's time is the largest box's CTA.
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ double s_val[8];
+  __shared__ int s_idx[8];
+  __shared__ int s_win;
   uint8_t* pos = p.pos + (static_cast<size_t>(b) * p.G + g) * p.A;
   for (int round = 0; round < kTopK; ++round) {
     double best = -1.0;
     int bi = 0x7fffffff;
-    for (int a = threadIdx.x; a < p.A; a += blockDim.x) {
-      const double v = s_metric[a];
-      if (v > best) {  // strictly greater: the smallest index wins among equals (indices ascend per thread)
+    for (int i = threadIdx.x; i < n_cand; i += blockDim.x) {
+      const double v = s_metric[i];
+      if (v > best) {  // strictly greater: the earliest candidate wins among equals
         best = v;
-        bi = a;
+        bi = i;
       }
     }
 #pragma unroll
@@ -263,7 +345,7 @@ __global__ void __launch_bounds__(256) tal_topk_kernel(const LossParams p) {
       // a metric of exactly 0 is an anchor outside the box (or a zero score): mask_in_gts drops it whichever of the
       // tied zeros torch.topk would have returned
       if (v > 0.0) {
-        pos[wi] = 1;
+        pos[cand_anchor(wi)] = 1;
         s_metric[wi] = -1.0;
         s_win = 1;
       } else {
@@ -319,7 +401,7 @@ __global__ void __launch_bounds__(256) tal_resolve_kernel(const LossParams p) {
   if (lab < 0) lab += p.nc;  // pd_scores[..., -1] of a padding row (tal_assigner.py:101-104); cannot win with IoU 0
   if (lab < 0 || lab >= p.nc) lab = 0;
   const double sc = p.pred_scores[ba * p.nc + lab];
-  const double align = __dmul_rn(sc, pow(iou, 6.0));
+  const double align = __dmul_rn(sc, pow6(iou));
   p.gt_idx[ba] = gs;
   p.fg[ba] = 1;
   p.align_a[ba] = align;
@@ -342,7 +424,25 @@ __device__ __forceinline__ double block_sum_256(double v, double* s_red /* [8] *
   return t;
 }
 
-// ---- 5. normalised target scores (tal_assigner.py:66-72) + sum ---------------------------------------------------------------
+// ---- 5. normalised target scores (tal_assigner.py:66-72), class of every anchor, target_scores_sum -------------------------
+// sums partial[0..n) in a fixed order
+__device__ __forceinline__ double reduce_partials(const double* part, int n, double* s_red) {
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) acc += part[i];
+  return block_sum_256(acc, s_red);
+}
+
+// true in exactly one block: the one that finishes last (its view of the other blocks' partial sums is complete)
+__device__ __forceinline__ bool last_block_done(int32_t* counter, int n_blocks) {
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(counter, 1) == n_blocks - 1;
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last != 0;
+}
+
 __global__ void __launch_bounds__(256) tal_norm_kernel(const LossParams p) {
   __shared__ double s_red[8];
   pdl_launch_dependents();
@@ -351,75 +451,89 @@ __global__ void __launch_bounds__(256) tal_norm_kernel(const LossParams p) {
   double acc = 0.0;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     double v = 0.0;
+    int tl = -1;
     if (p.fg[i]) {
       const int b = static_cast<int>(i / p.A);
       const int gs = p.gt_idx[i];
       const double pa = __longlong_as_double(static_cast<long long>(p.pos_align[b * p.G + gs]));
       const double po = __longlong_as_double(static_cast<long long>(p.pos_ovl[b * p.G + gs]));
       v = __ddiv_rn(__dmul_rn(p.align_a[i], po), __dadd_rn(pa, kTalEps));
+      const long long lab = static_cast<long long>(p.gt[(static_cast<size_t>(b) * p.G + gs) * 5]);
+      tl = lab < 0 ? 0 : static_cast<int>(lab);  // tal_assigner.py:143
     }
     p.norm[i] = v;
+    p.tlabel[i] = tl;
     acc += v;
   }
   const double t = block_sum_256(acc, s_red);
   if (threadIdx.x == 0) p.partial[blockIdx.x] = t;
-}
-
-// sums partial[which][0..n) in a fixed order into scalars[dst]
-__device__ __forceinline__ double reduce_partials(const double* part, int n, double* s_red) {
-  double acc = 0.0;
-  for (int i = threadIdx.x; i < n; i += 256) acc += part[i];
-  return block_sum_256(acc, s_red);
-}
-
-__global__ void __launch_bounds__(256) loss_tss_kernel(const LossParams p, int n_part) {
-  __shared__ double s_red[8];
-  pdl_launch_dependents();
-  pdl_wait();
-  const double t = reduce_partials(p.partial, n_part, s_red);
-  if (threadIdx.x == 0) p.scalars[4] = t;
+  if (last_block_done(p.counters + 2, gridDim.x)) {  // fixed-order sum whichever block comes last
+    const double tss = reduce_partials(p.partial, gridDim.x, s_red);
+    if (threadIdx.x == 0) p.scalars[4] = tss;
+  }
 }
 
 // ---- 6. varifocal loss (loss.py:181-192) + gradient ---------------------------------------------------------------------------
+struct VflOut {
+  double term;
+  float grad;
+};
+// one class probability `pr`; `t` = normalised target score if this is the anchor's assigned class, else nullptr semantics
+__device__ __forceinline__ VflOut vfl_one(float pr, bool is_t, double t, double inv_tss) {
+  const float l1 = fmaxf(log1pf(-pr), -100.0f);                // BCE's clamp
+  const float den = fmaxf((1.0f - pr) * pr, 1e-12f);           // BCE backward's clamp
+  VflOut o;
+  double grad = 0.0;
+  if (is_t) {
+    const float l2 = fmaxf(logf(pr), -100.0f);
+    const float t32 = static_cast<float>(t);
+    const float bce = (t32 - 1.0f) * l1 - t32 * l2;
+    o.term = static_cast<double>(bce) * t;                     // weight = gt_score on the assigned class
+    grad = t * static_cast<double>((pr - t32) / den);
+  } else {
+    const float w = 0.75f * (pr * pr);                         // alpha * p^gamma on every other class
+    const float bce = -l1;                                     // (0 - 1) * l1 - 0 * l2
+    o.term = static_cast<double>(bce) * static_cast<double>(w);
+    o.grad = (w * (pr / den) + bce * (1.5f * pr)) * static_cast<float>(inv_tss);  // fp32 like the reference's backward
+    return o;
+  }
+  o.grad = static_cast<float>(grad * inv_tss);                 // loss weight 'class' = 1.0
+  return o;
+}
+
+template <bool kVec4>
 __global__ void __launch_bounds__(256) loss_vfl_kernel(const LossParams p) {
   __shared__ double s_red[8];
   pdl_launch_dependents();
   pdl_wait();
-  const double tss = p.scalars[4];
-  const size_t n = static_cast<size_t>(p.B) * p.A * p.nc;
+  const double inv_tss = 1.0 / p.scalars[4];
   double acc = 0.0;
-  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const size_t row = i / p.nc;
-    const int c = static_cast<int>(i - row * p.nc);
-    const float pr = p.pred_scores[i];
-    bool is_t = false;
-    double t = 0.0;
-    if (p.fg[row]) {
-      const int b = static_cast<int>(row / p.A);
-      const double* gt = p.gt + (static_cast<size_t>(b) * p.G + p.gt_idx[row]) * 5;
-      long long lab = static_cast<long long>(gt[0]);
-      if (lab < 0) lab = 0;  // tal_assigner.py:143
-      if (lab == c) {
-        is_t = true;
-        t = p.norm[row];
-      }
+  if (kVec4) {
+    const unsigned per_row = p.nc >> 2;
+    const size_t n4 = static_cast<size_t>(p.B) * p.A * per_row;
+    const float4* in4 = reinterpret_cast<const float4*>(p.pred_scores);
+    float4* out4 = reinterpret_cast<float4*>(p.grad_scores);
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+      const size_t row = i / per_row;
+      const int c0 = static_cast<int>(i - row * per_row) << 2;
+      const float4 v = in4[i];
+      const int tl = p.tlabel[row];
+      const double t = tl >= 0 ? p.norm[row] : 0.0;
+      const VflOut a0 = vfl_one(v.x, tl == c0, t, inv_tss), a1 = vfl_one(v.y, tl == c0 + 1, t, inv_tss);
+      const VflOut a2 = vfl_one(v.z, tl == c0 + 2, t, inv_tss), a3 = vfl_one(v.w, tl == c0 + 3, t, inv_tss);
+      acc += (a0.term + a1.term) + (a2.term + a3.term);
+      if (out4) out4[i] = make_float4(a0.grad, a1.grad, a2.grad, a3.grad);
     }
-    const float l1 = fmaxf(log1pf(-pr), -100.0f), l2 = fmaxf(logf(pr), -100.0f);  // BCE's clamp
-    const float den = fmaxf((1.0f - pr) * pr, 1e-12f);                            // BCE backward's clamp
-    double term, grad;
-    if (is_t) {
-      const float t32 = static_cast<float>(t);
-      const float bce = (t32 - 1.0f) * l1 - t32 * l2;
-      term = static_cast<double>(bce) * t;
-      grad = t * static_cast<double>((pr - t32) / den);
-    } else {
-      const float w = 0.75f * (pr * pr);
-      const float bce = -l1 - 0.0f * l2;
-      term = static_cast<double>(bce) * static_cast<double>(w);
-      grad = static_cast<double>(w) * static_cast<double>(pr / den) + static_cast<double>(bce) * static_cast<double>(1.5f * pr);
+  } else {
+    const size_t n = static_cast<size_t>(p.B) * p.A * p.nc;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+      const size_t row = i / p.nc;
+      const int c = static_cast<int>(i - row * p.nc);
+      const int tl = p.tlabel[row];
+      const VflOut a = vfl_one(p.pred_scores[i], tl == c, tl >= 0 ? p.norm[row] : 0.0, inv_tss);
+      acc += a.term;
+      if (p.grad_scores) p.grad_scores[i] = a.grad;
     }
-    acc += term;
-    if (p.grad_scores) p.grad_scores[i] = static_cast<float>(grad / tss);  // loss weight 'class' = 1.0
   }
   const double t = block_sum_256(acc, s_red);
   if (threadIdx.x == 0) p.partial[kMaxPartials + blockIdx.x] = t;
@@ -445,12 +559,17 @@ __global__ void __launch_bounds__(256) loss_box_kernel(const LossParams p) {
   pdl_wait();
   const double tss = p.scalars[4];
   const size_t n = static_cast<size_t>(p.B) * p.A * 4;
-  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // (b, a, side); a quad = one anchor
   double iou_term = 0.0, dfl_term = 0.0;
+  // (anchor, side) items in blocks of 256, dealt round-robin to the CTAs; every thread of a CTA runs the same number of
+  // rounds (the quad shuffles need whole warps); a warp without a foreground lane skips the round after one byte load
+  const size_t chunks = (n + 255) / 256;
+  for (size_t chunk = blockIdx.x; chunk < chunks; chunk += gridDim.x) {
+  const size_t i = chunk * 256 + threadIdx.x;  // (b, a, side); a quad = one anchor
   const bool in_range = i < n;
   const size_t row = in_range ? (i >> 2) : 0;
   const int side = static_cast<int>(i & 3);
   const bool fg = in_range && p.fg[row];
+  if (!__any_sync(0xffffffffu, fg)) continue;
   // quads never straddle a warp and n % 4 == 0, so the shuffles below see whole anchors; lanes of background anchors run
   // the arithmetic on zeros and store nothing but zero gradients
   float prob[kRegBins];
@@ -499,7 +618,7 @@ __global__ void __launch_bounds__(256) loss_box_kernel(const LossParams p) {
     const Dual hull = cw * ch + eps;
     const Dual loss = dk(1.0) - (iou - (hull - uni) / hull);
     g_coord = loss.d;
-    if (side == 0) iou_term = loss.v * bw;  // one lane per anchor contributes the value
+    if (side == 0) iou_term += loss.v * bw;  // one lane per anchor contributes the value
     // DFL (loss.py:243-254): target distance of this side, clipped to [0, reg_max - 0.01] (general.py:43-49)
     const double csd = static_cast<double>(cs);
     double tgt = side < 2 ? csd - tbx[side] : tbx[side] - csd;
@@ -514,7 +633,7 @@ __global__ void __launch_bounds__(256) loss_box_kernel(const LossParams p) {
   double ce4 = dfl_ce;
   ce4 += __shfl_xor_sync(0xffffffffu, ce4, 1);
   ce4 += __shfl_xor_sync(0xffffffffu, ce4, 2);
-  if (fg && side == 0) dfl_term = (ce4 / 4.0) * bw;
+  if (fg && side == 0) dfl_term += (ce4 / 4.0) * bw;
   if (p.grad_distri && in_range) {
     float* go = p.grad_distri + i * kRegBins;
     if (fg) {
@@ -528,47 +647,40 @@ __global__ void __launch_bounds__(256) loss_box_kernel(const LossParams p) {
         gj += g_dfl * (pj - (j == tl ? wl : 0.0) - (j == tl + 1 ? wr : 0.0));
         go[j] = static_cast<float>(gj);
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < kRegBins; ++j) go[j] = 0.0f;
-    }
+    }  // background rows were zeroed by decode_kernel (or by the host's memset when the caller supplied the boxes)
   }
+  }  // chunk
   const double ti = block_sum_256(iou_term, s_red);
   const double td = block_sum_256(dfl_term, s_red);
   if (threadIdx.x == 0) {
     p.partial[2 * kMaxPartials + blockIdx.x] = ti;
     p.partial[3 * kMaxPartials + blockIdx.x] = td;
   }
-}
-
-// ---- 8. totals (loss.py:145-162) --------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) loss_final_kernel(const LossParams p, int n_vfl, int n_box) {
-  __shared__ double s_red[8];
-  pdl_launch_dependents();
-  pdl_wait();
-  const double cls = reduce_partials(p.partial + kMaxPartials, n_vfl, s_red);
-  const double iou = reduce_partials(p.partial + 2 * kMaxPartials, n_box, s_red);
-  const double dfl = reduce_partials(p.partial + 3 * kMaxPartials, n_box, s_red);
-  if (threadIdx.x == 0) {
-    const double tss = p.scalars[4];
-    const int num_fg = p.counters[0];
-    const double l_cls = cls / tss;                      // inf / nan without a single foreground anchor, as the reference
-    const double l_iou = num_fg > 0 ? iou / tss : 0.0;   // loss.py:205,238-240
-    const double l_dfl = num_fg > 0 ? dfl / tss : 0.0;
-    p.scalars[0] = 1.0 * l_cls + 2.5 * l_iou + 0.5 * l_dfl;
-    p.scalars[1] = 2.5 * l_iou;
-    p.scalars[2] = 0.5 * l_dfl;
-    p.scalars[3] = 1.0 * l_cls;
-    p.scalars[5] = static_cast<double>(num_fg);
-    p.scalars[6] = static_cast<double>(p.counters[1]);
-    p.scalars[7] = 0.0;
+  // ---- totals (loss.py:145-162) by whichever block finishes last, always in the same order ---------------------------------
+  if (last_block_done(p.counters + 3, gridDim.x)) {
+    const double cls = reduce_partials(p.partial + kMaxPartials, p.n_vfl, s_red);
+    const double iou = reduce_partials(p.partial + 2 * kMaxPartials, gridDim.x, s_red);
+    const double dfl = reduce_partials(p.partial + 3 * kMaxPartials, gridDim.x, s_red);
+    if (threadIdx.x == 0) {
+      const int num_fg = p.counters[0];
+      const double l_cls = cls / tss;                      // inf / nan without a single foreground anchor, as the reference
+      const double l_iou = num_fg > 0 ? iou / tss : 0.0;   // loss.py:205,238-240
+      const double l_dfl = num_fg > 0 ? dfl / tss : 0.0;
+      p.scalars[0] = 1.0 * l_cls + 2.5 * l_iou + 0.5 * l_dfl;
+      p.scalars[1] = 2.5 * l_iou;
+      p.scalars[2] = 0.5 * l_dfl;
+      p.scalars[3] = 1.0 * l_cls;
+      p.scalars[5] = static_cast<double>(num_fg);
+      p.scalars[6] = static_cast<double>(p.counters[1]);
+      p.scalars[7] = 0.0;
+    }
   }
 }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct LossLayout {
-  size_t gt, mask_gt, pos, boxes, gt_idx, fg, align_a, ovl_a, norm, pos_align, pos_ovl, partial, scalars, counters, total;
+  size_t gt, mask_gt, pos, boxes, gt_idx, fg, align_a, ovl_a, norm, tlabel, pos_align, pos_ovl, partial, scalars, counters, total;
 };
 static LossLayout loss_layout(size_t B, size_t A, size_t G) {
   LossLayout l;
@@ -587,11 +699,12 @@ static LossLayout loss_layout(size_t B, size_t A, size_t G) {
   l.align_a = take(B * A * 8);
   l.ovl_a = take(B * A * 8);
   l.norm = take(B * A * 8);
+  l.tlabel = take(B * A * 4);
   l.pos_align = take(B * G * 8);
   l.pos_ovl = take(B * G * 8);
   l.partial = take(static_cast<size_t>(4) * kMaxPartials * 8);
   l.scalars = take(8 * 8);
-  l.counters = take(2 * 4);
+  l.counters = take(4 * 4);
   l.total = o;
   return l;
 }
@@ -618,7 +731,7 @@ extern "C" int32_t mafb200_detect_loss(const float* pred_scores, const float* pr
   const int n0 = img_size / 8, n1 = img_size / 16, n2 = img_size / 32;
   const int A = n0 * n0 + n1 * n1 + n2 * n2;
   const int G = gt_cap > 0 ? gt_cap : 1;  // gt_cap 0: one padding row per image (no foreground; the reference's early return)
-  const size_t topk_smem = static_cast<size_t>(A) * 8;
+  const size_t topk_smem = static_cast<size_t>(A) * 8;  // one float64 metric per candidate (<= A)
   if (topk_smem > 200 * 1024) return fail(MAF_E_ARG, "detect_loss: %d anchors need %zu B of shared memory", A, topk_smem);
   if ((reinterpret_cast<uintptr_t>(pred_scores) | reinterpret_cast<uintptr_t>(pred_distri) | reinterpret_cast<uintptr_t>(workspace)) & 15)
     return fail(MAF_E_ALIGN, "detect_loss: predictions / workspace must be 16-B aligned");
@@ -658,11 +771,17 @@ extern "C" int32_t mafb200_detect_loss(const float* pred_scores, const float* pr
   p.partial = reinterpret_cast<double*>(ws + l.partial);
   p.scalars = scalars_out;
   p.counters = reinterpret_cast<int32_t*>(ws + l.counters);
+  p.tlabel = reinterpret_cast<int32_t*>(ws + l.tlabel);
   p.grad_scores = grad_scores;
   p.grad_distri = grad_distri;
   if (boxes_override && (reinterpret_cast<uintptr_t>(boxes_override) & 15)) return fail(MAF_E_ALIGN, "detect_loss: boxes must be 16-B aligned");
+  if ((reinterpret_cast<uintptr_t>(grad_scores) | reinterpret_cast<uintptr_t>(grad_distri)) & 15)
+    return fail(MAF_E_ALIGN, "detect_loss: gradients must be 16-B aligned");
 
   if (cudaMemsetAsync(p.pos, 0, static_cast<size_t>(batch) * G * A, st) != cudaSuccess)
+    return fail(MAF_E_CUDA, "detect_loss: cudaMemsetAsync failed");
+  if (boxes_override && grad_distri &&  // decode_kernel (skipped then) is what zeroes the background rows
+      cudaMemsetAsync(grad_distri, 0, static_cast<size_t>(batch) * A * 4 * kRegBins * sizeof(float), st) != cudaSuccess)
     return fail(MAF_E_CUDA, "detect_loss: cudaMemsetAsync failed");
   {
     static SmemOptIn opt_in;
@@ -676,18 +795,19 @@ extern "C" int32_t mafb200_detect_loss(const float* pred_scores, const float* pr
     if (b > kMaxPartials) b = kMaxPartials;
     return static_cast<int>(b);
   };
-  const int n_norm = blocks_for(rows, 4), n_vfl = blocks_for(rows * num_classes, 8);
-  const size_t box_blocks = (rows * 4 + 255) / 256;  // one thread per (anchor, side), no grid stride
-  if (box_blocks > static_cast<size_t>(kMaxPartials))
-    return fail(MAF_E_ARG, "detect_loss: batch x anchors = %zu too large (%zu box blocks > %d)", rows, box_blocks, kMaxPartials);
+  const int n_norm = blocks_for(rows, 4), n_vfl = blocks_for(rows * num_classes, 16);
+  p.n_vfl = n_vfl;
+  size_t box_blocks = (rows * 4 + 255) / 256;  // chunks of 256 (anchor, side) items, dealt round-robin
+  if (box_blocks > 1184) box_blocks = 1184;     // 8 CTAs on each of 148 SMs
   launch_pdl(loss_targets_kernel, dim3(1), dim3(256), 0, st, p);
   if (!boxes_override) launch_pdl(loss_decode_kernel, dim3(static_cast<unsigned>((rows * 4 + 255) / 256)), dim3(256), 0, st, p);
   launch_pdl(tal_topk_kernel, dim3(G, batch), dim3(256), topk_smem, st, p);
   launch_pdl(tal_resolve_kernel, dim3((A + 255) / 256, batch), dim3(256), 0, st, p);
   launch_pdl(tal_norm_kernel, dim3(n_norm), dim3(256), 0, st, p);
-  launch_pdl(loss_tss_kernel, dim3(1), dim3(256), 0, st, p, n_norm);
-  launch_pdl(loss_vfl_kernel, dim3(n_vfl), dim3(256), 0, st, p);
+  if (num_classes % 4 == 0)
+    launch_pdl(loss_vfl_kernel<true>, dim3(n_vfl), dim3(256), 0, st, p);
+  else
+    launch_pdl(loss_vfl_kernel<false>, dim3(n_vfl), dim3(256), 0, st, p);
   launch_pdl(loss_box_kernel, dim3(static_cast<unsigned>(box_blocks)), dim3(256), 0, st, p);
-  launch_pdl(loss_final_kernel, dim3(1), dim3(256), 0, st, p, n_vfl, static_cast<int>(box_blocks));
   return check_launch("detect_loss kernels");
 }
