@@ -294,14 +294,17 @@ MAFB200_API int32_t mafb200_scale_detections(const float* det, const int32_t* co
  *   grad_scores / grad_distri  optional fp32 [B,A,nc] / [B,A,68]: d loss / d pred_scores, d loss / d pred_distri
  *   out_gt_idx / out_fg / out_target_score  optional [B,A] int32 / uint8 / double: the assignment (target_gt_idx,
  *                fg_mask, and the one non-zero entry of each row of target_scores)
+ *   assigner     MAF_ASSIGN_TAL or MAF_ASSIGN_ATSS (warm-up: target scores = IoU with the predicted box, fp32 as the reference)
  * Nothing allocates or synchronises; all kernels are enqueued on `stream`. */
+#define MAF_ASSIGN_TAL 0  /* TaskAlignedAssigner(topk=13, alpha=1, beta=6): epoch_num >= warmup_epoch (loss.py:92-100) */
+#define MAF_ASSIGN_ATSS 1 /* ATSSAssigner(topk=9), yolov6/assigners/atss_assigner.py:17-87: the warm-up epochs (loss.py:83-91) */
 MAFB200_API size_t mafb200_loss_workspace_bytes(int32_t batch, int32_t anchors, int32_t gt_cap);
 MAFB200_API int32_t mafb200_detect_loss(const float* pred_scores, const float* pred_distri, const float* targets,
                                         int32_t num_targets, int32_t batch, int32_t img_size, int32_t num_classes,
                                         int32_t gt_cap, const float* boxes_override, void* workspace,
                                         size_t workspace_bytes, double* scalars_out, float* grad_scores,
                                         float* grad_distri, int32_t* out_gt_idx, uint8_t* out_fg,
-                                        double* out_target_score, void* stream);
+                                        double* out_target_score, int32_t assigner, void* stream);
 
 MAFB200_API int64_t mafb200_launch_count(void);
 

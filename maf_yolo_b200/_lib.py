@@ -95,7 +95,7 @@ _SIGNATURES = {
     "mafb200_loss_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "mafb200_detect_loss": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                         C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
-                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "mafb200_launch_count": (C.c_int64, []),
 }
 DETECT_CFG_BYTES = 16 + 256  # sizeof(maf_detect_cfg)

@@ -1,7 +1,8 @@
-// K10 — training-side kernels: task-aligned label assignment + varifocal / GIoU / DFL loss, forward
-// value AND the gradients w.r.t. the head outputs, for the reference's `ComputeLoss.__call__` after its warm-up epochs
-// (yolov6/models/loss.py:56-162 with formal_assigner = TaskAlignedAssigner(topk=13, alpha=1, beta=6),
-// yolov6/assigners/tal_assigner.py:22-151, assigner_utils.py:25-89, figure_iou.py:27-65, general.py:29-49).
+// K10 — training-side kernels: label assignment + varifocal / GIoU / DFL loss, forward value AND the
+// gradients w.r.t. the head outputs, for the reference's `ComputeLoss.__call__` (yolov6/models/loss.py:56-162): formal_assigner =
+// TaskAlignedAssigner(topk=13, alpha=1, beta=6) (yolov6/assigners/tal_assigner.py:22-151, assigner_utils.py:25-89) and, while
+// epoch_num < warmup_epoch, warmup_assigner = ATSSAssigner(9) (atss_assigner.py:17-161, iou2d_calculator.py:201-242);
+// figure_iou.py:27-65, general.py:29-49.
 //
 // The reference materialises [B, G, 8400] float64 tensors five times over (IoU, metric, in-box mask, top-k one-hot with
 // 8400 classes, ...: the "OOM RuntimeError ... CPU mode" branch of loss.py:95-133) and loops over the targets in
@@ -9,7 +10,8 @@
 //
 //   targets_kernel   [T,6] fp32 rows -> padded [B,G,5] float64 (class, xyxy pixels), original order kept
 //   decode_kernel    DFL softmax-expectation -> boxes [B,A,4] fp32 in stride units      (4 lanes per anchor)
-//   topk_kernel      one CTA per (image, box): IoU / in-box test / alignment metric of all A anchors into shared memory,
+//   atss_select      (warm-up) one warp per (image, box): 9 closest anchor centres per level, mean + std IoU threshold -> pos
+//   topk_kernel      (formal) one CTA per (image, box): IoU / in-box test / alignment metric of all A anchors into shared memory,
 //                    13 rounds of block arg-max -> byte map pos[B,G,A]
 //   resolve_kernel   one thread per anchor: boxes that claim it; more than one -> the box with the highest IoU over ALL
 //                    boxes; atomicMax of the per-box normalisers (non-negative float64 as uint64)
@@ -60,6 +62,7 @@ struct LossParams {
   double* scalars;           // [8]: loss, 2.5 iou, 0.5 dfl, cls, tss, num_fg, target overflow, (spare)
   int32_t* counters;         // [4]: num_fg, target overflow, blocks done (norm stage), blocks done (box stage)
   int32_t* tlabel;           // [B,A] class of the assigned box, -1 on background anchors
+  int32_t atss;              // 1: warm-up (ATSS) assigner instead of the task-aligned one
   int32_t n_vfl;             // blocks of the varifocal kernel (its partial sums are folded by the box kernel's last block)
   float* grad_scores;        // optional [B,A,nc]
   float* grad_distri;        // optional [B,A,68]
@@ -103,6 +106,20 @@ __device__ __forceinline__ double iou_gt_pred(const double* g, float fx1, float 
   const double area1 = __dmul_rn(clip0(__dsub_rn(g[2], g[0])), clip0(__dsub_rn(g[3], g[1])));
   const double area2 = __fmul_rn(fmaxf(__fsub_rn(fx2, fx1), 0.0f), fmaxf(__fsub_rn(fy2, fy1), 0.0f));
   const double uni = __dadd_rn(__dsub_rn(__dadd_rn(area1, area2), overlap), kTalEps);
+  return __ddiv_rn(overlap, uni);
+}
+
+// iou2d_calculator.py:201-242 (mode 'iou'): ground truth (float64) against an ANCHOR box (fp32, a 5-stride square around the
+// anchor point: anchor_generator.py:32-41) — the ATSS assigner's overlaps.  No clamp on the areas, union floored at 1e-6.
+__device__ __forceinline__ double iou_gt_anchor(const double* g, float acx, float acy, float stride) {
+  const float half = __fmul_rn(__fmul_rn(5.0f, stride), 0.5f);
+  const float fx1 = __fsub_rn(acx, half), fy1 = __fsub_rn(acy, half), fx2 = __fadd_rn(acx, half), fy2 = __fadd_rn(acy, half);
+  const double area1 = __dmul_rn(__dsub_rn(g[2], g[0]), __dsub_rn(g[3], g[1]));
+  const double area2 = __fmul_rn(__fsub_rn(fx2, fx1), __fsub_rn(fy2, fy1));
+  const double x1 = fmax(g[0], static_cast<double>(fx1)), y1 = fmax(g[1], static_cast<double>(fy1));
+  const double x2 = fmin(g[2], static_cast<double>(fx2)), y2 = fmin(g[3], static_cast<double>(fy2));
+  const double overlap = __dmul_rn(clip0(__dsub_rn(x2, x1)), clip0(__dsub_rn(y2, y1)));
+  const double uni = fmax(__dsub_rn(__dadd_rn(area1, area2), overlap), 1e-6);
   return __ddiv_rn(overlap, uni);
 }
 
@@ -357,6 +374,118 @@ __global__ void __launch_bounds__(256) tal_topk_kernel(const LossParams p) {
   }
 }
 
+// ---- 3b. ATSS warm-up assigner (atss_assigner.py:44-71): candidates of one box -------------------------------------------------
+// One warp per (image, box).  Per level the 9 anchor centres closest to the box centre (they always lie in the 9 x 9 window of
+// cells around the centre's cell, shifted into the grid at the borders); threshold = mean + unbiased std of the 27 candidates'
+// anchor-box IoUs; positives = candidates above it whose centre lies strictly inside the box.
+__global__ void __launch_bounds__(256) atss_select_kernel(const LossParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int pair = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (pair >= p.B * p.G) return;
+  if (!p.mask_gt[pair]) return;
+  const int b = pair / p.G;
+  const double* gt = p.gt + static_cast<size_t>(pair) * 5;
+  const double gb[4] = {gt[1], gt[2], gt[3], gt[4]};
+  const double gcx = __ddiv_rn(__dadd_rn(gb[0], gb[2]), 2.0), gcy = __ddiv_rn(__dadd_rn(gb[1], gb[3]), 2.0);  // assigner_utils.py:14-16
+  uint8_t* pos = p.pos + static_cast<size_t>(pair) * p.A;
+  const int n_l[3] = {p.n0, p.n1, p.n2};
+  // this lane's selected candidate of each level (lanes 0..8 hold the 9 picks of a level): anchor index and IoU
+  int sel_a[3] = {-1, -1, -1};
+  double sel_iou[3] = {0.0, 0.0, 0.0};
+  double sum = 0.0;
+  int n_sel = 0;
+  int level_off = 0;
+#pragma unroll
+  for (int l = 0; l < 3; ++l) {
+    const int n = n_l[l];
+    const float st = static_cast<float>(8 << l);
+    const int win = n < 9 ? n : 9;
+    int cx0 = static_cast<int>(floor(gcx / static_cast<double>(st))), cy0 = static_cast<int>(floor(gcy / static_cast<double>(st)));
+    cx0 = cx0 < 0 ? 0 : (cx0 > n - 1 ? n - 1 : cx0);
+    cy0 = cy0 < 0 ? 0 : (cy0 > n - 1 ? n - 1 : cy0);
+    int xs = cx0 - 4, ys = cy0 - 4;
+    xs = xs < 0 ? 0 : (xs > n - win ? n - win : xs);
+    ys = ys < 0 ? 0 : (ys > n - win ? n - win : ys);
+    // distances of the window's cells (3 per lane), assigner_utils.py:17-21: float64 centre - fp32 anchor centre
+    double d[3];
+    int ai[3];
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const int c = lane + 32 * u;
+      d[u] = INFINITY;
+      ai[u] = 0x7fffffff;
+      if (c < win * win) {
+        const int cy = ys + c / win, cx = xs + c % win;
+        const float acx = __fmul_rn(static_cast<float>(cx) + 0.5f, st), acy = __fmul_rn(static_cast<float>(cy) + 0.5f, st);
+        const double dx = __dsub_rn(gcx, static_cast<double>(acx)), dy = __dsub_rn(gcy, static_cast<double>(acy));
+        d[u] = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+        ai[u] = level_off + cy * n + cx;
+      }
+    }
+    const int k = win * win < 9 ? win * win : 9;
+    for (int r = 0; r < k; ++r) {
+      double best = d[0];
+      int bi = ai[0];
+#pragma unroll
+      for (int u = 1; u < 3; ++u)
+        if (d[u] < best || (d[u] == best && ai[u] < bi)) {
+          best = d[u];
+          bi = ai[u];
+        }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov < best || (ov == best && oi < bi)) {
+          best = ov;
+          bi = oi;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 3; ++u)
+        if (ai[u] == bi) d[u] = INFINITY;  // taken
+      if (lane == r) sel_a[l] = bi;
+    }
+    if (sel_a[l] >= 0) {
+      const int local = sel_a[l] - level_off;
+      const int cy = local / n, cx = local - cy * n;
+      sel_iou[l] = iou_gt_anchor(gb, __fmul_rn(static_cast<float>(cx) + 0.5f, st), __fmul_rn(static_cast<float>(cy) + 0.5f, st), st);
+      sum += sel_iou[l];
+      ++n_sel;
+    }
+    level_off += n * n;
+  }
+  // mean + unbiased std over all candidates of the box (atss_assigner.py:136-139)
+  double tot = sum;
+  int cnt = n_sel;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  const double mean = tot / static_cast<double>(cnt);
+  double ss = 0.0;
+#pragma unroll
+  for (int l = 0; l < 3; ++l)
+    if (sel_a[l] >= 0) ss += (sel_iou[l] - mean) * (sel_iou[l] - mean);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const double thr = mean + sqrt(ss / static_cast<double>(cnt - 1));
+  level_off = 0;
+#pragma unroll
+  for (int l = 0; l < 3; ++l) {
+    if (sel_a[l] >= 0 && sel_iou[l] > thr) {
+      const Anchor an = anchor_of(p, sel_a[l]);
+      const double ax = an.px, ay = an.py;
+      const double dmin = fmin(fmin(__dsub_rn(ax, gb[0]), __dsub_rn(ay, gb[1])), fmin(__dsub_rn(gb[2], ax), __dsub_rn(gb[3], ay)));
+      if (dmin > kTalEps) pos[sel_a[l]] = 1;
+    }
+  }
+  (void)b;
+}
+
 // ---- 4. one box per anchor ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) tal_resolve_kernel(const LossParams p) {
   pdl_launch_dependents();
@@ -386,13 +515,14 @@ __global__ void __launch_bounds__(256) tal_resolve_kernel(const LossParams p) {
     double best = -1.0;
     for (int g = 0; g < p.G; ++g) {
       const double* gt = p.gt + (static_cast<size_t>(b) * p.G + g) * 5;
-      const double v = iou_gt_pred(gt + 1, pb[0], pb[1], pb[2], pb[3]);
+      // the overlaps the assigner works with: prediction boxes (task-aligned) or anchor boxes (ATSS)
+      const double v = p.atss ? iou_gt_anchor(gt + 1, an.px, an.py, an.stride) : iou_gt_pred(gt + 1, pb[0], pb[1], pb[2], pb[3]);
       if (v > best) {
         best = v;
         gs = g;
       }
     }
-    iou = best;
+    iou = p.atss ? iou_gt_pred(p.gt + (static_cast<size_t>(b) * p.G + gs) * 5 + 1, pb[0], pb[1], pb[2], pb[3]) : best;
   } else {
     iou = iou_gt_pred(p.gt + (static_cast<size_t>(b) * p.G + gs) * 5 + 1, pb[0], pb[1], pb[2], pb[3]);
   }
@@ -458,6 +588,9 @@ __global__ void __launch_bounds__(256) tal_norm_kernel(const LossParams p) {
       const double pa = __longlong_as_double(static_cast<long long>(p.pos_align[b * p.G + gs]));
       const double po = __longlong_as_double(static_cast<long long>(p.pos_ovl[b * p.G + gs]));
       v = __ddiv_rn(__dmul_rn(p.align_a[i], po), __dadd_rn(pa, kTalEps));
+      // ATSS soft label (atss_assigner.py:82-85): IoU of the assigned box with the predicted box, multiplied IN PLACE into
+      // the fp32 one-hot, i.e. rounded to fp32
+      if (p.atss) v = static_cast<double>(static_cast<float>(p.ovl_a[i]));
       const long long lab = static_cast<long long>(p.gt[(static_cast<size_t>(b) * p.G + gs) * 5]);
       tl = lab < 0 ? 0 : static_cast<int>(lab);  // tal_assigner.py:143
     }
@@ -722,8 +855,9 @@ extern "C" int32_t mafb200_detect_loss(const float* pred_scores, const float* pr
                                        int32_t num_targets, int32_t batch, int32_t img_size, int32_t num_classes,
                                        int32_t gt_cap, const float* boxes_override, void* workspace, size_t workspace_bytes,
                                        double* scalars_out, float* grad_scores, float* grad_distri, int32_t* out_gt_idx,
-                                       uint8_t* out_fg, double* out_target_score, void* stream) {
+                                       uint8_t* out_fg, double* out_target_score, int32_t assigner, void* stream) {
   if (!pred_scores || !pred_distri || !workspace || !scalars_out) return fail(MAF_E_ARG, "detect_loss: null pointer");
+  if (assigner != MAF_ASSIGN_TAL && assigner != MAF_ASSIGN_ATSS) return fail(MAF_E_ARG, "detect_loss: assigner %d", assigner);
   if (num_targets < 0 || (num_targets > 0 && !targets)) return fail(MAF_E_ARG, "detect_loss: bad targets");
   if (batch <= 0 || batch > 65535 || num_classes <= 0 || img_size <= 0 || img_size % 32 != 0)
     return fail(MAF_E_ARG, "detect_loss: batch %d / classes %d / image size %d (must be a multiple of 32)", batch, num_classes, img_size);
@@ -774,6 +908,7 @@ extern "C" int32_t mafb200_detect_loss(const float* pred_scores, const float* pr
   p.tlabel = reinterpret_cast<int32_t*>(ws + l.tlabel);
   p.grad_scores = grad_scores;
   p.grad_distri = grad_distri;
+  p.atss = assigner == MAF_ASSIGN_ATSS;
   if (boxes_override && (reinterpret_cast<uintptr_t>(boxes_override) & 15)) return fail(MAF_E_ALIGN, "detect_loss: boxes must be 16-B aligned");
   if ((reinterpret_cast<uintptr_t>(grad_scores) | reinterpret_cast<uintptr_t>(grad_distri)) & 15)
     return fail(MAF_E_ALIGN, "detect_loss: gradients must be 16-B aligned");
@@ -801,7 +936,10 @@ extern "C" int32_t mafb200_detect_loss(const float* pred_scores, const float* pr
   if (box_blocks > 1184) box_blocks = 1184;     // 8 CTAs on each of 148 SMs
   launch_pdl(loss_targets_kernel, dim3(1), dim3(256), 0, st, p);
   if (!boxes_override) launch_pdl(loss_decode_kernel, dim3(static_cast<unsigned>((rows * 4 + 255) / 256)), dim3(256), 0, st, p);
-  launch_pdl(tal_topk_kernel, dim3(G, batch), dim3(256), topk_smem, st, p);
+  if (p.atss)
+    launch_pdl(atss_select_kernel, dim3((batch * G + 7) / 8), dim3(256), 0, st, p);
+  else
+    launch_pdl(tal_topk_kernel, dim3(G, batch), dim3(256), topk_smem, st, p);
   launch_pdl(tal_resolve_kernel, dim3((A + 255) / 256, batch), dim3(256), 0, st, p);
   launch_pdl(tal_norm_kernel, dim3(n_norm), dim3(256), 0, st, p);
   if (num_classes % 4 == 0)

@@ -11,9 +11,10 @@ its device in the reference and is ignored here; `pred_scores` [B,A,nc] are clas
 [B,A,68] DFL logits.  `targets` is the collated [T,6] tensor (image, class, cx, cy, w, h).  Like the reference the
 loss is float64 (its target tensor is float64, loss.py:165-169) and `loss_items` = (2.5 iou, 0.5 dfl, 1.0 cls), detached.
 
-Scope: the FORMAL assigner (epoch_num >= warmup_epoch).  The ATSS warm-up assigner of the first `warmup_epoch` epochs
-(yolov6/assigners/atss_assigner.py) is not implemented: such a call raises NotImplementedError unless
-`warmup_epoch=0` is passed.  There is no CPU path: tensors must live on an sm_100 GPU.
+Both assigners of the reference are implemented: ATSS (yolov6/assigners/atss_assigner.py) while `epoch_num < warmup_epoch`,
+the task-aligned assigner afterwards (loss.py:83-100).  One deviation: in the warm-up epochs the reference's class loss is
+an fp32 sum (its target scores become fp32 there); this path accumulates it in float64 like the other terms (relative
+difference ~1e-7).  There is no CPU path: tensors must live on an sm_100 GPU.
 """
 from __future__ import annotations
 
@@ -24,7 +25,7 @@ from . import _lib
 
 class _DetectLossFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, pred_scores, pred_distri, targets, img_size, num_classes, gt_cap, owner):
+    def forward(ctx, pred_scores, pred_distri, targets, img_size, num_classes, gt_cap, owner, assigner):
         ps = pred_scores.detach().float().contiguous()
         pd = pred_distri.detach().float().contiguous()
         b, a, nc = ps.shape
@@ -43,7 +44,7 @@ class _DetectLossFn(torch.autograd.Function):
             ps.data_ptr(), pd.data_ptr(), tg.data_ptr() if tg.numel() else None, tg.shape[0], b, img_size, num_classes, gt_cap,
             owner._boxes_override.data_ptr() if owner._boxes_override is not None else None, ws.data_ptr(), ws_bytes,
             scalars.data_ptr(), gs.data_ptr() if need_grad else None, gd.data_ptr() if need_grad else None,
-            gt_idx.data_ptr(), fg.data_ptr(), tscore.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+            gt_idx.data_ptr(), fg.data_ptr(), tscore.data_ptr(), assigner, torch.cuda.current_stream(dev).cuda_stream))
         owner.last = dict(scalars=scalars, target_gt_idx=gt_idx, fg_mask=fg, target_score=tscore)
         ctx.save_for_backward(gs, gd)
         ctx.in_dtypes = (pred_scores.dtype, pred_distri.dtype)
@@ -55,11 +56,11 @@ class _DetectLossFn(torch.autograd.Function):
         gs, gd = ctx.saved_tensors
         g = g_loss.to(torch.float32)
         return ((gs * g).to(ctx.in_dtypes[0]) if gs is not None else None,
-                (gd * g).to(ctx.in_dtypes[1]) if gd is not None else None, None, None, None, None, None)
+                (gd * g).to(ctx.in_dtypes[1]) if gd is not None else None, None, None, None, None, None, None)
 
 
 class ComputeLoss:
-    """Drop-in for `yolov6.models.loss.ComputeLoss` (same constructor arguments and call) on the formal-assigner branch."""
+    """Drop-in for `yolov6.models.loss.ComputeLoss` (same constructor arguments and call)."""
 
     def __init__(self, fpn_strides=(8, 16, 32), grid_cell_size=5.0, grid_cell_offset=0.5, num_classes=80, ori_img_size=640,
                  warmup_epoch=3, use_dfl=True, reg_max=16, iou_type="giou", loss_weight=None):
@@ -86,9 +87,7 @@ class ComputeLoss:
 
     def __call__(self, outputs, targets, epoch_num, step_num, gt_cap=None):
         _feats, pred_scores, pred_distri = outputs
-        if epoch_num < self.warmup_epoch:
-            raise NotImplementedError("the ATSS warm-up assigner (epoch < warmup_epoch, atss_assigner.py) is not implemented; "
-                                      "construct ComputeLoss(warmup_epoch=0) to use the task-aligned assigner from epoch 0")
+        assigner = 1 if epoch_num < self.warmup_epoch else 0  # loss.py:83: ATSS while warming up, task-aligned afterwards
         if not pred_scores.is_cuda:
             raise RuntimeError("mafb200 ComputeLoss has no CPU path: predictions must be CUDA tensors")
         if pred_scores.type() != pred_distri.type():
@@ -96,5 +95,6 @@ class ComputeLoss:
         if gt_cap is None:  # largest number of boxes in one image (one small device -> host read, as the reference's .cpu())
             t = targets.view(-1, 6)
             gt_cap = int(torch.bincount(t[:, 0].long(), minlength=1).max().item()) if t.shape[0] else 0
-        loss, scalars = _DetectLossFn.apply(pred_scores, pred_distri, targets, self.ori_img_size, self.num_classes, int(gt_cap), self)
+        loss, scalars = _DetectLossFn.apply(pred_scores, pred_distri, targets, self.ori_img_size, self.num_classes, int(gt_cap), self,
+                                            assigner)
         return loss, scalars[1:4].detach()

@@ -3,7 +3,8 @@
 Run in the build container (where /root/reference exists):  python tests/golden/make_golden_loss.py
 Runs `yolov6.models.loss.ComputeLoss` (formal assigner: epoch_num >= warmup_epoch) on the CPU — the reference hard-codes
 `.cuda()` on two parameter-free sub-modules (loss.py:52-53), which is neutralised by making `nn.Module.cuda` the identity
-for the construction — on the seeded cases of tests/_losscases.py and stores per case (tests/golden/loss_<case>.npz):
+for the construction — on the seeded cases of tests/_losscases.py, with the formal assigner (epoch 5: loss_<case>.npz) and, for
+the two cases with targets, with the ATSS warm-up assigner (epoch 0: loss_<case>_atss.npz), and stores per case:
   loss, loss_items                        float64, exactly as returned
   fg_index [F]                            flat (image * 8400 + anchor) indices of the foreground anchors
   fg_label [F], fg_box [F,4], fg_score [F] assigned class / box (pixels) / normalised target score of those anchors
@@ -35,25 +36,27 @@ def reference_loss():
         torch.nn.Module.cuda = cuda
 
 
-def run_reference(cl, scores, distri, targets):
-    """-> loss, items, assignment dict, (grad_scores, grad_distri)."""
+def run_reference(cl, scores, distri, targets, epoch=5):
+    """-> loss, items, assigner outputs, (grad_scores, grad_distri).  epoch 5: formal (task-aligned) assigner; epoch 0:
+    ATSS warm-up assigner (loss.py:83)."""
     ps = scores.clone().requires_grad_()
     pd = distri.clone().requires_grad_()
     bs = ps.shape[0]
     feats = [torch.zeros(bs, 1, 80, 80), torch.zeros(bs, 1, 40, 40), torch.zeros(bs, 1, 20, 20)]
     captured = {}
-    orig = cl.formal_assigner.forward
+    assigner = cl.formal_assigner if epoch >= cl.warmup_epoch else cl.warmup_assigner
+    orig = assigner.forward
 
     def spy(*a, **k):
         out = orig(*a, **k)
         captured["out"] = [o.clone() for o in out]
         return out
 
-    cl.formal_assigner.forward = spy
+    assigner.forward = spy
     try:
-        loss, items = cl((feats, ps, pd), targets.clone(), 5, 1)
+        loss, items = cl((feats, ps, pd), targets.clone(), epoch, 1)
     finally:
-        cl.formal_assigner.forward = orig
+        assigner.forward = orig
     if torch.isfinite(loss):
         loss.backward()
         grads = (ps.grad.clone(), pd.grad.clone())
@@ -64,14 +67,14 @@ def run_reference(cl, scores, distri, targets):
 
 def main():
     cl = reference_loss()
-    for name in _losscases.CASES:
+    for name, epoch, suffix in [(n, 5, "") for n in _losscases.CASES] + [(n, 0, "_atss") for n in ("sparse", "crowded")]:
         scores, distri, targets = _losscases.make_case(name)
-        loss, items, (t_labels, t_boxes, t_scores, fg), (gs, gd) = run_reference(cl, scores, distri, targets)
+        loss, items, (t_labels, t_boxes, t_scores, fg), (gs, gd) = run_reference(cl, scores, distri, targets, epoch)
         fg_flat = fg.reshape(-1).bool()
         idx = torch.nonzero(fg_flat).squeeze(1)
         samp = torch.randint(0, gs.numel(), (4096,), generator=torch.Generator().manual_seed(7))
         np.savez_compressed(
-            os.path.join(HERE, f"loss_{name}.npz"),
+            os.path.join(HERE, f"loss_{name}{suffix}.npz"),
             loss=np.float64(loss.item()), loss_items=items.double().numpy(),
             fg_index=idx.numpy().astype(np.int64),
             fg_label=t_labels.reshape(-1)[idx].numpy().astype(np.int64),
@@ -80,7 +83,7 @@ def main():
             grad_scores_fg=gs.reshape(-1, gs.shape[-1])[idx].numpy(), grad_distri_fg=gd.reshape(-1, gd.shape[-1])[idx].numpy(),
             sample_index=samp.numpy(), grad_scores_sample=gs.reshape(-1)[samp].numpy(),
             grad_scores_sum=np.float64(gs.double().sum().item()), grad_distri_abs_sum=np.float64(gd.double().abs().sum().item()))
-        print(name, "loss", loss.item(), "items", items.tolist(), "fg", int(idx.numel()),
+        print(name + suffix, "loss", loss.item(), "items", items.tolist(), "fg", int(idx.numel()),
               "multi-claimed anchors would show as fg with IoU-resolved boxes; T =", targets.shape[0])
 
 

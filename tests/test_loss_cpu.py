@@ -12,11 +12,11 @@ from tests import _losscases
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
 
-def _oracle_run(name):
+def _oracle_run(name, warmup=False):
     scores, distri, targets = _losscases.make_case(name)
     ps = scores.clone().requires_grad_()
     pd = distri.clone().requires_grad_()
-    loss, items, asg = ol.compute_loss(ps, pd, targets, return_assignment=True)
+    loss, items, asg = ol.compute_loss(ps, pd, targets, return_assignment=True, warmup=warmup)
     if torch.isfinite(loss):
         loss.backward()
         grads = (ps.grad, pd.grad)
@@ -26,10 +26,12 @@ def _oracle_run(name):
 
 
 @pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("warmup", [False, True])
 @pytest.mark.parametrize("name", list(_losscases.CASES))
-def test_loss_oracle_bitexact_vs_reference(name):
+def test_loss_oracle_bitexact_vs_reference(name, warmup):
     """Strongest pin: the restatement equals yolov6.models.loss.ComputeLoss bit for bit — loss, loss items, the
-    assigner's four outputs and the autograd gradients w.r.t. both head outputs."""
+    assigner's four outputs and the autograd gradients w.r.t. both head outputs — with the formal (task-aligned) assigner
+    and with the ATSS assigner of the warm-up epochs."""
     import sys
 
     sys.path.insert(0, GOLDEN)
@@ -37,8 +39,8 @@ def test_loss_oracle_bitexact_vs_reference(name):
 
     cl = mg.reference_loss()
     scores, distri, targets = _losscases.make_case(name)
-    loss_r, items_r, (t_labels, t_boxes, t_scores, fg), (gs_r, gd_r) = mg.run_reference(cl, scores, distri, targets)
-    loss_o, items_o, asg, (gs_o, gd_o) = _oracle_run(name)
+    loss_r, items_r, (t_labels, t_boxes, t_scores, fg), (gs_r, gd_r) = mg.run_reference(cl, scores, distri, targets, 0 if warmup else 5)
+    loss_o, items_o, asg, (gs_o, gd_o) = _oracle_run(name, warmup)
     # float64 whenever there is a target (the numpy-built target tensor); fp32 on the reference's no-target early return
     assert loss_r.dtype == loss_o.dtype == (torch.float64 if targets.shape[0] else torch.float32)
     assert torch.equal(loss_r, loss_o) or (torch.isinf(loss_r) and torch.isinf(loss_o))
@@ -52,12 +54,12 @@ def test_loss_oracle_bitexact_vs_reference(name):
         assert torch.equal(gs_r, gs_o) and torch.equal(gd_r, gd_o)
 
 
-@pytest.mark.parametrize("name", list(_losscases.CASES))
+@pytest.mark.parametrize("name", list(_losscases.CASES) + ["sparse_atss", "crowded_atss"])
 def test_loss_oracle_reproduces_golden(name):
     """The committed vectors (generated from the reference by tests/golden/make_golden_loss.py) from the seeds alone; this
     is the pin that travels to the GPU box.  Index sets exactly; floats to 1e-9 (another CPU's libm / vector width)."""
     gold = np.load(os.path.join(GOLDEN, f"loss_{name}.npz"))
-    loss, items, asg, (gs, gd) = _oracle_run(name)
+    loss, items, asg, (gs, gd) = _oracle_run(name.replace("_atss", ""), warmup=name.endswith("_atss"))
     if np.isinf(gold["loss"]):
         assert torch.isinf(loss) and asg["fg_mask"].sum() == 0
         return
