@@ -228,9 +228,16 @@ MAFB200_API int32_t mafb200_nms_select(const float* boxes, int32_t box_stride, i
  * runs, so one captured CUDA graph serves every threshold.  workspace: layout / size of mafb200_nms; its per-image
  * counters must be zeroed by mafb200_detect_reset (stream-ordered) before the CLS launches of a batch.
  * With the three levels' CLS + REG launches followed by mafb200_nms_select the detections equal those of the
- * pred-writing launches followed by mafb200_nms, bit for bit. */
+ * pred-writing launches followed by mafb200_nms, bit for bit.
+ *   kind MAF_HEAD_CLS_TRAIN / MAF_HEAD_REG_TRAIN: the TRAIN-form outputs of Detect_yaml.forward (`self.training or val_loss`,
+ *       yolov6/models/yolo.py:333-354) for frozen-BN (folded) weights: `pred` is then pred_scores [n, total_anchors, nc]
+ *       (sigmoid class probabilities) resp. pred_distri [n, total_anchors, 68] (raw DFL logits, side-major), fp32 from the
+ *       fp32 accumulators; `boxes` and `detect_cfg` must be NULL.  Same packed weights as CLS / REG.  These are the inputs
+ *       of mafb200_detect_loss (validation loss). */
 #define MAF_HEAD_CLS 0
 #define MAF_HEAD_REG 1
+#define MAF_HEAD_CLS_TRAIN 2
+#define MAF_HEAD_REG_TRAIN 3
 typedef struct maf_detect_cfg {
   float conf;          /* conf_thres as fp32 (torch compares in fp32) */
   float skip_below;    /* logit bound under which sigmoid(z) cannot exceed conf */

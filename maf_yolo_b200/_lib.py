@@ -99,7 +99,7 @@ _SIGNATURES = {
     "mafb200_launch_count": (C.c_int64, []),
 }
 DETECT_CFG_BYTES = 16 + 256  # sizeof(maf_detect_cfg)
-HEAD_CLS, HEAD_REG = 0, 1
+HEAD_CLS, HEAD_REG, HEAD_CLS_TRAIN, HEAD_REG_TRAIN = 0, 1, 2, 3
 
 _lib = None
 

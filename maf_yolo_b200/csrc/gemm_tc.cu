@@ -72,6 +72,8 @@ struct GemmParams {
   uint32_t idesc;
   // ---- K7: head-prediction epilogues (mafb200_head_pred; kEpi 1 = DFL box decode, 2 = class sigmoid / filter) ----
   float* pred;                 // [B, A, no] fp32 or nullptr
+  int32_t cls_off;             // first class column inside a row of `pred` (5 for the eval tensor, 0 for train-form scores)
+  int32_t raw_reg;             // kEpi 1: store the 68 raw DFL logits (train-form pred_distri) instead of decoding them
   float* boxes;                // [B, A, 4] fp32 or nullptr
   const maf_detect_cfg* cfg;   // device memory; non-null = emit NMS candidates (kEpi 2)
   int32_t* ncand;              // [B]
@@ -342,10 +344,20 @@ __device__ __forceinline__ void head_epilogue_loop(const GemmParams& p, const Ge
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[16 * s2 + i]) + s_bias[32 * half + 16 * s2 + i];
           v[16] = last[2 * half + s2];
-          dist[2 * half + s2] = dfl_side(v);
+          if (p.raw_reg) {
+            // train-form output (Detect_yaml.forward train / val_loss branch, yolo.py:333-346): reg_output flattened to
+            // [B, A, 68] = side-major, bin-minor, fp32, no softmax
+            if (row_ok) {
+              float* o = p.pred + grow * 68 + (2 * half + s2) * 17;
+#pragma unroll
+              for (int i = 0; i < 17; ++i) o[i] = v[i];
+            }
+          } else {
+            dist[2 * half + s2] = dfl_side(v);
+          }
         }
       }
-      if (row_ok) {
+      if (row_ok && !p.raw_reg) {
         const int gy = al / p.lvl_w, gx = al - gy * p.lvl_w;
         const float ax = static_cast<float>(gx) + 0.5f, ay = static_cast<float>(gy) + 0.5f;
         const float x1 = ax - dist[0], y1 = ay - dist[1], x2 = ax + dist[2], y2 = ay + dist[3];
@@ -362,7 +374,7 @@ __device__ __forceinline__ void head_epilogue_loop(const GemmParams& p, const Ge
         if (p.boxes != nullptr) *reinterpret_cast<float4*>(p.boxes + grow * 4) = make_float4(cx, cy, bw, bh);
       }
     } else {
-      float* dst = (p.pred != nullptr && row_ok) ? p.pred + grow * p.no + 5 : nullptr;
+      float* dst = (p.pred != nullptr && row_ok) ? p.pred + grow * p.no + p.cls_off : nullptr;
       const bool emit = p.cfg != nullptr && row_ok;
       const int a = p.anchor_off + al;
       float best = -INFINITY;  // single-label: best class probability so far (first maximum)
@@ -907,6 +919,11 @@ extern "C" int32_t mafb200_head_pred(const maf_tensor* src, const void* w_packed
                                      size_t workspace_bytes, void* stream) {
   if (!valid_f16_view(src) || !aligned_f16_view(src)) return fail(MAF_E_ARG, "head_pred: bad src tensor");
   if (!w_packed || !bias || (reinterpret_cast<uintptr_t>(w_packed) & 15)) return fail(MAF_E_ARG, "head_pred: bad weights");
+  const bool train_form = kind == MAF_HEAD_CLS_TRAIN || kind == MAF_HEAD_REG_TRAIN;
+  if (train_form) {
+    if (!pred || boxes || detect_cfg) return fail(MAF_E_ARG, "head_pred(train form): pred only");
+    kind = kind == MAF_HEAD_CLS_TRAIN ? MAF_HEAD_CLS : MAF_HEAD_REG;
+  }
   if (kind != MAF_HEAD_CLS && kind != MAF_HEAD_REG) return fail(MAF_E_ARG, "head_pred: kind %d", kind);
   if (nc < 1 || nc > 128) return fail(MAF_E_ARG, "head_pred: nc=%d (1..128)", nc);
   const long long L = static_cast<long long>(src->h) * src->w;
@@ -943,7 +960,9 @@ extern "C" int32_t mafb200_head_pred(const maf_tensor* src, const void* w_packed
   p.lvl_w = src->w;
   p.anchor_off = anchor_off;
   p.total_anchors = total_anchors;
-  p.no = 5 + nc;
+  p.no = train_form ? nc : 5 + nc;
+  p.cls_off = train_form ? 0 : 5;
+  p.raw_reg = train_form && kind == MAF_HEAD_REG;
   p.nc = nc;
   p.lvl_stride = stride;
   if (kind == MAF_HEAD_CLS && detect_cfg) {

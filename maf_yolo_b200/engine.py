@@ -383,6 +383,7 @@ class Engine:
         self.n_streams = max(1, n_streams) if use_cuda_graph else 1
         if reuse_buffers is None:
             reuse_buffers = self.n_streams == 1
+        self.reuse_buffers = reuse_buffers
         with torch.cuda.device(self.device):
             nbytes = self.plan.assign_offsets(batch, reuse=reuse_buffers)
             self.arena = torch.zeros(nbytes // 2, dtype=torch.float16, device=self.device)  # padding channels finite
@@ -414,6 +415,7 @@ class Engine:
         self._detect_filters: Dict[Tuple[int, ...], torch.Tensor] = {}
         self.boxes: Optional[List[torch.Tensor]] = None
         self.nms_ws: Optional[List[torch.Tensor]] = None
+        self.train_out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None  # (pred_scores, pred_distri), mode "train"
         # K7 detect mode: thresholds / class filter live in a small DEVICE struct the cls_pred epilogues read when they
         # run, so one captured graph serves every (conf_thres, multi_label, classes); host copies are immutable, cached
         self.detect_cfg_dev: Optional[torch.Tensor] = None
@@ -510,7 +512,7 @@ class Engine:
             return lambda: ops.upsample2x(reads[0], writes[0])
         if op.kind == "detect_reset":
             def reset():
-                if self._detect is not None:
+                if self._detect is not None and self._detect != "train":
                     ops.detect_reset(self.nms_ws[self.last_index], self.batch)
 
             return reset
@@ -525,7 +527,10 @@ class Engine:
             self._weights[op.name] = (w, b)
 
             def head_pred():
-                if self._detect is None:
+                if self._detect == "train":  # train-form outputs (yolo.py:333-354) for the validation loss
+                    ops.head_pred(reads[0], w, b, op.act + "_train", op.anchor_off, total, stride, nc,
+                                  pred=self.train_out[0 if op.act == "cls" else 1])
+                elif self._detect is None:
                     ops.head_pred(reads[0], w, b, op.act, op.anchor_off, total, stride, nc, pred=self.pred)
                 elif op.act == "cls":
                     ops.head_pred(reads[0], w, b, "cls", op.anchor_off, total, stride, nc, detect_cfg=self.detect_cfg_dev,
@@ -657,6 +662,15 @@ class Engine:
         self._detect = detect
         if detect is None:
             return
+        if detect == "train":
+            if not self.plan.k7:
+                raise RuntimeError("train-form outputs need the K7 plan (MAFB200_K7=1, return_featmaps=False)")
+            if self.train_out is None:
+                with torch.cuda.device(self.device):
+                    a = self.plan.anchors
+                    self.train_out = (torch.empty((self.batch, a, self.graph.nc), dtype=torch.float32, device=self.device),
+                                      torch.empty((self.batch, a, 68), dtype=torch.float32, device=self.device))
+            return
         if self.boxes is None:
             with torch.cuda.device(self.device):
                 a, nc = self.plan.anchors, self.graph.nc
@@ -684,7 +698,7 @@ class Engine:
     def _upload_detect_cfg(self) -> None:
         """K7 detect mode: stream-ordered copy of the configuration struct (only when it changed).  Called after the
         waits that order this forward behind the previous one, so no launch in flight still reads the old values."""
-        if self._detect is not None and self.plan.k7 and self._detect_cfg_current != self._detect:
+        if self._detect is not None and self._detect != "train" and self.plan.k7 and self._detect_cfg_current != self._detect:
             self.detect_cfg_dev.copy_(self._detect_cfg_host[self._detect], non_blocking=True)
             self._detect_cfg_current = self._detect
 
@@ -692,7 +706,7 @@ class Engine:
         """Captured graphs: per prediction buffer and — K7 — per MODE only (thresholds are read from device memory);
         without K7 the thresholds are launch arguments, so per configuration, bounded to the 8 most recent."""
         if self.plan.k7:
-            return (k, detect is not None)
+            return (k, "train" if detect == "train" else detect is not None)
         key = (k, detect)
         if key not in self._graphs and len(self._graphs) >= 8:
             self._graphs.pop(next(iter(self._graphs)))
@@ -704,7 +718,7 @@ class Engine:
         self._set_detect(detect)
         if not self.use_cuda_graph:
             self.run_eager(x)
-            return self.pred if detect is None else self.boxes[self.last_index]
+            return self._result(detect, self.last_index)
         x = self._check_input(x)
         self._x = x
         k = self._flip
@@ -728,7 +742,7 @@ class Engine:
         full = self._full_graphs.get(fkey)
         if full is not None:
             full.replay()
-            return self.pred if detect is None else self.boxes[k]
+            return self._result(detect, k)
         if gkey not in self._graphs:
             self._calls[0]()
             for call in self._calls[1:]:  # warm-up outside capture (sets func attributes, loads modules)
@@ -760,10 +774,15 @@ class Engine:
                 self._ptr_seen.clear()
             self._full_graphs[fkey] = g
             g.replay()
-            return self.pred if detect is None else self.boxes[k]
+            return self._result(detect, k)
         self._calls[0]()
         self._graphs[gkey].replay()
-        return self.pred if detect is None else self.boxes[k]
+        return self._result(detect, k)
+
+    def _result(self, detect, k: int):
+        if detect is None:
+            return self.pred
+        return self.train_out if detect == "train" else self.boxes[k]
 
     __call__ = forward
 

@@ -86,6 +86,9 @@ class B200DetectModel(torch.nn.Module):
     forward(x, val_loss=False) -> [pred, featmaps]:  pred is the `[B, A, 5+nc]` fp32 tensor of
     Detect_yaml's eval branch (yolo.py:355-396); featmaps — unused by every caller
     (yolov6/core/evaler.py:168, yolov6/layers/common.py:368) — is [] unless `return_featmaps`.
+    forward(x, val_loss=True) -> [(feats, pred_scores [B,A,nc], pred_distri [B,A,68]), []]: the train-form outputs of
+    Detect_yaml (yolo.py:333-354) with frozen BN — the input of `maf_yolo_b200.loss.ComputeLoss` (validation loss).
+    `.train()` raises: batch-stat BN and the backward pass are not built.
     Keeps the attributes callers read: `stride`, `nc`, `names` (evaler.py:94,151,246).
     `.half()` / `.float()` (evaler.py:112) are accepted and change nothing: the compute type is
     fixed (fp16 operands, fp32 accumulate) and the output is fp32, as the reference's is.
@@ -144,11 +147,21 @@ class B200DetectModel(torch.nn.Module):
 
     @torch.no_grad()
     def forward(self, x: torch.Tensor, val_loss: bool = False):
-        if val_loss:
-            raise NotImplementedError("val_loss=True is the training-time branch (yolo.py:333-354); inference only here")
         if not x.is_cuda:
             raise RuntimeError("B200DetectModel needs a CUDA input tensor: there is no CPU fallback on this path")
         eng = self.engine_for(x)
+        if val_loss:
+            # Detect_yaml.forward's `self.training or val_loss` branch (yolo.py:333-354) in eval mode (BN frozen = the folded
+            # weights): (feats, pred_scores [B,A,nc] probabilities, pred_distri [B,A,68] DFL logits) — what ComputeLoss takes
+            # (the trainer's validation loss).  The two tensors come from the cls_pred / reg_pred GEMM epilogues in fp32.
+            with torch.cuda.device(x.device):
+                scores, distri = eng.forward(x, detect="train")
+                scores, distri = scores.clone(), distri.clone()
+                if eng.reuse_buffers:  # the level stems' arena ranges may have been handed to later layers
+                    feats = [torch.zeros((x.shape[0], lv[0].c, lv[0].buf.h, lv[0].buf.w), device=x.device) for lv in eng.plan.level_views]
+                else:
+                    feats = [eng.view(lv[0]).to_nchw() for lv in eng.plan.level_views]  # Head_DepthUni's `x` = stem output
+            return [(feats, scores, distri), []]
         with torch.cuda.device(x.device):
             pred = eng.forward(x)
             if not self.borrow_output:

@@ -208,9 +208,11 @@ def detect_reset(workspace: torch.Tensor, batch: int) -> None:
 def head_pred(src: NHWC, w_packed: torch.Tensor, bias: torch.Tensor, kind: str, anchor_off: int, total_anchors: int,
               stride: float, nc: int, pred: Optional[torch.Tensor] = None, boxes: Optional[torch.Tensor] = None,
               detect_cfg: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None) -> None:
-    """K7: cls_pred / reg_pred 1x1 conv of one level with sigmoid / DFL decode / candidate filter in the epilogue."""
+    """K7: cls_pred / reg_pred 1x1 conv of one level with sigmoid / DFL decode / candidate filter in the epilogue;
+    kind "cls_train" / "reg_train": the train-form outputs (pred = pred_scores [B,A,nc] / pred_distri [B,A,68])."""
+    kinds = {"cls": _lib.HEAD_CLS, "reg": _lib.HEAD_REG, "cls_train": _lib.HEAD_CLS_TRAIN, "reg_train": _lib.HEAD_REG_TRAIN}
     check(lib().mafb200_head_pred(src.ref(), w_packed.data_ptr(), bias.data_ptr(),
-                                  _lib.HEAD_CLS if kind == "cls" else _lib.HEAD_REG, anchor_off, total_anchors,
+                                  kinds[kind], anchor_off, total_anchors,
                                   float(stride), nc, pred.data_ptr() if pred is not None else None,
                                   boxes.data_ptr() if boxes is not None else None,
                                   detect_cfg.data_ptr() if detect_cfg is not None else None,

@@ -365,12 +365,65 @@ def test_api_contract(cuda_device):
     assert model.eval() is model and model.half() is model and model.float() is model
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         model(x)  # CPU tensor
-    with pytest.raises(NotImplementedError):
-        model(x.to(cuda_device), val_loss=True)
     with pytest.raises(RuntimeError):
         model.train()
     with pytest.raises(AssertionError, match="conf_thresh must be in 0.0 to 1.0"):
         mb.non_max_suppression(torch.zeros(1, 10, 85, device=cuda_device), conf_thres=1.5)
+
+
+def _train_form_reference(spec, sd, x):
+    """Oracle forward without the eval decode -> (feats, pred_scores [B,A,nc], pred_distri [B,A,68]) as Detect_yaml's
+    train / val_loss branch returns them (yolo.py:333-354)."""
+    from oracle import model as om
+
+    outs = om.forward_train_form(spec, sd, x, decode=False)
+    scores = torch.cat([o[1].flatten(2).permute(0, 2, 1) for o in outs], 1)
+    distri = torch.cat([o[2].flatten(2).permute(0, 2, 1) for o in outs], 1)
+    return [o[0] for o in outs], scores, distri
+
+
+@pytest.mark.parametrize("variant", ["n", "s"])
+def test_val_loss_branch_and_validation_loss(cuda_device, variant):
+    """`model(x, val_loss=True)` — Detect_yaml's train-form outputs with frozen BN — against the oracle, and the validation
+    loss of the reference's trainer end to end on this library: our forward -> our ComputeLoss vs oracle forward -> oracle
+    loss.  (Conditioned weights: the signal reaches the heads.)"""
+    import maf_yolo_b200 as mb
+    from maf_yolo_b200.loss import ComputeLoss
+    from oracle import loss as ol
+    from tests import _cond, _losscases
+
+    fx = _cond.load_fixture(variant, "strict")
+    g, sd, x = _cond.fixture_inputs(variant, fx)
+    from oracle import model as om
+
+    spec = om.parse_model(om.variant_rows(variant))
+    x = torch.cat([x, x.flip(3)], 0)  # two images
+    feats_r, scores_r, distri_r = _train_form_reference(spec, sd, x)
+    model = mb.from_state_dict(sd, variant)
+    (feats, scores, distri), fm = model(x.to(cuda_device), val_loss=True)
+    torch.cuda.synchronize()
+    assert fm == [] and scores.shape == (2, 8400, 80) and distri.shape == (2, 8400, 68) and scores.dtype == torch.float32
+    assert [tuple(f.shape) for f in feats] == [tuple(f.shape) for f in feats_r]
+    e_s = (scores.cpu() - scores_r).abs().max().item()
+    e_d = (distri.cpu() - distri_r).abs().max().item() / distri_r.abs().max().item()
+    e_f = max(((f.cpu() - r).abs().max() / r.abs().max()).item() for f, r in zip(feats, feats_r))
+    print(f"PARITY val_loss branch {variant}: pred_scores max abs {e_s:.2e}, pred_distri max abs / max |ref| {e_d:.2e}, feats {e_f:.2e}")
+    assert e_s <= 2e-2 and e_d <= 1e-2 and e_f <= 2e-2
+    # a second call returns fresh tensors (the reference's contract) with the same values
+    (_, s2, d2), _ = model(x.to(cuda_device), val_loss=True)
+    assert s2.data_ptr() != scores.data_ptr() and torch.equal(s2, scores) and torch.equal(d2, distri)
+    # the eval branch still works on the same model / engine afterwards
+    pred = model(x.to(cuda_device))[0]
+    assert pred.shape == (2, 8400, 85)
+    # validation loss end to end
+    _, _, targets = _losscases.make_case("sparse")
+    targets = targets[targets[:, 0] < 2]
+    crit = ComputeLoss(warmup_epoch=0)
+    loss, items = crit((feats, scores, distri), targets.to(cuda_device), 0, 0)
+    loss_r, items_r = ol.compute_loss(scores_r, distri_r, targets)
+    rel = abs(loss.item() - loss_r.item()) / abs(loss_r.item())
+    print(f"PARITY validation loss {variant}: {loss.item():.6f} vs oracle {loss_r.item():.6f} (rel {rel:.2e}); items {items.tolist()} vs {items_r.tolist()}")
+    assert rel <= 2e-2
 
 
 def test_second_device_in_the_same_process(cuda_device):

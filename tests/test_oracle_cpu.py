@@ -119,6 +119,24 @@ def test_oracle_bitexact_vs_reference_modules():
             assert np.array_equal(r.numpy(), o)
 
 
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present (GPU box)")
+def test_oracle_train_form_outputs_vs_reference():
+    """`Model.forward(x, val_loss=True)` in eval mode (yolo.py:333-354): (feats, cls_score_list, reg_distri_list) — the
+    oracle's undecoded forward, flattened the same way, bit for bit."""
+    g = topology.build_graph("n")
+    sd = synth.random_state_dict(g, seed=3)
+    m = ref_loader.build_model("n")
+    m.load_state_dict(sd, strict=True)
+    x = synthetic_image(1, seed=5)
+    with torch.no_grad():
+        (feats, scores, distri), _ = m(x, val_loss=True)
+    spec = om.parse_model(om.variant_rows("n"))
+    outs = om.forward_train_form(spec, sd, x, decode=False)
+    assert torch.equal(scores, torch.cat([o[1].flatten(2).permute(0, 2, 1) for o in outs], 1))
+    assert torch.equal(distri, torch.cat([o[2].flatten(2).permute(0, 2, 1) for o in outs], 1))
+    assert all(torch.equal(a, o[0]) for a, o in zip(feats, outs))
+
+
 @pytest.mark.parametrize("variant", ["n", "s", "m"])
 @pytest.mark.parametrize("kind", ["strict", "rich"])
 def test_oracle_reproduces_conditioned_fixtures(variant, kind):
