@@ -407,7 +407,9 @@ def run_ours(a):
     host_u8 = [torch.randint(0, 256, (B, 3, 640, 640), generator=gen, dtype=torch.uint8).pin_memory() for _ in range(2)]
     # device-resident fp32 inputs (two, rotated; 157 MB each at B=32 — larger than the 126 MB L2)
     x_f32 = [(h.to(dev).float() / 255).contiguous() for h in host_u8]
-    n_in = 2 * in_flight  # device input buffers of the e2e path: in_flight being read + as many being filled
+    # device input buffers of the e2e path: in_flight being read + the copies running `lookahead` steps ahead + slack
+    lookahead = in_flight
+    n_in = 2 * in_flight + lookahead
     x_u8 = [torch.empty_like(host_u8[0], device=dev) for _ in range(n_in)]
     det = torch.empty((B, EVAL_NMS["max_det"], 6), dtype=torch.float32, device=dev)
     cnt = torch.empty((B,), dtype=torch.int32, device=dev)
@@ -536,20 +538,41 @@ def run_ours(a):
         det_host[j].copy_(d[:B] if world == 1 else d[rank * B:(rank + 1) * B], non_blocking=True)
         cnt_host[j].copy_(c[:B] if world == 1 else c[rank * B:(rank + 1) * B], non_blocking=True)
 
-    def e2e_step(i):
-        k = i % n_in
+    # Input staging runs `lookahead` steps ahead of the compute, as a serving loop's loader does: step i enqueues the H2D
+    # copy of batch i + lookahead and computes batch i.  (Issued in the same call, the copy of batch i landed too late to keep
+    # both engine replicas busy: 18.5k vs 19.3k images/s, tools/exp_e2e.py.)  One H2D copy and one D2H read per step either
+    # way; the `lookahead` copies in flight when the timed region opens are balanced by those still in flight when it closes.
+    e2e_n = [0]
+
+    def issue_copy(m):
+        k = m % n_in
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[k])
-            x_u8[k].copy_(host_u8[i % 2], non_blocking=True)
+            x_u8[k].copy_(host_u8[m % 2], non_blocking=True)
             ready[k].record(copy_stream)
+
+    for m in range(lookahead):
+        issue_copy(m)
+
+    def e2e_step(_i):
+        i = e2e_n[0]
+        e2e_n[0] += 1
+        issue_copy(i + lookahead)
+        k = i % n_in
         main_stream.wait_event(ready[k])
         t = step(x_u8[k], after=d2h)
         if pipelined:
             consumed[k] = t.consumed  # fires when the forward (the only reader of x_u8[k]) has run
         else:
+            consumed[k] = torch.cuda.Event()
             consumed[k].record(main_stream)
 
-    for i in range(max(3 * n_in, a.warmup)):  # every (engine replica, buffer, input address) combination at least twice
+    # warm-up: every (engine replica, prediction buffer, input address) combination at least twice — the whole-forward graph
+    # of a combination is captured the second time it is seen, and a capture inside the timed region costs milliseconds
+    import math
+
+    cycle = n_in * (2 * in_flight) // math.gcd(n_in, 2 * in_flight)
+    for i in range(max(2 * cycle + n_in, a.warmup)):
         e2e_step(i)
     ms_e2e = timed(e2e_step, a.steps)
     e2e_value = B * world * a.steps / (ms_e2e / 1e3)
@@ -656,7 +679,8 @@ def run_ours(a):
                                 "streams, each batch's NMS runs on a side stream (double-buffered predictions); every "
                                 "step's forward+decode+NMS completes inside the timed region") if pipelined else "sequential"},
         "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_bytes,
-                "ms_per_step": round(ms_e2e / a.steps, 4), "input": "pinned uint8 NCHW (the dataloader's dtype)"},
+                "ms_per_step": round(ms_e2e / a.steps, 4), "input": "pinned uint8 NCHW (the dataloader's dtype)",
+                "staging": f"H2D copies enqueued {lookahead} steps ahead of their compute ({n_in} device input buffers)"},
         "gpu_launches": per_step_launches * a.steps, "gpu_launches_per_step": per_step_launches,
         "eager_api_launches_in_timed_region": int(counted),
         "breakdown_ms": {"forward_decode": round(ms_fwd / a.steps, 4), "nms": round(ms_nms / a.steps, 4)},

@@ -18,9 +18,8 @@
 
 namespace mafb200 {
 
-// `lut` (shared memory, 256 floats = u / 255.0f computed once per CTA with the fp32 division the reference
-// performs, evaler.py:163) is only read by the uint8 specialisations: one LDS instead of an IEEE division
-// (~10 instructions) per input element — the uint8 path was 0.1 ms per forward slower than fp32 without it.
+// (Round 1 read u / 255.0f from a 256-entry shared-memory table `lut`; round 2 multiplies — see Raw<uint8_t>::cvt.  The
+// parameter stays in the signature of cvt() so that the three specialisations read alike.)
 // Raw loads and their conversion are separate so that ALL loads of a tile can be issued before the first use (and a
 // whole tile ahead, see the kernel): Raw<T>::px = one pixel, Raw<T>::pair = the aligned pixel pair (2*ox, 2*ox+1).
 template <typename T>
@@ -55,8 +54,18 @@ struct Raw<uint8_t> {
   static __device__ __forceinline__ pair zero_pair() { return make_uchar2(0, 0); }
   static __device__ __forceinline__ px ld_px(const uint8_t* p) { return __ldg(p); }
   static __device__ __forceinline__ pair ld_pair(const uint8_t* p) { return __ldg(reinterpret_cast<const uchar2*>(p)); }
-  static __device__ __forceinline__ float cvt(px v, const float* lut) { return lut[v]; }
-  static __device__ __forceinline__ float2 cvt(pair v, const float* lut) { return make_float2(lut[v.x], lut[v.y]); }
+  // u * (1 / 255) in fp32 differs from the reference's u / 255 (evaler.py:163) in the last bit for 126 of the 256 values,
+  // but the value is rounded to fp16 for the tensor core right away and THAT is identical for all 256
+  // (tests/test_host_cpu.py::test_u8_scale_is_exact_in_fp16).  Two instructions per element; the 256-entry table it
+  // replaces cost one shared-memory load with ~3-way bank conflicts per element (uint8 input was 4 % slower than fp32).
+  // float(u) without the quarter-rate I2F: 0x4B000000 | u is the float 2^23 + u, and fma(2^23 + u, r, -2^23 r) = fl(u r)
+  // exactly (-2^23 r is a power-of-two multiple of r, so the only rounding is that of u r): one LOP + one FFMA per element.
+  static __device__ __forceinline__ float scale(uint32_t u) {
+    constexpr float r = 1.0f / 255.0f;
+    return fmaf(__uint_as_float(0x4B000000u | u), r, -8388608.0f * r);
+  }
+  static __device__ __forceinline__ float cvt(px v, const float*) { return scale(v); }
+  static __device__ __forceinline__ float2 cvt(pair v, const float*) { return make_float2(scale(v.x), scale(v.y)); }
 };
 
 constexpr int kStemK = 32;                 // 27 taps padded to 2 x UMMA_K

@@ -263,3 +263,17 @@ def test_convert_blocks_surgery_on_reference_model():
     m.float()  # reference Model._apply touches detect.stride / detect.grid (yolo.py:211-215)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(torch.zeros(1, 3, 64, 64))
+
+
+def test_u8_scale_is_exact_in_fp16():
+    """The stem kernel turns a uint8 pixel into the fp16 operand of its MMA as fp16(u * (1/255)) — two instructions —
+    where the reference computes u / 255 in fp32 (evaler.py:163) before the model's first conv sees it.  The fp32
+    products differ from the quotients in the last bit for about half of the values; after the rounding to fp16 all 256
+    are identical, which is what makes the shortcut bit-exact for the path."""
+    import numpy as np
+
+    u = np.arange(256, dtype=np.float32)
+    quotient = u / np.float32(255)
+    product = u * (np.float32(1.0) / np.float32(255))
+    assert (quotient != product).sum() > 100
+    assert np.array_equal(quotient.astype(np.float16), product.astype(np.float16))

@@ -175,6 +175,13 @@ def test_stem_conv(cuda_device, dtype, cout):
     ops.stem_conv3x3s2(x.to(cuda_device), wp, bp, "relu", dst)
     torch.cuda.synchronize()
     _close(dst.to_nchw(), ref, f"stem conv {dtype} cout={cout}")
+    if dtype == torch.uint8:
+        # raw uint8 input == the reference's `imgs.float() / 255` fed as fp32, bit for bit (the /255 folded into the kernel
+        # is a multiplication whose fp16 rounding equals the division's for all 256 values)
+        dst2 = ops.NHWC.empty(n, h // 2, w // 2, cout, cuda_device)
+        ops.stem_conv3x3s2(xf.to(cuda_device), wp, bp, "relu", dst2)
+        torch.cuda.synchronize()
+        assert torch.equal(dst.to_nchw(), dst2.to_nchw())
 
 
 DW_CASES = [(72, 3, 40, 40, 2, "silu"), (144, 5, 40, 40, 1, "silu"), (288, 7, 40, 40, 1, "silu"),
