@@ -150,23 +150,30 @@ __global__ void __launch_bounds__(128, 8) stem_conv_kernel(const T* __restrict__
   typename Raw<T>::pair pr[9];
   typename Raw<T>::px lf[9];
   bool from_lane = false;
+  // Index arithmetic in 32 bits with ONE 64-bit base per tile (ncu: the kernel is issue-bound — issue slots 68-70 % busy,
+  // 577 warp instructions per output pixel of which ~40 % were 64-bit address arithmetic, predicates and selects): the
+  // nine (ky, ci) rows of a pixel are base + ky * w + ci * h * w elements, offsets that fit 32 bits inside one image.
+  const uint32_t hw = static_cast<uint32_t>(h) * static_cast<uint32_t>(w);
   auto issue_loads = [&](long long tile) {
     const long long idx = tile * 128 + t;
     const uint32_t cidx = static_cast<uint32_t>(idx < total ? idx : total - 1);  // total < 2^31 (checked by the host)
     const uint32_t row = cidx / static_cast<uint32_t>(wo);                       // 32-bit divisions: 3x fewer instructions
     const int ox = static_cast<int>(cidx - row * static_cast<uint32_t>(wo));
-    const int b = static_cast<int>(row / static_cast<uint32_t>(ho));
-    const int oy = static_cast<int>(row - static_cast<uint32_t>(b) * static_cast<uint32_t>(ho));
+    const uint32_t b = row / static_cast<uint32_t>(ho);
+    const int oy = static_cast<int>(row - b * static_cast<uint32_t>(ho));
     from_lane = lane > 0 && ox > 0;  // lane-1 then holds output pixel ox-1 of the same row
     const bool need_left = lane == 0 && ox > 0;  // ox == 0: the tap is padding
-    const T* xb = x + static_cast<size_t>(b) * 3 * h * w;
+    // rows 2*oy-1, 2*oy, 2*oy+1: only the first can be above the image (oy == 0), only the last below it (h is even)
+    const T* base = x + static_cast<size_t>(b) * (3u * hw) + (static_cast<uint32_t>(2 * oy) * static_cast<uint32_t>(w) + 2u * ox);
+    const bool top_ok = oy > 0;
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
-      const int iy = 2 * oy + ky - 1;
-      const bool row_ok = iy >= 0 && iy < h;
+      const bool row_ok = ky != 0 || top_ok;
 #pragma unroll
       for (int ci = 0; ci < 3; ++ci) {
-        const T* rowp = xb + (static_cast<size_t>(ci) * h + (row_ok ? iy : 0)) * w + 2 * ox;
+        // (ky - 1) * w + ci * hw relative to the pixel pair of the centre row; a masked-off row reads the centre row's address
+        const int off = (row_ok ? (ky - 1) * w : 0) + static_cast<int>(ci * hw);
+        const T* rowp = base + off;
         pr[ky * 3 + ci] = row_ok ? Raw<T>::ld_pair(rowp) : Raw<T>::zero_pair();
         lf[ky * 3 + ci] = (row_ok && need_left) ? Raw<T>::ld_px(rowp - 1) : Raw<T>::zero_px();
       }
