@@ -11,7 +11,7 @@
 // One CTA = one 10 x 20 output tile of one image, ALL channels; 256 threads = 8 warps, each warp one 5 x 5 pixel unit
 // with lane = channel pair (the FFMA loop of dwconv.cu at CB = 64).  Per 64-channel block:
 //   TMA halo tile (14 x 24 x 64 ch, OOB zero fill = padding)  ->  25 x 25 packed FFMA2 per thread  ->  bias + act1  ->
-//   fp16 pairs written by hand into the SWIZZLE_128B K-major A tile (row = pixel 0..199 of the tile, 16-byte chunk
+//   fp16 pairs written by hand into the SWIZZLE_128B K-major A tile (row = 25 * warp + pixel of the warp's unit, 16-byte chunk
 //   index ^ (row & 7): a warp writes the 128 bytes of ONE row per instruction, conflict free)  ->  fence.proxy.async  ->
 //   one thread issues 2 M tiles x 4 tcgen05.mma (128 x N x 16) against that block's slice of W2 (it arrives with the
 //   halo tile, two slots), accumulating over the channel blocks in TMEM.
@@ -161,16 +161,36 @@ __global__ void __launch_bounds__(FwTile<kFwTX, kFwTY>::kThreads, kCtas) dwpw_ke
       tma_load_tile_4d(s_in, &p.tm_in, bar_in, c0 + kFwCB, x0 - P, y0 - P, img);
     }
 
-    // bias is already in the accumulator; act1, fp16, SW128 K-major A tile: row = pixel, 4 bytes per lane
+    // bias is already in the accumulator; act1, fp16, SW128 K-major A tile, 4 bytes per lane.  A-tile ROW of a pixel =
+    // warp * 25 + (i * 5 + r): any bijection works as long as the epilogue reads the same one, and with this one the swizzle
+    // phase (row & 7) = ((i * 5 + r) + warp * 25) & 7 takes one of 8 values that depend on the compile-time (i, r) and on the
+    // warp only — the 8 chunk addresses are computed once per thread and every store is base + immediate (was ~5 address
+    // instructions per pixel in a kernel that is issue-bound for k = 3: ncu issue slots 67 % busy).
+    // Lanes beyond C hold zero weights and a zero bias, so their accumulators are exactly 0 and act1(0) = 0 needs no select.
+    {
+      const int row0 = warp * 25;
+      uint8_t* wbase = s_a + row0 * 128 + ((lane & 3) << 2);
+      uint8_t* pre[8];
 #pragma unroll
-    for (int i = 0; i < 5; ++i)
+      for (int k7 = 0; k7 < 8; ++k7) pre[k7] = wbase + (((lane >> 2) ^ ((k7 + row0) & 7)) << 4);
+      auto write_tile = [&](auto act_c) {  // the activation is a compile-time constant inside: no switch per element
+        constexpr int kAct = decltype(act_c)::value;
 #pragma unroll
-      for (int r = 0; r < 5; ++r) {
-        const int prow = (oy0 + i) * kFwTX + ox0 + r;
-        const float a = apply_act_fast(acc[i][r].x, p.act1), c = apply_act_fast(acc[i][r].y, p.act1);
-        *reinterpret_cast<uint32_t*>(s_a + prow * 128 + ((((lane >> 2) ^ (prow & 7)) << 4) | ((lane & 3) << 2))) =
-            ch_ok ? pack_half2(a, c) : 0u;
-      }
+        for (int i = 0; i < 5; ++i)
+#pragma unroll
+          for (int r = 0; r < 5; ++r) {
+            const int c = i * 5 + r;  // compile-time after unrolling
+            const float a = apply_act_fast(acc[i][r].x, kAct), b2 = apply_act_fast(acc[i][r].y, kAct);
+            *reinterpret_cast<uint32_t*>(pre[c & 7] + c * 128) = pack_half2(a, b2);
+          }
+      };
+      if (p.act1 == ACT_SILU)
+        write_tile(std::integral_constant<int, ACT_SILU>{});
+      else if (p.act1 == ACT_RELU)
+        write_tile(std::integral_constant<int, ACT_RELU>{});
+      else
+        write_tile(std::integral_constant<int, ACT_NONE>{});
+    }
     fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core
     tc_fence_before_sync();
     __syncthreads();
@@ -193,10 +213,12 @@ __global__ void __launch_bounds__(FwTile<kFwTX, kFwTY>::kThreads, kCtas) dwpw_ke
   tc_fence_after_sync();
   {
     const int mt = warp >> 2, quarter = warp & 3;
-    const int prow = mt * 128 + quarter * 32 + lane;
-    const int py = prow / kFwTX, px = prow - py * kFwTX;
+    // accumulator row R = unit (R / 25) pixel (R % 25) (see the A-tile write): unit u sits at (u / (TX / 5), u % (TX / 5))
+    const int R = mt * 128 + quarter * 32 + lane;
+    const int unit = R / 25, c = R - unit * 25;
+    const int py = (unit / (kFwTX / 5)) * 5 + c / 5, px = (unit % (kFwTX / 5)) * 5 + c % 5;
     const int gy = y0 + py, gx = x0 + px;
-    const bool ok = prow < kFwTX * kFwTY && gy < p.H && gx < p.W;
+    const bool ok = R < kFwTX * kFwTY && gy < p.H && gx < p.W;
     __half* orow = p.out + ((static_cast<size_t>(img) * p.H + (ok ? gy : 0)) * p.W + (ok ? gx : 0)) * p.out_ld;
     const uint32_t taddr = tmem_base + mt * p.tile_n + (static_cast<uint32_t>(quarter * 32) << 16);
 #pragma unroll 1
