@@ -139,3 +139,40 @@ def test_no_cpu_path(cuda_device):
     scores, distri, targets = _losscases.make_case("sparse")
     with pytest.raises(RuntimeError):  # no CPU path
         ComputeLoss(warmup_epoch=0)((None, scores, distri), targets, 0, 0)
+
+
+@pytest.mark.parametrize("img,nc,warmup", [(320, 80, False), (640, 3, False), (320, 6, True), (64, 80, False)])
+def test_other_image_sizes_and_class_counts(cuda_device, img, nc, warmup):
+    """Image sizes other than 640 (anchor grid derived from the size), class counts that are not a multiple of 4 (the
+    scalar varifocal path) and a tiny pyramid (64 px: 8 x 8 + 4 x 4 + 2 x 2 anchors, fewer than 9 cells on a level for the
+    ATSS window) against the oracle run live."""
+    from maf_yolo_b200.loss import ComputeLoss
+
+    g = torch.Generator().manual_seed(100 + img + nc)
+    a = (img // 8) ** 2 + (img // 16) ** 2 + (img // 32) ** 2
+    bs = 2
+    scores = torch.sigmoid(torch.randn(bs, a, nc, generator=g) * 1.5 - 2.0)
+    distri = torch.randn(bs, a, 68, generator=g)
+    rows = []
+    for b in range(bs):
+        for _ in range(4):
+            cx, cy = (0.2 + 0.6 * torch.rand(2, generator=g)).tolist()
+            w, h = (0.2 + 0.5 * torch.rand(2, generator=g)).tolist()
+            rows.append([float(b), float(int(torch.randint(0, nc, (1,), generator=g))), cx, cy, w, h])
+    targets = torch.tensor(rows, dtype=torch.float32)
+    ps, pd = scores.clone().requires_grad_(), distri.clone().requires_grad_()
+    lo, io, asg = ol.compute_loss(ps, pd, targets, img_size=img, num_classes=nc, return_assignment=True, warmup=warmup)
+    lo.backward()
+    crit = ComputeLoss(num_classes=nc, ori_img_size=img, warmup_epoch=3 if warmup else 0)
+    cs, cd = scores.to(cuda_device).requires_grad_(), distri.to(cuda_device).requires_grad_()
+    loss, items = crit((None, cs, cd), targets.to(cuda_device), 0, 0)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert torch.equal(crit.last["fg_mask"].cpu().bool(), asg["fg_mask"]), (int(crit.last["fg_mask"].sum()), int(asg["fg_mask"].sum()))
+    f = asg["fg_mask"]
+    assert int(f.sum()) > 0
+    assert torch.equal(crit.last["target_gt_idx"].cpu().long()[f], asg["target_gt_idx"][f])
+    np.testing.assert_allclose(loss.item(), lo.item(), rtol=2e-5)
+    np.testing.assert_allclose(items.cpu().numpy(), io.double().numpy(), rtol=2e-5)
+    assert (cs.grad.cpu() - ps.grad).abs().max() / ps.grad.abs().max() < 2e-4
+    assert (cd.grad.cpu() - pd.grad).abs().max() / pd.grad.abs().max() < 2e-4
