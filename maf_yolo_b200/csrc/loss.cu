@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(256) loss_targets_kernel(const LossParams p) {
   __syncthreads();
   const double scale = static_cast<double>(p.img);
   __shared__ int16_t s_img[4096];  // image index of every row (the slot count below is O(T^2) reads)
-  const bool staged = p.T <= 4096;
+  const bool staged = p.T <= 4096 && p.B <= 32767;  // int16 image indices
   if (staged)
     for (int t = threadIdx.x; t < p.T; t += blockDim.x) {
       const int b = static_cast<int>(p.targets[static_cast<size_t>(t) * 6]);
